@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by EXECUTING the reference's own pure-Python
+oracles (nothing is copied; the reference files are loaded from where they lie).
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+
+Reference code executed:
+  vllm/_custom_ops.py:774-931   ref_schedule_cache_evictions      (K1 + K2)
+  vllm/_custom_ops.py:1022-1062 ref_count_block_evictions         (K3)
+  vllm/_custom_ops.py:1108-1154 ref_schedule_t1_cache_moves       (K4)
+  vllm/_custom_ops.py:1182-1216 ref_execute_cache_moves           (K5)
+  tests/kernels/test_kvcompress_attention.py:41-54 ref_masked_attention (K7/K8)
+  tests/kernels/test_kvcompress_cache.py pattern for K6 (a 4-line Python loop,
+  re-derived here from csrc/kvcompress_cache_kernels.cu:44-88 because the
+  reference test file is a checker, not a generator).
+
+The inputs follow BASELINE.json configs[0] ("4-head x 256-KV synthetic metrics")
+plus small ragged multi-sequence cases in the style of
+tests/kernels/test_kvcompress_eviction.py:412-418 (S=3, L=2, H=2, B=4, seed 4).
+Every .npz stores inputs AND reference outputs, so tests need no reference.
+"""
+import ast
+import contextlib
+import importlib.util
+import io
+import os
+import sys
+import types
+from typing import Optional
+
+import numpy as np
+import torch
+
+REF = os.environ.get("KVC_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+MAX_INT = 2147483000
+
+
+def _load_reference_custom_ops():
+    """Import reference vllm/_custom_ops.py with its non-KVC imports stubbed."""
+    class _Bench:
+        def wrap(self, *a, **k):
+            return lambda f: f
+
+    stubs = {
+        "vllm": types.ModuleType("vllm"),
+        "vllm.envs": types.ModuleType("vllm.envs"),
+        "vllm._core_ext": types.ModuleType("vllm._core_ext"),
+        "vllm.logger": types.ModuleType("vllm.logger"),
+        "vllm.platforms": types.ModuleType("vllm.platforms"),
+        "vllm.benchmark": types.ModuleType("vllm.benchmark"),
+    }
+    stubs["vllm"].__path__ = []
+    stubs["vllm._core_ext"].ScalarType = type("ScalarType", (), {})
+    import logging
+    stubs["vllm.logger"].init_logger = lambda name: logging.getLogger(name)
+    stubs["vllm.platforms"].current_platform = types.SimpleNamespace(is_tpu=lambda: True)
+    stubs["vllm.benchmark"].BENCHMARKER = _Bench()
+    stubs["vllm"].envs = stubs["vllm.envs"]
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location(
+            "vllm._custom_ops", os.path.join(REF, "vllm", "_custom_ops.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        # the reference's ref_schedule_cache_evictions uses `tqdm` without importing it
+        # (_custom_ops.py:846); provide the name so the function can run unmodified.
+        mod.tqdm = lambda it, *a, **k: it
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod
+
+
+def _load_function_from_file(path: str, name: str):
+    """Compile ONE function of a reference file (by AST) without importing the file."""
+    tree = ast.parse(open(path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name][0]
+    ns = {"torch": torch, "Optional": Optional}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        return fn(*a, **k)
+
+
+# --------------------------------------------------------------------------
+# synthetic input builders
+# --------------------------------------------------------------------------
+def build_eviction_inputs(rng, S, L, H, B, ctx, interleave=True, position_mode="logical"):
+    """ctx: int array [S, L, H].  Returns dict of K1 inputs (numpy int32)."""
+    ctx = np.asarray(ctx, dtype=np.int32)
+    nblk = (ctx + B - 1) // B
+    total_blocks = int(nblk.sum())
+    hanging = np.where(ctx % B == 0, B, ctx % B).astype(np.int32)
+    hanging[ctx == 0] = B
+    # masked block arrays: one entry per allocated block
+    seq_of, layer_of, head_of, vblk_of = [], [], [], []
+    for s in range(S):
+        for l in range(L):
+            for h in range(H):
+                for b in range(nblk[s, l, h]):
+                    seq_of.append(s); layer_of.append(l); head_of.append(h); vblk_of.append(b)
+    seq_of = np.array(seq_of, np.int32); layer_of = np.array(layer_of, np.int32)
+    head_of = np.array(head_of, np.int32); vblk_of = np.array(vblk_of, np.int32)
+    if interleave:  # physical order is arbitrary in the engine (boolean mask over the cache)
+        perm = rng.permutation(total_blocks)
+        seq_of, layer_of, head_of, vblk_of = seq_of[perm], layer_of[perm], head_of[perm], vblk_of[perm]
+    metrics = (rng.permutation(total_blocks * B).astype(np.float32) / (total_blocks * B)).reshape(total_blocks, B)
+    logical = vblk_of[:, None] * B + np.arange(B, dtype=np.int32)[None]
+    if position_mode == "logical":
+        kv_position = logical.astype(np.int32)
+    else:  # positions no longer monotone in logical index (state after a previous compression)
+        kv_position = np.empty_like(logical)
+        for s in range(S):
+            for l in range(L):
+                for h in range(H):
+                    sel = np.where((seq_of == s) & (layer_of == l) & (head_of == h))[0]
+                    n = len(sel) * B
+                    pos = rng.permutation(n).astype(np.int32)
+                    order = np.argsort(vblk_of[sel])
+                    kv_position[sel[order]] = pos.reshape(-1, B)
+    # sort: by (seq, metric) -- reference metrics.py:849-966 sort_seq_metrics
+    flat_seq = np.repeat(seq_of, B)
+    order = np.lexsort((metrics.reshape(-1), flat_seq))
+    sorted_indices = order.astype(np.int32)
+    blocks_per_seq = np.array([(seq_of == s).sum() for s in range(S)], np.int64)
+    seq_block_offsets = np.concatenate([[0], np.cumsum(blocks_per_seq)[:-1]]).astype(np.int32)
+    alloc = (nblk * B).reshape(-1)
+    evicted_kv_offsets = np.concatenate([[0], np.cumsum(alloc)[:-1]]).astype(np.int32).reshape(S, L, H)
+    return dict(S=S, L=L, H=H, B=B, context_lens=ctx, hanging_token_count=hanging,
+                layer_by_block=layer_of, head_by_block=head_of, virtual_block_num_by_block=vblk_of,
+                seq_by_block=seq_of, metrics=metrics, kv_position=kv_position,
+                sorted_indices=sorted_indices, seq_block_offsets=seq_block_offsets,
+                evicted_kv_offsets=evicted_kv_offsets, total_kv=int(alloc.sum()))
+
+
+def run_ref_evictions(ops, inp, budgets, protected, last_position, truncate=True):
+    t = lambda a, dt=torch.int32: torch.tensor(np.asarray(a), dtype=dt)
+    N = inp["total_kv"]
+    ekv = torch.zeros(N, dtype=torch.int32)          # wrapper zeroes it (_custom_ops.py:966)
+    elog = torch.full((N,), -7, dtype=torch.int32)   # sentinel: untouched stays -7
+    cnt = torch.zeros((inp["S"], inp["L"], inp["H"]), dtype=torch.int32)
+    quiet(ops.ref_schedule_cache_evictions,
+          ekv, elog, cnt, t(inp["hanging_token_count"]).clone(), t(inp["evicted_kv_offsets"]),
+          t(inp["sorted_indices"]), t(inp["seq_block_offsets"]), t(inp["layer_by_block"]),
+          t(inp["head_by_block"]), t(inp["virtual_block_num_by_block"]), t(budgets),
+          t(inp["context_lens"]), t(inp["hanging_token_count"]), t(inp["kv_position"]),
+          t(last_position), t(protected), inp["B"], False, None, N, MAX_INT, truncate)
+    return ekv.numpy(), elog.numpy(), cnt.numpy()
+
+
+def gen_evictions(ops):
+    cases = {}
+    rng = np.random.RandomState(0)
+    # BASELINE.json configs[0]: 4 heads x 256 KV, budgets {0, 8, 40, 56}, protected {0, 32}
+    for name, ctx in (("c1_full", [[[256, 256, 256, 256]]]), ("c1_ragged", [[[256, 250, 241, 225]]])):
+        inp = build_eviction_inputs(rng, 1, 1, 4, 16, ctx, interleave=True)
+        for prot in (0, 32):
+            for budget in (0, 8, 40, 56):
+                if name == "c1_ragged" and budget == 56 and prot == 32:
+                    budget = 52  # ragged heads have fewer evictable blocks (ref asserts feasibility)
+                if budget == 0:
+                    # the reference's Python oracle cannot run a zero budget (it takes max() of an
+                    # empty list, _custom_ops.py:902); K1's early return (:85-87) is covered by an
+                    # explicit expectation in tests/test_oracle_golden.py instead.
+                    continue
+                ekv, elog, cnt = run_ref_evictions(ops, inp, [budget], [prot], [255])
+                cases[f"{name}_p{prot}_e{budget}"] = dict(
+                    inp, budgets=np.array([budget], np.int32), protected=np.array([prot], np.int32),
+                    last_position=np.array([255], np.int32), truncate=np.array(1),
+                    out_evicted_kv_indices=ekv, out_evicted_logical_indices=elog, out_evicted_kv_count=cnt)
+    # small ragged multi-sequence cases (style of test_kvcompress_eviction.py:412-418)
+    rng = np.random.RandomState(4)
+    for k, (S, L, H, B, maxblk) in enumerate([(3, 2, 2, 4, 3), (2, 3, 2, 2, 4), (4, 2, 3, 1, 6), (2, 2, 4, 16, 5)]):
+        hang = rng.randint(1, B + 1, size=(S, L, H))
+        ctx = rng.randint(0, maxblk + 1, size=(S, L, H)) * B + hang
+        inp = build_eviction_inputs(rng, S, L, H, B, ctx, interleave=True,
+                                    position_mode="shuffled" if k % 2 else "logical")
+        nblk = (np.asarray(ctx) + B - 1) // B
+        last = np.array([int(np.asarray(ctx)[s].max()) - 1 for s in range(S)], np.int32)
+        prot = np.array([0 if k % 2 == 0 else min(B, 2)] * S, np.int32)
+        # feasible budgets: at most half the evictable blocks
+        budgets = []
+        for s in range(S):
+            evictable = int(nblk[s].sum()) - int(((prot[s] + B - 1) // B) * L * H)
+            budgets.append(max(1, evictable // 2))
+        budgets = np.array(budgets, np.int32)
+        if k % 2:  # shuffled positions: protect by position, budget must stay feasible -> small
+            budgets = np.minimum(budgets, 2)
+        for trunc in (True, False):
+            try:
+                ekv, elog, cnt = run_ref_evictions(ops, inp, budgets, prot, last, truncate=trunc)
+            except AssertionError:
+                budgets = np.minimum(budgets, 1)
+                ekv, elog, cnt = run_ref_evictions(ops, inp, budgets, prot, last, truncate=trunc)
+            cases[f"multi{k}_t{int(trunc)}"] = dict(
+                inp, budgets=budgets, protected=prot, last_position=last, truncate=np.array(int(trunc)),
+                out_evicted_kv_indices=ekv, out_evicted_logical_indices=elog, out_evicted_kv_count=cnt)
+    return cases
+
+
+def gen_count_blocks(ops):
+    """K3 golden: V2-format input (rows of B sorted logical indices, NULL rows after)."""
+    cases = {}
+    rng = np.random.RandomState(1)
+    for k, (S, L, H, B) in enumerate([(2, 2, 2, 4), (1, 1, 4, 16), (3, 1, 2, 2)]):
+        nblk = rng.randint(1, 5, size=(S, L, H))
+        hanging = rng.randint(1, B + 1, size=(S, L, H)).astype(np.int32)
+        hanging[0, 0, 0] = B  # keeps the reference's debug branch (_custom_ops.py:1057-1059) inert
+        alloc = (nblk * B).reshape(-1)
+        offs = np.concatenate([[0], np.cumsum(alloc)[:-1]]).astype(np.int32).reshape(S, L, H)
+        total = int(alloc.sum())
+        logical = np.full(total, MAX_INT, np.int32)
+        ev_blocks = np.zeros((S, L, H), np.int32)
+        for s in range(S):
+            for l in range(L):
+                for h in range(H):
+                    e = rng.randint(0, nblk[s, l, h] + 1)
+                    ev_blocks[s, l, h] = e
+                    if e == 0:
+                        # the Python reference nulls [start-B+hanging, start) when nothing is evicted
+                        # (_custom_ops.py:1054-1055: no `evicted_blocks > 0` guard, unlike the kernel
+                        # :210) and would clobber the previous head; hanging == B makes that slice empty.
+                        hanging[s, l, h] = B
+                    if e:
+                        vals = np.sort(rng.choice(nblk[s, l, h] * B, e * B, replace=False)).astype(np.int32)
+                        logical[offs[s, l, h]: offs[s, l, h] + e * B] = vals
+        inp_logical = logical.copy()
+        out_cnt = torch.zeros((S, L, H), dtype=torch.int32)
+        lg = torch.tensor(logical)
+        quiet(ops.ref_count_block_evictions, out_cnt, lg, torch.tensor(offs), torch.tensor(hanging),
+              B, MAX_INT, torch.tensor(ev_blocks.reshape(S, -1).sum(-1)), None, lg.clone() + 1)
+        cases[f"count{k}"] = dict(S=S, L=L, H=H, B=B, evicted_kv_offsets=offs, hanging_token_count=hanging,
+                                  in_evicted_logical_indices=inp_logical,
+                                  out_evicted_logical_indices=lg.numpy(), out_evicted_block_count=out_cnt.numpy())
+    return cases
+
+
+def build_move_inputs(rng, S, L, H, B, D, x, dtype, max_blocks):
+    """State for K4/K5: block tables, evicted index lists (ascending, NULL tail), caches."""
+    ctx = rng.randint(1, max_blocks * B + 1, size=(L, S, H)).astype(np.int32)
+    nblk = (ctx + B - 1) // B
+    MB = int(nblk.max()) + 1
+    NB = int(nblk.sum()) + 3
+    phys = rng.permutation(NB)
+    block_tables = np.zeros((L, S, H, MB), np.int32)
+    p = 0
+    for l in range(L):
+        for s in range(S):
+            for h in range(H):
+                n = nblk[l, s, h]
+                block_tables[l, s, h, :n] = phys[p:p + n]
+                p += n
+    alloc = np.transpose(nblk, (1, 0, 2)).reshape(-1) * B
+    offs = np.concatenate([[0], np.cumsum(alloc)[:-1]]).astype(np.int32).reshape(S, L, H)
+    total = int(alloc.sum())
+    logical = np.full(total, MAX_INT, np.int32)
+    ev_cnt = np.zeros((S, L, H), np.int32)
+    for s in range(S):
+        for l in range(L):
+            for h in range(H):
+                c = int(rng.randint(0, ctx[l, s, h] + 1))
+                ev_cnt[s, l, h] = c
+                logical[offs[s, l, h]: offs[s, l, h] + c] = np.sort(
+                    rng.choice(ctx[l, s, h], c, replace=False)).astype(np.int32)
+    k_cache = rng.randint(0, 2 ** (8 * dtype().itemsize) - 1 if dtype != np.float32 else 2 ** 24,
+                          size=(NB, D // x, B, x)).astype(dtype)
+    v_cache = rng.randint(0, 2 ** (8 * dtype().itemsize) - 1 if dtype != np.float32 else 2 ** 24,
+                          size=(NB, D, B)).astype(dtype)
+    kv_metrics = rng.rand(NB, B).astype(np.float32)
+    kv_position = rng.randint(0, 10000, size=(NB, B)).astype(np.int32)
+    return dict(S=S, L=L, H=H, B=B, D=D, x=x, context_lens_lsh=ctx, block_tables=block_tables,
+                evicted_kv_offsets=offs, evicted_logical_indices=logical, evicted_kv_count=ev_cnt,
+                k_cache=k_cache, v_cache=v_cache, kv_metrics=kv_metrics, kv_position=kv_position,
+                total_kv=total)
+
+
+def gen_moves(ops):
+    cases = {}
+    rng = np.random.RandomState(2)
+    for k, (S, L, H, B, D, x, dt, mb) in enumerate([
+            (3, 2, 2, 4, 2, 2, np.uint16, 3),      # reference test shape (D=2)
+            (2, 2, 3, 16, 128, 8, np.uint16, 4),   # production layout fp16/bf16
+            (2, 1, 2, 2, 4, 1, np.float32, 5),
+            (1, 2, 2, 1, 4, 2, np.uint16, 7)]):
+        inp = build_move_inputs(rng, S, L, H, B, D, x, dt, mb)
+        moves = torch.zeros((inp["total_kv"], 2), dtype=torch.int32)  # wrapper zero-fills (:1168)
+        mcnt = torch.zeros((S, L, H), dtype=torch.int32)
+        quiet(ops.ref_schedule_t1_cache_moves, moves, mcnt, torch.tensor(inp["evicted_logical_indices"]),
+              torch.tensor(inp["evicted_kv_count"]), torch.tensor(inp["evicted_kv_offsets"]),
+              torch.tensor(inp["block_tables"]), torch.tensor(inp["context_lens_lsh"]), B)
+        # K5 on the schedule K4 produced (torch has no uint16 arithmetic; view as int16/float32)
+        tv = (lambda a: torch.tensor(a.view(np.int16))) if dt == np.uint16 else (lambda a: torch.tensor(a))
+        kc, vc = tv(inp["k_cache"].copy()), tv(inp["v_cache"].copy())
+        km, kp = torch.tensor(inp["kv_metrics"].copy()), torch.tensor(inp["kv_position"].copy())
+        quiet(ops.ref_execute_cache_moves, kc, vc, km, kp, moves, mcnt,
+              torch.tensor(inp["evicted_kv_offsets"]), 1, 1)
+        cases[f"moves{k}"] = dict(inp, out_cache_moves_idx=moves.numpy(), out_cache_moves_count=mcnt.numpy(),
+                                  out_k_cache=kc.numpy().view(dt), out_v_cache=vc.numpy().view(dt),
+                                  out_kv_metrics=km.numpy(), out_kv_position=kp.numpy())
+    return cases
+
+
+def gen_attention():
+    """K7/K8 golden via the reference test's ref_masked_attention on gathered K/V."""
+    ref_masked_attention = _load_function_from_file(
+        os.path.join(REF, "tests", "kernels", "test_kvcompress_attention.py"), "ref_masked_attention")
+    cases = {}
+    g = torch.Generator().manual_seed(0)
+    rng = np.random.RandomState(3)
+    for k, (S, Hq, H, D, B, max_ctx, dtype, alibi, buf) in enumerate([
+            (3, 8, 2, 128, 16, 70, torch.float16, False, 0),
+            (2, 8, 8, 128, 16, 40, torch.bfloat16, False, 3),
+            (2, 16, 2, 128, 16, 600, torch.float16, True, 0),   # > one 512-token partition
+            (1, 4, 1, 128, 16, 33, torch.float16, False, 100)]):
+        Q = Hq // H
+        x = 8
+        ctx = rng.randint(1, max_ctx + 1, size=(S, H)).astype(np.int32)
+        ctx[0, 0] = max_ctx
+        nblk = (ctx + B - 1) // B
+        MB = int(nblk.max()) + 2
+        NB = int(nblk.sum()) + 5
+        phys = rng.permutation(NB)
+        bt = np.zeros((S, H, MB), np.int32)
+        p = 0
+        for s in range(S):
+            for h in range(H):
+                bt[s, h, :nblk[s, h]] = phys[p:p + nblk[s, h]]
+                p += nblk[s, h]
+        scale = float(D ** -0.5)
+        q = (torch.rand((S, Hq, D), generator=g) * 2 - 1).mul(scale).to(dtype)
+        kc = (torch.rand((NB, D // x, B, x), generator=g) * 2 - 1).mul(scale).to(dtype)
+        vc = (torch.rand((NB, D, B), generator=g) * 2 - 1).mul(scale).to(dtype)
+        kv_position = rng.randint(0, 200, size=(NB, B)).astype(np.int32)
+        last_position = np.full(S, 199, np.int32)
+        buf_len = np.full(S, buf, np.int32)
+        slopes = torch.rand(Hq, generator=g).float() if alibi else None
+        out = torch.zeros((S, Hq, D), dtype=torch.float32)
+        metric = torch.full((NB, B, Q), -1.0, dtype=torch.float32)  # -1 == untouched
+        for s in range(S):
+            for h in range(H):
+                n = int(ctx[s, h])
+                blk = torch.tensor(bt[s, h, np.arange(n) // B], dtype=torch.long)
+                off = torch.arange(n) % B
+                keys = kc[blk, :, off, :].reshape(n, 1, D).float()
+                vals = vc[blk, :, off].reshape(n, 1, D).float()
+                for qh in range(h * Q, (h + 1) * Q):
+                    bias = None
+                    if slopes is not None:
+                        pos = torch.arange(n).int()
+                        bias = slopes[qh].view(1, 1, 1) * (pos - n + 1).float().view(1, 1, -1)
+                    o, attn = ref_masked_attention(q[s, qh].float().view(1, 1, D), keys, vals, scale, bias)
+                    out[s, qh] = o.view(D)
+                    rec = torch.tensor(kv_position[blk.numpy(), off.numpy()] <= last_position[s] - buf_len[s])
+                    metric[blk[rec], off[rec], qh - h * Q] = attn[0, 0, rec]
+        view16 = lambda t: t.view(torch.int16).numpy().view(np.uint16)
+        cases[f"attn{k}"] = dict(S=S, Hq=Hq, H=H, D=D, B=B, x=x, is_bf16=int(dtype == torch.bfloat16),
+                                 scale=np.float32(scale), query=view16(q), key_cache=view16(kc),
+                                 value_cache=view16(vc), block_tables=bt, context_lens=ctx,
+                                 kv_position=kv_position, last_position=last_position,
+                                 kv_metric_buffer_len=buf_len,
+                                 alibi_slopes=(slopes.numpy() if alibi else np.zeros(0, np.float32)),
+                                 out=out.numpy(), kv_metric_out=metric.numpy())
+    return cases
+
+
+def gen_cache_write():
+    """K6 golden (csrc/kvcompress_cache_kernels.cu:44-88; loop shape of
+    tests/kernels/test_kvcompress_cache.py:118-141)."""
+    cases = {}
+    rng = np.random.RandomState(5)
+    for k, (T, H, D, B, x, NB) in enumerate([(5, 2, 128, 16, 8, 6), (3, 4, 16, 4, 8, 7)]):
+        key = rng.randint(0, 65535, size=(T, H, D)).astype(np.uint16)
+        val = rng.randint(0, 65535, size=(T, H, D)).astype(np.uint16)
+        kc = rng.randint(0, 65535, size=(NB, D // x, B, x)).astype(np.uint16)
+        vc = rng.randint(0, 65535, size=(NB, D, B)).astype(np.uint16)
+        metrics = rng.rand(NB, B).astype(np.float32)
+        bias = rng.rand(H).astype(np.float32)
+        slots = rng.choice(NB * B, T * H, replace=False).astype(np.int64).reshape(T, H)
+        slots[0, 0] = -1  # padding token
+        okc, ovc, om = kc.copy(), vc.copy(), metrics.copy()
+        for t in range(T):
+            for h in range(H):
+                s = slots[t, h]
+                if s < 0:
+                    continue
+                b, o = s // B, s % B
+                okc[b, :, o, :] = key[t, h].reshape(D // x, x)
+                ovc[b, :, o] = val[t, h]
+                om[b, o] = bias[h]
+        cases[f"cache{k}"] = dict(key=key, value=val, key_cache=kc, value_cache=vc, kv_metrics=metrics,
+                                  kv_metric_head_bias=bias, slot_mapping=slots,
+                                  out_key_cache=okc, out_value_cache=ovc, out_kv_metrics=om)
+    return cases
+
+
+def save(name, cases):
+    flat = {}
+    for cname, d in cases.items():
+        for k, v in d.items():
+            flat[f"{cname}/{k}"] = np.asarray(v)
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **flat)
+    print(f"wrote {path}: {len(cases)} cases, {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def main():
+    ops = _load_reference_custom_ops()
+    save("evictions.npz", gen_evictions(ops))
+    save("count_blocks.npz", gen_count_blocks(ops))
+    save("moves.npz", gen_moves(ops))
+    save("attention.npz", gen_attention())
+    save("cache_write.npz", gen_cache_write())
+
+
+if __name__ == "__main__":
+    main()
