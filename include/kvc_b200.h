@@ -1,0 +1,269 @@
+/*
+ * kvc_b200.h -- C ABI of libkvc_b200.so: the B200-native (sm_100a) KV-Compress
+ * eviction / compaction / paged-attention hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain device pointers,
+ * sizes and a CUDA stream; no torch types.  Each one replaces exactly one op of
+ * the reference's torch C++ extension (csrc/torch_bindings.cpp) and keeps that
+ * op's argument meaning, tensor layouts, in-place behaviour and error cases.
+ * vllm-kvcompress_b200/csrc/torch_bindings.cpp re-exports them under the
+ * reference's own dispatcher schemas (torch.ops._C / _C_cache_ops / _C_kvc_ops),
+ * so the fork's Python (vllm/_custom_ops.py) calls them unchanged; INTEGRATION.md
+ * shows the binding a maintainer adds.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless a parameter says "host".
+ *  - All index tensors are int32 and contiguous (the reference kernels
+ *    reinterpret_cast<int*> them, csrc/kvcompress_eviction_kernels.cu:527-542);
+ *    slot_mapping is int64 (csrc/kvcompress_cache_kernels.cu:36).
+ *  - Nothing is allocated and nothing synchronises: launches are asynchronous on
+ *    `stream` (reference: at::cuda::getCurrentCUDAStream(), :551-552).  Ops that
+ *    need scratch take it from the caller (`workspace`, size from the matching
+ *    *_workspace_bytes function).
+ *  - Return value: KVC_OK (0) or a negative kvc_status; kvc_last_error() gives the
+ *    message of the last failure on the calling thread.  Unsupported
+ *    block/head/vector sizes fail with KVC_ERR_UNSUPPORTED exactly where the
+ *    reference raises TORCH_CHECK(false, "Unsupported ...").
+ *  - [S,L,H] = (sequence, layer, kv head) row-major; [L,S,H] likewise.
+ *    B = KV block size (tokens per block); one physical block holds B tokens of
+ *    ONE kv head of ONE layer (vllm/attention/ops/paged_attn.py:256-284):
+ *      k_cache [NB, D/x, B, x]   (x = 16 / sizeof(cache element))
+ *      v_cache [NB, D, B]
+ *      kv_metrics [NB, B] f32, kv_position [NB, B] i32.
+ */
+#ifndef KVC_B200_H_
+#define KVC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(KVC_BUILDING_LIB)
+#define KVC_API __attribute__((visibility("default")))
+#else
+#define KVC_API
+#endif
+
+/* cudaStream_t without dragging cuda_runtime.h into C callers */
+typedef struct CUstream_st* kvc_stream_t;
+
+typedef enum kvc_status {
+  KVC_OK = 0,
+  KVC_ERR_UNSUPPORTED = -1, /* reference: TORCH_CHECK(false, "Unsupported ...") */
+  KVC_ERR_INVALID = -2,     /* null pointer / negative size / bad alignment */
+  KVC_ERR_WORKSPACE = -3,   /* workspace missing or too small */
+  KVC_ERR_CUDA = -4         /* a CUDA runtime call or launch failed */
+} kvc_status;
+
+/* cache element type of k_cache / v_cache / query */
+typedef enum kvc_dtype {
+  KVC_F16 = 0,
+  KVC_BF16 = 1,
+  KVC_F32 = 2,
+  KVC_U8 = 3 /* fp8_e5m2 stored as bytes: bit-copy ops only */
+} kvc_dtype;
+
+/* Message for the last non-OK status returned on this thread ("" if none). */
+KVC_API const char* kvc_last_error(void);
+/* Library/ABI version, bumped when a signature changes. */
+KVC_API int kvc_abi_version(void);
+/* Compiled-for architecture string, e.g. "sm_100a". */
+KVC_API const char* kvc_arch(void);
+
+/* ---------------------------------------------------------------------------
+ * schedule_cache_evictions (+ truncate)                                    K1/K2
+ * replaces _C_kvc_ops::schedule_cache_evictions
+ *   csrc/torch_bindings.cpp:374-386, csrc/kvcompress_eviction.h:5-28,
+ *   kernels csrc/kvcompress_eviction_kernels.cu:27-188, launcher :492-555.
+ * Walks, per sequence, its metric-sorted slot list; appends (head id, logical
+ * index) of every evictable slot to that head's segment until
+ * evicted_blocks_per_seq[s] whole blocks are freed.  Results are bit-identical
+ * to the reference's one-thread-per-sequence walk; here the walk is a chunked
+ * multi-bin rank (histogram -> scan -> stable scatter).
+ *   evicted_kv_indices       [max_evicted_kv] out
+ *   evicted_logical_indices  [max_evicted_kv] out
+ *   evicted_kv_count         [S,L,H] out
+ *   remaining_kv_count       [S,L,H] in/out scratch; caller passes a copy of
+ *                            hanging_token_count (vllm/_custom_ops.py:987)
+ *   evicted_kv_offsets       [S,L,H]
+ *   sorted_indices           [total_blocks*B] slot ids sorted by (seq, metric)
+ *   seq_block_offsets        [S]
+ *   layer_by_block, head_by_block, virtual_block_num_by_block [total_blocks]
+ *   evicted_blocks_per_seq   [S]
+ *   context_lens             [S,L,H]   (NOTE: [S,L,H] here, _custom_ops.py:995)
+ *   hanging_token_count      [S,L,H]
+ *   kv_position              [total_blocks, B]
+ *   last_position, protected_window_size [S]
+ *   control_layers           [num_control_layers] or NULL
+ * block_size in {1,2,4,16} else KVC_ERR_UNSUPPORTED (:474-490).
+ * ------------------------------------------------------------------------- */
+KVC_API size_t kvc_schedule_cache_evictions_workspace_bytes(
+    int num_seqs, int num_layers, int num_kv_heads, int total_blocks,
+    int block_size);
+
+KVC_API int kvc_schedule_cache_evictions(
+    int* evicted_kv_indices, int* evicted_logical_indices,
+    int* evicted_kv_count, int* remaining_kv_count,
+    const int* evicted_kv_offsets, const int* sorted_indices,
+    const int* seq_block_offsets, const int* layer_by_block,
+    const int* head_by_block, const int* virtual_block_num_by_block,
+    const int* evicted_blocks_per_seq, const int* context_lens,
+    const int* hanging_token_count, const int* kv_position,
+    const int* last_position, const int* protected_window_size,
+    int num_seqs, int num_layers, int num_kv_heads, int total_blocks,
+    int block_size, int evict_evenly_per_layer, const int* control_layers,
+    int num_control_layers, int max_evicted_kv, int null_eviction_index,
+    int truncate, void* workspace, size_t workspace_bytes,
+    kvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * truncate_cache_evictions                                                   K2
+ * replaces _C_kvc_ops::truncate_cache_evictions
+ *   csrc/torch_bindings.cpp:389-394, csrc/kvcompress_eviction.h:30-38,
+ *   kernel csrc/kvcompress_eviction_kernels.cu:158-188, launcher :585-610.
+ * ------------------------------------------------------------------------- */
+KVC_API int kvc_truncate_cache_evictions(
+    int* evicted_kv_indices, int* evicted_logical_indices,
+    int* evicted_kv_count, const int* evicted_kv_offsets,
+    const int* hanging_token_count, int num_seqs, int num_layers,
+    int num_kv_heads, int block_size, int max_evicted_kv,
+    int null_eviction_index, kvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * count_block_evictions                                                      K3
+ * replaces _C_kvc_ops::count_block_evictions
+ *   csrc/torch_bindings.cpp:397-401, csrc/kvcompress_eviction.h:40-46,
+ *   kernel csrc/kvcompress_eviction_kernels.cu:190-221, launcher :640-664.
+ * total_kvs = numel(evicted_logical_indices).
+ * ------------------------------------------------------------------------- */
+KVC_API int kvc_count_block_evictions(
+    int* evicted_block_count, int* evicted_logical_indices,
+    const int* evicted_kv_offsets, const int* hanging_token_count,
+    int num_seqs, int num_layers, int num_kv_heads, int total_kvs,
+    int block_size, int null_value, kvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * schedule_t1_cache_moves                                                    K4
+ * replaces _C_kvc_ops::schedule_t1_cache_moves
+ *   csrc/torch_bindings.cpp:404-409, csrc/kvcompress_eviction.h:48-56,
+ *   kernel csrc/kvcompress_eviction_kernels.cu:223-289, launcher :698-726.
+ *   cache_moves_idx [max_evicted_kv, 2] (dst, src) physical slot ids, out
+ *   cache_moves_count [S,L,H] out
+ *   evicted_logical_indices [max_evicted_kv] (ascending per head segment)
+ *   evicted_kv_count, evicted_kv_offsets [S,L,H]
+ *   block_tables [L,S,H,MB], context_lens [L,S,H]
+ * ------------------------------------------------------------------------- */
+KVC_API int kvc_schedule_t1_cache_moves(
+    int* cache_moves_idx, int* cache_moves_count,
+    const int* evicted_logical_indices, const int* evicted_kv_count,
+    const int* evicted_kv_offsets, const int* block_tables,
+    const int* context_lens, int num_seqs, int num_layers, int num_kv_heads,
+    int max_num_blocks_per_seq, int block_size, kvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * execute_cache_moves                                                        K5
+ * replaces _C_kvc_ops::execute_cache_moves
+ *   csrc/torch_bindings.cpp:412-417, csrc/kvcompress_eviction.h:69-78,
+ *   kernel csrc/kvcompress_eviction_kernels.cu:359-435, launcher :858-929.
+ * Bit-copies K, V, metric and position of every scheduled (dst, src) pair.
+ * head_size in {1,2,4,128}, vec_size (x) in {1,2,8}, block_size in {1,2,4,16}
+ * else KVC_ERR_UNSUPPORTED (:793-856).  blocks_per_head / threads_per_head are
+ * launch hints in the reference (cache_engine.py:149-150); results never depend
+ * on them and this implementation ignores them.
+ * Algorithmic bytes per move (D=128, 2-byte cache): 2*(2*128*2+4+4)+8 = 1048.
+ * ------------------------------------------------------------------------- */
+KVC_API int kvc_execute_cache_moves(
+    void* k_cache, void* v_cache, float* kv_metrics, int* kv_position,
+    const int* cache_moves_idx, const int* cache_moves_count,
+    const int* evicted_kv_offsets, int num_seqs, int num_layers,
+    int num_kv_heads, int64_t num_blocks, int head_size, int vec_size,
+    int block_size, int dtype /* kvc_dtype */, int blocks_per_head,
+    int threads_per_head, kvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * kvcompress_reshape_and_cache                                               K6
+ * replaces _C_cache_ops::kvcompress_reshape_and_cache
+ *   csrc/torch_bindings.cpp:354-362, csrc/kvcompress_cache.h:5-15,
+ *   kernel csrc/kvcompress_cache_kernels.cu:27-89, launcher :111-139.
+ *   key, value [T, H, D] with token strides key_stride / value_stride (elements)
+ *   slot_mapping [T, H] int64 (<0 = padding)
+ *   kv_metric_head_bias [H] f32: metric of every written slot is set to it.
+ * kv_cache_dtype "auto" only (dtype = element type of key AND cache).
+ * ------------------------------------------------------------------------- */
+KVC_API int kvc_reshape_and_cache(
+    const void* key, const void* value, void* key_cache, void* value_cache,
+    float* kv_metrics, const int64_t* slot_mapping,
+    const float* kv_metric_head_bias, int num_tokens, int num_heads,
+    int head_size, int block_size, int x, int64_t key_stride,
+    int64_t value_stride, int dtype /* kvc_dtype */, kvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * kvcompress_paged_attention_v1 / v2                                     K7 / K8
+ * replaces _C::kvcompress_paged_attention_v1 / _v2
+ *   csrc/torch_bindings.cpp:53-80, csrc/ops.h:18-37, 67-90,
+ *   kernels csrc/attention/kvcompress_attention_kernels.cu:95-651,
+ *   launchers :683-771, :878-978.
+ * Single-query (decode) attention over per-(seq, kv head) block tables and
+ * context lengths; additionally writes each KV's softmax probability per query
+ * head to kv_metric_out[slot*Q + q_off] iff record_kv_metrics and
+ * kv_position[slot] <= last_position[s] - kv_metric_buffer_len[s] (:124,:305-313).
+ *   out [S, Hq, D]; query [S, Hq, D] row stride q_stride (elements)
+ *   kv_metric_out [NB, B, Q] f32
+ *   block_tables [S, H, MB], context_lens [S, H]
+ *   alibi_slopes [Hq] f32 or NULL
+ * v2 extra buffers (caller-allocated, same shapes as the reference):
+ *   exp_sums, max_logits [S, Hq, P] f32, tmp_out [S, Hq, P, D] (query dtype),
+ *   P = ceil(max_context_len / 512); tmp_kv_metric_out is accepted for ABI
+ *   compatibility and never touched.
+ * head_size must be 128 (:745-770), block_size 16, dtype F16/BF16,
+ * kv_cache_dtype "auto" (the only combination the KVC engine can run end to
+ * end: K5 supports B in {1,2,4,16}, the reference attention B in {8,16,32}).
+ * ------------------------------------------------------------------------- */
+KVC_API int kvc_paged_attention_v1(
+    void* out, float* kv_metric_out, const void* query, const void* key_cache,
+    const void* value_cache, int num_seqs, int num_heads, int num_kv_heads,
+    int head_size, float scale, const int* block_tables,
+    const int* context_lens, const int* kv_position, const int* last_position,
+    const int* kv_metric_buffer_len, int block_size, int max_context_len,
+    int max_num_blocks_per_seq, int64_t q_stride, int64_t kv_block_stride,
+    const float* alibi_slopes, int dtype /* kvc_dtype */,
+    int record_kv_metrics, kvc_stream_t stream);
+
+KVC_API int kvc_paged_attention_v2(
+    void* out, float* kv_metric_out, float* exp_sums, float* max_logits,
+    void* tmp_out, float* tmp_kv_metric_out, const void* query,
+    const void* key_cache, const void* value_cache, int num_seqs,
+    int num_heads, int num_kv_heads, int head_size, float scale,
+    const int* block_tables, const int* context_lens, const int* kv_position,
+    const int* last_position, const int* kv_metric_buffer_len, int block_size,
+    int max_context_len, int max_num_blocks_per_seq, int64_t q_stride,
+    int64_t kv_block_stride, const float* alibi_slopes,
+    int dtype /* kvc_dtype */, int record_kv_metrics, kvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Additive (not in the reference's op list): decode attention that folds the
+ * per-step metric aggregation into the kernel.
+ * replaces the chain  CompressionMetrics.clear_temp_metrics()  (zero [NB,B,Q]),
+ * paged_attention_kvc_v1(record=True), CompressionMetrics.aggregate_decode()
+ * (metrics += (temp**2).sum(-1) over the WHOLE cache)
+ *   vllm/kvcompress/metrics.py:337-342, 429-439; llm_engine.py:1621-1634
+ * with one launch that does  kv_metrics[slot] += sum_q p[slot,q]^2  for the
+ * slots it visits (same recording rule as above).  No [NB,B,Q] buffers.
+ * ------------------------------------------------------------------------- */
+KVC_API int kvc_paged_attention_fused_metrics(
+    void* out, float* kv_metrics /* [NB,B] f32, accumulated in place */,
+    const void* query, const void* key_cache, const void* value_cache,
+    int num_seqs, int num_heads, int num_kv_heads, int head_size, float scale,
+    const int* block_tables, const int* context_lens, const int* kv_position,
+    const int* last_position, const int* kv_metric_buffer_len, int block_size,
+    int max_context_len, int max_num_blocks_per_seq, int64_t q_stride,
+    int64_t kv_block_stride, const float* alibi_slopes,
+    int dtype /* kvc_dtype */, kvc_stream_t stream);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+#endif /* KVC_B200_H_ */

@@ -1,0 +1,522 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything here calls the CUDA
+kernels through the C ABI (vllm_kvcompress_b200.capi -> libkvc_b200.so) and checks them
+against (1) the committed golden vectors produced by the reference's Python oracles,
+(2) the C oracle on seeded random inputs, and (3) the reference's own CUDA kernels
+(oracle/_ref/_kvc_ref.so) when that library is present.  Integer / byte results must be
+bit-exact; attention is checked at the reference's tolerance (atol 1e-3, rtol 1e-5 on the
+output; default allclose on recorded probabilities)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_util import load_cases
+
+pytestmark = pytest.mark.gpu
+
+MAX_INT = 2147483000
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "_kvc_ref.so")
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from vllm_kvcompress_b200 import capi as c
+    assert c.abi_version() == 1
+    return c
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import kvc_oracle
+    kvc_oracle.build()
+    return kvc_oracle
+
+
+@pytest.fixture(scope="module")
+def ref_ops():
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref/_kvc_ref.so (reference CUDA kernels) not built")
+    torch.ops.load_library(REF_SO)
+    return torch.ops._kvc_ref
+
+
+def cu(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def cu16(a, is_bf16):
+    """uint16 numpy bits -> fp16/bf16 cuda tensor"""
+    t = torch.as_tensor(np.ascontiguousarray(a).view(np.int16)).cuda()
+    return t.view(torch.bfloat16 if is_bf16 else torch.float16)
+
+
+def bits16(t):
+    return t.view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+# ---------------------------------------------------------------------------
+# A. golden vectors through the C ABI
+# ---------------------------------------------------------------------------
+EVICT = load_cases("evictions.npz")
+COUNT = load_cases("count_blocks.npz")
+MOVES = load_cases("moves.npz")
+ATTN = load_cases("attention.npz")
+CACHE = load_cases("cache_write.npz")
+
+
+def run_k1(capi, c, budgets=None, truncate=None, evenly=False, control=None, remaining=None):
+    S, L, H, B = int(c["S"]), int(c["L"]), int(c["H"]), int(c["B"])
+    N = int(c["total_kv"])
+    ekv = torch.zeros(N, dtype=torch.int32, device="cuda")
+    elog = torch.full((N,), -7, dtype=torch.int32, device="cuda")
+    cnt = torch.full((S, L, H), 99, dtype=torch.int32, device="cuda")
+    rem = cu(c["hanging_token_count"] if remaining is None else remaining, torch.int32)
+    i = lambda k: cu(c[k], torch.int32)
+    capi.schedule_cache_evictions(
+        ekv, elog, cnt, rem, i("evicted_kv_offsets"), i("sorted_indices"), i("seq_block_offsets"),
+        i("layer_by_block"), i("head_by_block"), i("virtual_block_num_by_block"),
+        cu(c["budgets"] if budgets is None else budgets, torch.int32), i("context_lens"),
+        i("hanging_token_count"), i("kv_position"), i("last_position"), i("protected"), B, evenly,
+        None if control is None else cu(control, torch.int32), N, MAX_INT,
+        bool(c["truncate"]) if truncate is None else truncate)
+    torch.cuda.synchronize()
+    return ekv.cpu().numpy(), elog.cpu().numpy(), cnt.cpu().numpy(), rem.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", sorted(EVICT))
+def test_k1_golden(capi, name):
+    c = EVICT[name]
+    ekv, elog, cnt, _ = run_k1(capi, c)
+    np.testing.assert_array_equal(cnt, c["out_evicted_kv_count"])
+    if int(c["truncate"]):
+        np.testing.assert_array_equal(elog, c["out_evicted_logical_indices"])
+        np.testing.assert_array_equal(ekv, c["out_evicted_kv_indices"])
+    else:
+        offs = c["evicted_kv_offsets"].reshape(-1)
+        written = np.zeros(len(elog), bool)
+        for o, n in zip(offs, cnt.reshape(-1)):
+            written[o:o + n] = True
+        np.testing.assert_array_equal(elog[written], c["out_evicted_logical_indices"][written])
+        np.testing.assert_array_equal(ekv[written], c["out_evicted_kv_indices"][written])
+        assert (elog[~written] == -7).all() and (ekv[~written] == 0).all()
+
+
+@pytest.mark.parametrize("name", sorted(COUNT))
+def test_k3_golden(capi, name):
+    c = COUNT[name]
+    logical = cu(c["in_evicted_logical_indices"], torch.int32)
+    out = torch.zeros(tuple(c["out_evicted_block_count"].shape), dtype=torch.int32, device="cuda")
+    capi.count_block_evictions(out, logical, cu(c["evicted_kv_offsets"], torch.int32),
+                               cu(c["hanging_token_count"], torch.int32), int(c["B"]), MAX_INT)
+    np.testing.assert_array_equal(out.cpu().numpy(), c["out_evicted_block_count"])
+    np.testing.assert_array_equal(logical.cpu().numpy(), c["out_evicted_logical_indices"])
+
+
+def torch_cache(a):
+    if a.dtype == np.uint16:
+        return cu16(a, False)
+    return cu(a)
+
+
+def cache_bits(t, like):
+    return bits16(t) if like.dtype == np.uint16 else t.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", sorted(MOVES))
+def test_k4_k5_golden(capi, name):
+    c = MOVES[name]
+    B = int(c["B"])
+    moves = torch.zeros((int(c["total_kv"]), 2), dtype=torch.int32, device="cuda")
+    mcnt = torch.zeros(tuple(c["evicted_kv_count"].shape), dtype=torch.int32, device="cuda")
+    offs = cu(c["evicted_kv_offsets"], torch.int32)
+    capi.schedule_t1_cache_moves(moves, mcnt, cu(c["evicted_logical_indices"], torch.int32),
+                                 cu(c["evicted_kv_count"], torch.int32), offs,
+                                 cu(c["block_tables"], torch.int32), cu(c["context_lens_lsh"], torch.int32), B)
+    np.testing.assert_array_equal(mcnt.cpu().numpy(), c["out_cache_moves_count"])
+    np.testing.assert_array_equal(moves.cpu().numpy(), c["out_cache_moves_idx"])
+    kc, vc = torch_cache(c["k_cache"]), torch_cache(c["v_cache"])
+    km, kp = cu(c["kv_metrics"]), cu(c["kv_position"], torch.int32)
+    capi.execute_cache_moves(kc, vc, km, kp, moves, mcnt, offs)
+    np.testing.assert_array_equal(cache_bits(kc, c["k_cache"]), c["out_k_cache"])
+    np.testing.assert_array_equal(cache_bits(vc, c["v_cache"]), c["out_v_cache"])
+    np.testing.assert_array_equal(km.cpu().numpy(), c["out_kv_metrics"])
+    np.testing.assert_array_equal(kp.cpu().numpy(), c["out_kv_position"])
+
+
+def run_attention(capi, c, version, record=True):
+    S, Hq, H, D, B = (int(c[k]) for k in ("S", "Hq", "H", "D", "B"))
+    Q = Hq // H
+    bf = bool(c["is_bf16"])
+    q, kc, vc = cu16(c["query"], bf), cu16(c["key_cache"], bf), cu16(c["value_cache"], bf)
+    out = torch.zeros((S, Hq, D), dtype=q.dtype, device="cuda")
+    NB = kc.shape[0]
+    bt, cl = cu(c["block_tables"], torch.int32), cu(c["context_lens"], torch.int32)
+    kp, lp, bl = (cu(c[k], torch.int32) for k in ("kv_position", "last_position", "kv_metric_buffer_len"))
+    slopes = cu(c["alibi_slopes"]) if c["alibi_slopes"].size else None
+    max_ctx = int(c["context_lens"].max())
+    scale = float(c["scale"])
+    if version == "fused":
+        metrics = torch.zeros((NB, B), dtype=torch.float32, device="cuda")
+        capi.paged_attention_fused_metrics(out, metrics, q, kc, vc, H, scale, bt, cl, kp, lp, bl, B,
+                                           max_ctx, slopes)
+        return out.float().cpu().numpy(), metrics.cpu().numpy()
+    metric = torch.full((NB, B, Q), -1.0, dtype=torch.float32, device="cuda")
+    if version == "v1":
+        capi.paged_attention_v1(out, metric, q, kc, vc, H, scale, bt, cl, kp, lp, bl, B, max_ctx,
+                                slopes, record)
+    else:
+        P = (max_ctx + 511) // 512
+        es = torch.empty((S, Hq, P), dtype=torch.float32, device="cuda")
+        ml = torch.empty_like(es)
+        tmp = torch.empty((S, Hq, P, D), dtype=q.dtype, device="cuda")
+        tmpm = torch.empty_like(metric)
+        capi.paged_attention_v2(out, metric, es, ml, tmp, tmpm, q, kc, vc, H, scale, bt, cl, kp, lp,
+                                bl, B, max_ctx, slopes, record)
+    torch.cuda.synchronize()
+    return out.float().cpu().numpy(), metric.cpu().numpy()
+
+
+@pytest.mark.parametrize("version", ["v1", "v2"])
+@pytest.mark.parametrize("name", sorted(ATTN))
+def test_attention_golden(capi, name, version):
+    c = ATTN[name]
+    out, metric = run_attention(capi, c, version)
+    # reference tolerance: tests/kernels/test_kvcompress_attention.py:356-357
+    np.testing.assert_allclose(out, c["out"], atol=1e-3, rtol=1e-5)
+    untouched = c["kv_metric_out"] == -1.0
+    assert ((metric == -1.0) == untouched).all()
+    np.testing.assert_allclose(metric[~untouched], c["kv_metric_out"][~untouched], atol=2e-5, rtol=2e-3)
+
+
+@pytest.mark.parametrize("name", sorted(ATTN))
+def test_attention_fused_metrics_golden(capi, name):
+    c = ATTN[name]
+    out, metrics = run_attention(capi, c, "fused")
+    np.testing.assert_allclose(out, c["out"], atol=1e-3, rtol=1e-5)
+    gm = c["kv_metric_out"].copy()
+    gm[gm == -1.0] = 0.0
+    np.testing.assert_allclose(metrics, (gm ** 2).sum(-1), atol=1e-6, rtol=5e-3)
+
+
+def test_attention_record_off_leaves_metrics_alone(capi):
+    c = ATTN["attn0"]
+    out, metric = run_attention(capi, c, "v1", record=False)
+    np.testing.assert_allclose(out, c["out"], atol=1e-3, rtol=1e-5)
+    assert (metric == -1.0).all()
+
+
+@pytest.mark.parametrize("name", sorted(CACHE))
+def test_k6_golden(capi, name):
+    c = CACHE[name]
+    kc, vc, m = cu16(c["key_cache"], False), cu16(c["value_cache"], False), cu(c["kv_metrics"])
+    capi.reshape_and_cache(cu16(c["key"], False), cu16(c["value"], False), kc, vc, m,
+                           cu(c["slot_mapping"], torch.int64), cu(c["kv_metric_head_bias"]))
+    np.testing.assert_array_equal(bits16(kc), c["out_key_cache"])
+    np.testing.assert_array_equal(bits16(vc), c["out_value_cache"])
+    np.testing.assert_array_equal(m.cpu().numpy(), c["out_kv_metrics"])
+
+
+# ---------------------------------------------------------------------------
+# B. seeded random inputs vs the C oracle (sizes the oracle finishes in seconds)
+# ---------------------------------------------------------------------------
+def k1_case(seed, S, L, H, B, max_blocks, prot, frac, shuffled_pos):
+    from tests.golden.make_golden import build_eviction_inputs  # pure numpy builder
+    rng = np.random.RandomState(seed)
+    hang = rng.randint(1, B + 1, size=(S, L, H))
+    ctx = rng.randint(0, max_blocks + 1, size=(S, L, H)) * B + hang
+    inp = build_eviction_inputs(rng, S, L, H, B, ctx, interleave=True,
+                                position_mode="shuffled" if shuffled_pos else "logical")
+    nblk = (ctx + B - 1) // B
+    inp["last_position"] = np.array([int(ctx[s].max()) - 1 for s in range(S)], np.int32)
+    inp["protected"] = np.full(S, prot, np.int32)
+    inp["budgets"] = np.array([int(nblk[s].sum() * frac) for s in range(S)], np.int32)
+    inp["truncate"] = np.array(1)
+    return inp
+
+
+def oracle_k1(O, c, truncate, evenly=False, control=None):
+    S, L, H, B = int(c["S"]), int(c["L"]), int(c["H"]), int(c["B"])
+    N = int(c["total_kv"])
+    ekv = np.zeros(N, np.int32)
+    elog = np.full(N, -7, np.int32)
+    cnt = np.full((S, L, H), 99, np.int32)
+    rem = c["hanging_token_count"].astype(np.int32).copy()
+    O.schedule_cache_evictions(ekv, elog, cnt, rem, c["evicted_kv_offsets"], c["sorted_indices"],
+                               c["seq_block_offsets"], c["layer_by_block"], c["head_by_block"],
+                               c["virtual_block_num_by_block"], c["budgets"], c["context_lens"],
+                               c["hanging_token_count"], c["kv_position"], c["last_position"],
+                               c["protected"], B, evenly, control, N, MAX_INT, truncate)
+    return ekv, elog, cnt, rem
+
+
+@pytest.mark.parametrize("truncate", [True, False])
+@pytest.mark.parametrize("cfg", [
+    # (seed, S, L, H, B, max_blocks, protected, budget fraction, shuffled positions)
+    (1, 3, 2, 2, 4, 3, 0, 0.5, False),
+    (2, 4, 4, 8, 16, 20, 32, 0.6, False),     # several 1024-entry chunks per sequence, cut mid-chunk
+    (3, 2, 8, 8, 16, 40, 20, 0.9, True),
+    (4, 5, 3, 4, 16, 30, 0, 1.5, False),      # budget never reached: every valid slot is evicted
+    (5, 3, 2, 3, 2, 50, 3, 0.3, True),
+    (6, 6, 4, 2, 1, 300, 5, 0.7, False),      # B=1
+    (7, 1, 32, 8, 16, 12, 32, 0.8, False),    # Llama-3-8B head count (256 bins)
+    (8, 2, 80, 8, 16, 3, 16, 0.5, False),     # Llama-3-70B head count (640 bins)
+])
+def test_k1_random_vs_oracle(capi, O, cfg, truncate):
+    c = k1_case(*cfg)
+    want = oracle_k1(O, c, truncate)
+    got = run_k1(capi, c, truncate=truncate)
+    for w, g, nm in zip(want, got, ("evicted_kv_indices", "evicted_logical_indices", "evicted_kv_count",
+                                    "remaining_kv_count")):
+        np.testing.assert_array_equal(g, w, err_msg=nm)
+
+
+@pytest.mark.parametrize("control", [None, [1]])
+def test_k1_evict_evenly_per_layer(capi, O, control):
+    c = k1_case(11, 3, 4, 3, 1, 200, 4, 0.5, False)
+    c["budgets"] = (c["budgets"] // 4) * 4
+    ctl = None if control is None else np.array(control, np.int32)
+    want = oracle_k1(O, c, True, evenly=True, control=ctl)
+    got = run_k1(capi, c, truncate=True, evenly=True, control=ctl)
+    for w, g in zip(want[:3], got[:3]):
+        np.testing.assert_array_equal(g, w)
+
+
+def test_unsupported_block_size_raises(capi):
+    c = dict(k1_case(1, 1, 1, 1, 4, 2, 0, 0.5, False))
+    c["B"] = np.array(8)
+    with pytest.raises(capi.KvcError, match="Unsupported block size"):
+        run_k1(capi, c)
+
+
+def random_moves_state(seed, S, L, H, B, D, max_blocks, dtype=np.uint16):
+    from tests.golden.make_golden import build_move_inputs
+    return build_move_inputs(np.random.RandomState(seed), S, L, H, B, D, 16 // np.dtype(dtype).itemsize
+                             if D >= 8 else 1, dtype, max_blocks)
+
+
+@pytest.mark.parametrize("cfg", [(21, 4, 4, 8, 16, 128, 30), (22, 2, 2, 4, 16, 128, 200),
+                                 (23, 3, 2, 2, 4, 4, 9), (24, 2, 3, 2, 1, 2, 40)])
+def test_k4_k5_random_vs_oracle(capi, O, cfg):
+    seed, S, L, H, B, D, mb = cfg
+    c = random_moves_state(seed, S, L, H, B, D, mb)
+    N = int(c["total_kv"])
+    wm = np.zeros((N, 2), np.int32)
+    wc = np.zeros((S, L, H), np.int32)
+    O.schedule_cache_moves(wm, wc, c["evicted_logical_indices"], c["evicted_kv_count"],
+                           c["evicted_kv_offsets"], c["block_tables"], c["context_lens_lsh"], B)
+    moves = torch.zeros((N, 2), dtype=torch.int32, device="cuda")
+    mcnt = torch.zeros((S, L, H), dtype=torch.int32, device="cuda")
+    offs = cu(c["evicted_kv_offsets"], torch.int32)
+    capi.schedule_t1_cache_moves(moves, mcnt, cu(c["evicted_logical_indices"], torch.int32),
+                                 cu(c["evicted_kv_count"], torch.int32), offs,
+                                 cu(c["block_tables"], torch.int32), cu(c["context_lens_lsh"], torch.int32), B)
+    np.testing.assert_array_equal(mcnt.cpu().numpy(), wc)
+    np.testing.assert_array_equal(moves.cpu().numpy(), wm)
+    kc, vc = c["k_cache"].copy(), c["v_cache"].copy()
+    km, kp = c["kv_metrics"].copy(), c["kv_position"].copy()
+    O.execute_cache_moves(kc, vc, km, kp, wm, wc, c["evicted_kv_offsets"])
+    gk, gv = torch_cache(c["k_cache"]), torch_cache(c["v_cache"])
+    gm, gp = cu(c["kv_metrics"]), cu(c["kv_position"], torch.int32)
+    capi.execute_cache_moves(gk, gv, gm, gp, moves, mcnt, offs)
+    np.testing.assert_array_equal(cache_bits(gk, c["k_cache"]), kc)
+    np.testing.assert_array_equal(cache_bits(gv, c["v_cache"]), vc)
+    np.testing.assert_array_equal(gm.cpu().numpy(), km)
+    np.testing.assert_array_equal(gp.cpu().numpy(), kp)
+
+
+def test_k2_k3_random_vs_oracle(capi, O):
+    rng = np.random.RandomState(31)
+    S, L, H, B = 5, 4, 8, 16
+    nblk = rng.randint(1, 9, size=(S, L, H))
+    hanging = rng.randint(1, B + 1, size=(S, L, H)).astype(np.int32)
+    alloc = (nblk * B).reshape(-1)
+    offs = np.concatenate([[0], np.cumsum(alloc)[:-1]]).astype(np.int32).reshape(S, L, H)
+    total = int(alloc.sum()) + 777  # slack: the last head's tail runs to max_evicted_kv
+    cnt = np.minimum(rng.randint(0, 9 * B, size=(S, L, H)), nblk * B).astype(np.int32)
+    ekv = rng.randint(0, 1000, size=total).astype(np.int32)
+    elog = rng.randint(0, 1000, size=total).astype(np.int32)
+    w = [ekv.copy(), elog.copy(), cnt.copy()]
+    O.truncate_cache_evictions(w[0], w[1], w[2], offs, hanging, B, total, MAX_INT)
+    g = [cu(ekv), cu(elog), cu(cnt)]
+    capi.truncate_cache_evictions(g[0], g[1], g[2], cu(offs), cu(hanging), B, total, MAX_INT)
+    for a, b in zip(w, g):
+        np.testing.assert_array_equal(b.cpu().numpy(), a)
+    # K3 on V2-format rows
+    logical = np.full(total, MAX_INT, np.int32)
+    for i, (o, n) in enumerate(zip(offs.reshape(-1), nblk.reshape(-1))):
+        e = rng.randint(0, n + 1)
+        logical[o:o + e * B] = rng.randint(0, n * B, size=e * B)
+    wl, wc = logical.copy(), np.zeros((S, L, H), np.int32)
+    O.count_block_evictions(wc, wl, offs, hanging, B, MAX_INT)
+    gl, gc = cu(logical), torch.zeros((S, L, H), dtype=torch.int32, device="cuda")
+    capi.count_block_evictions(gc, gl, cu(offs), cu(hanging), B, MAX_INT)
+    np.testing.assert_array_equal(gc.cpu().numpy(), wc)
+    np.testing.assert_array_equal(gl.cpu().numpy(), wl)
+
+
+def attn_case(seed, S, Hq, H, max_ctx, bf16, alibi, buf, min_ctx=1):
+    rng = np.random.RandomState(seed)
+    g = torch.Generator().manual_seed(seed)
+    D, B, x = 128, 16, 8
+    ctx = rng.randint(min_ctx, max_ctx + 1, size=(S, H)).astype(np.int32)
+    ctx[0, 0] = max_ctx
+    nblk = (ctx + B - 1) // B
+    MB = int(nblk.max()) + 1
+    NB = int(nblk.sum()) + 3
+    phys = rng.permutation(NB)
+    bt = np.zeros((S, H, MB), np.int32)
+    p = 0
+    for s in range(S):
+        for h in range(H):
+            bt[s, h, :nblk[s, h]] = phys[p:p + nblk[s, h]]
+            p += nblk[s, h]
+    dt = torch.bfloat16 if bf16 else torch.float16
+    scale = D ** -0.5
+    mk = lambda shape: (torch.rand(shape, generator=g) * 2 - 1).mul(scale * 4).to(dt)
+    q, kc, vc = mk((S, Hq, D)), mk((NB, D // x, B, x)), mk((NB, D, B))
+    v16 = lambda t: t.view(torch.int16).numpy().view(np.uint16)
+    return dict(S=S, Hq=Hq, H=H, D=D, B=B, is_bf16=int(bf16), scale=np.float32(scale), query=v16(q),
+                key_cache=v16(kc), value_cache=v16(vc), block_tables=bt, context_lens=ctx,
+                kv_position=rng.randint(0, 300, size=(NB, B)).astype(np.int32),
+                last_position=np.full(S, 299, np.int32), kv_metric_buffer_len=np.full(S, buf, np.int32),
+                alibi_slopes=(rng.rand(Hq).astype(np.float32) if alibi else np.zeros(0, np.float32)))
+
+
+@pytest.mark.parametrize("version", ["v1", "v2", "fused"])
+@pytest.mark.parametrize("cfg", [
+    (41, 5, 32, 8, 160, False, False, 0),     # Llama-3-8B GQA group (Q=4), compressed-length contexts
+    (42, 3, 64, 8, 200, True, False, 10),     # Llama-3-70B group (Q=8), bf16
+    (43, 2, 8, 8, 1500, False, True, 0),      # MHA, several partitions, alibi
+    (44, 2, 24, 2, 700, False, False, 50),    # Q=12 (two n-tiles)
+    (45, 4, 4, 4, 17, True, False, 0),        # tiny ragged contexts
+])
+def test_attention_random_vs_oracle(capi, O, cfg, version):
+    c = attn_case(*cfg)
+    S, Hq, H, D, B = (int(c[k]) for k in ("S", "Hq", "H", "D", "B"))
+    Q = Hq // H
+    want = np.zeros((S, Hq, D), np.float32)
+    wmet = np.full((c["key_cache"].shape[0], B, Q), -1.0, np.float32)
+    slopes = c["alibi_slopes"] if c["alibi_slopes"].size else None
+    O.paged_attention_kvc(want, wmet, c["query"], c["key_cache"], c["value_cache"], H, float(c["scale"]),
+                          c["block_tables"], c["context_lens"], c["kv_position"], c["last_position"],
+                          c["kv_metric_buffer_len"], slopes, bool(c["is_bf16"]), True)
+    out, metric = run_attention(capi, c, version)
+    # bf16 output rounding alone is 2^-9 relative; values here are O(0.1)
+    np.testing.assert_allclose(out, want, atol=2e-3 if c["is_bf16"] else 1e-3, rtol=1e-2)
+    if version == "fused":
+        wm = wmet.copy()
+        wm[wm == -1.0] = 0
+        np.testing.assert_allclose(metric, (wm ** 2).sum(-1), atol=1e-6, rtol=1e-2)
+    else:
+        untouched = wmet == -1.0
+        assert ((metric == -1.0) == untouched).all()
+        np.testing.assert_allclose(metric[~untouched], wmet[~untouched], atol=2e-5, rtol=5e-3)
+
+
+def test_k6_random_vs_oracle(capi, O):
+    rng = np.random.RandomState(51)
+    T, H, D, B, x, NB = 37, 8, 128, 16, 8, 64
+    key = rng.randint(0, 65535, size=(T, H, D)).astype(np.uint16)
+    val = rng.randint(0, 65535, size=(T, H, D)).astype(np.uint16)
+    kc = rng.randint(0, 65535, size=(NB, D // x, B, x)).astype(np.uint16)
+    vc = rng.randint(0, 65535, size=(NB, D, B)).astype(np.uint16)
+    m = rng.rand(NB, B).astype(np.float32)
+    bias = rng.rand(H).astype(np.float32)
+    slots = rng.choice(NB * B, T * H, replace=False).astype(np.int64).reshape(T, H)
+    slots[3, :] = -1
+    wk, wv, wm = kc.copy(), vc.copy(), m.copy()
+    O.reshape_and_cache_kvc(key, val, wk, wv, wm, slots, bias)
+    gk, gv, gm = cu16(kc, False), cu16(vc, False), cu(m)
+    capi.reshape_and_cache(cu16(key, False), cu16(val, False), gk, gv, gm, cu(slots, torch.int64), cu(bias))
+    np.testing.assert_array_equal(bits16(gk), wk)
+    np.testing.assert_array_equal(bits16(gv), wv)
+    np.testing.assert_array_equal(gm.cpu().numpy(), wm)
+
+
+# ---------------------------------------------------------------------------
+# C. kernel-vs-kernel against the reference's own CUDA kernels (oracle/_ref)
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [(2, 4, 4, 8, 16, 20, 32, 0.6, False), (7, 1, 32, 8, 16, 12, 32, 0.8, False),
+                                 (3, 2, 8, 8, 16, 40, 20, 0.9, True)])
+def test_k1_vs_reference_cuda(capi, ref_ops, cfg):
+    c = k1_case(*cfg)
+    S, L, H, B = int(c["S"]), int(c["L"]), int(c["H"]), int(c["B"])
+    N = int(c["total_kv"])
+    i = lambda k: cu(c[k], torch.int32)
+    ekv = torch.zeros(N, dtype=torch.int32, device="cuda")
+    elog = torch.full((N,), -7, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros((S, L, H), dtype=torch.int32, device="cuda")
+    rem = i("hanging_token_count")
+    ref_ops.schedule_cache_evictions(ekv, elog, cnt, rem, i("evicted_kv_offsets"), i("sorted_indices"),
+                                     i("seq_block_offsets"), i("layer_by_block"), i("head_by_block"),
+                                     i("virtual_block_num_by_block"), i("budgets"), i("context_lens"),
+                                     i("hanging_token_count"), i("kv_position"), i("last_position"),
+                                     i("protected"), B, False, None, N, MAX_INT, True)
+    torch.cuda.synchronize()
+    got = run_k1(capi, c, truncate=True)
+    np.testing.assert_array_equal(got[0], ekv.cpu().numpy())
+    np.testing.assert_array_equal(got[1], elog.cpu().numpy())
+    np.testing.assert_array_equal(got[2], cnt.cpu().numpy())
+    np.testing.assert_array_equal(got[3], rem.cpu().numpy())
+
+
+def test_k4_k5_vs_reference_cuda(capi, ref_ops):
+    c = random_moves_state(61, 4, 4, 8, 16, 128, 40)
+    S, L, H = c["evicted_kv_count"].shape
+    N, B = int(c["total_kv"]), 16
+    args = [cu(c["evicted_logical_indices"], torch.int32), cu(c["evicted_kv_count"], torch.int32),
+            cu(c["evicted_kv_offsets"], torch.int32), cu(c["block_tables"], torch.int32),
+            cu(c["context_lens_lsh"], torch.int32)]
+    rm, rc = torch.zeros((N, 2), dtype=torch.int32, device="cuda"), torch.zeros((S, L, H), dtype=torch.int32, device="cuda")
+    ref_ops.schedule_t1_cache_moves(rm, rc, *args, B)
+    gm, gc = torch.zeros_like(rm), torch.zeros_like(rc)
+    capi.schedule_t1_cache_moves(gm, gc, *args, B)
+    assert torch.equal(gm, rm) and torch.equal(gc, rc)
+    state = lambda: (torch_cache(c["k_cache"]), torch_cache(c["v_cache"]), cu(c["kv_metrics"]),
+                     cu(c["kv_position"], torch.int32))
+    r, g = state(), state()
+    ref_ops.execute_cache_moves(*r, rm, rc, args[2], 1, 16)
+    capi.execute_cache_moves(*g, gm, gc, args[2])
+    for a, b in zip(r, g):
+        assert torch.equal(a.view(torch.int16) if a.dtype == torch.float16 else a,
+                           b.view(torch.int16) if b.dtype == torch.float16 else b)
+
+
+@pytest.mark.parametrize("version", ["v1", "v2"])
+@pytest.mark.parametrize("cfg", [(41, 5, 32, 8, 160, False, False, 0), (42, 3, 64, 8, 200, True, False, 0),
+                                 (43, 2, 8, 8, 1500, False, True, 0)])
+def test_attention_vs_reference_cuda(capi, ref_ops, cfg, version):
+    c = attn_case(*cfg)
+    S, Hq, H, D, B = (int(c[k]) for k in ("S", "Hq", "H", "D", "B"))
+    Q = Hq // H
+    bf = bool(c["is_bf16"])
+    q, kc, vc = cu16(c["query"], bf), cu16(c["key_cache"], bf), cu16(c["value_cache"], bf)
+    NB = kc.shape[0]
+    bt, cl = cu(c["block_tables"], torch.int32), cu(c["context_lens"], torch.int32)
+    kp, lp, bl = (cu(c[k], torch.int32) for k in ("kv_position", "last_position", "kv_metric_buffer_len"))
+    slopes = cu(c["alibi_slopes"]) if c["alibi_slopes"].size else None
+    max_ctx = int(c["context_lens"].max())
+    rout = torch.zeros((S, Hq, D), dtype=q.dtype, device="cuda")
+    rmet = torch.full((NB, B, Q), -1.0, dtype=torch.float32, device="cuda")
+    if version == "v1":
+        ref_ops.kvcompress_paged_attention_v1(rout, rmet, q, kc, vc, H, float(c["scale"]), bt, cl, kp, lp, bl,
+                                              B, max_ctx, slopes, "auto", 1.0, 1.0, True)
+    else:
+        P = (max_ctx + 511) // 512
+        es = torch.empty((S, Hq, P), dtype=torch.float32, device="cuda")
+        ml = torch.empty_like(es)
+        tmp = torch.empty((S, Hq, P, D), dtype=q.dtype, device="cuda")
+        tmpm = torch.zeros_like(rmet)
+        ref_ops.kvcompress_paged_attention_v2(rout, rmet, es, ml, tmp, tmpm, q, kc, vc, H, float(c["scale"]),
+                                              bt, cl, kp, lp, bl, B, max_ctx, slopes, "auto", 1.0, 1.0, True)
+    torch.cuda.synchronize()
+    out, metric = run_attention(capi, c, version)
+    np.testing.assert_allclose(out, rout.float().cpu().numpy(), atol=1e-3, rtol=1e-2)
+    rm = rmet.cpu().numpy()
+    assert ((metric == -1.0) == (rm == -1.0)).all()
+    np.testing.assert_allclose(metric, rm, atol=2e-5, rtol=5e-3)

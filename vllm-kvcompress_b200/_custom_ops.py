@@ -1,0 +1,142 @@
+"""Python op shim with the reference's names, argument order and pre-processing.
+
+Mirror of the KV-Compress part of the reference's vllm/_custom_ops.py
+(paged_attention_kvc_v1/v2 :135-203, reshape_and_cache_kvc :641-658,
+schedule_cache_evictions :934-1006, count_block_evictions :1065-1086,
+schedule_cache_moves :1158-1179, execute_cache_moves :1220-1256): callers in
+vllm/kvcompress/{metrics,scheduler}.py, vllm/worker/cache_engine.py and
+vllm/attention/ops/paged_attn.py can import these instead.  The ops resolve to
+torch.ops._C / _C_cache_ops / _C_kvc_ops registered by this package's _C.so, i.e. to
+the sm_100a kernels; there is no Python / CPU fallback (the reference keeps slow
+``ref_*`` Python twins next to each wrapper -- here those live in oracle/ and are
+test-only).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import native
+
+native.load_torch_ops()
+
+MAX_INT = 2147483000  # vllm/_custom_ops.py:773
+
+
+def paged_attention_kvc_v1(out, kv_metric_out, query, key_cache, value_cache, num_kv_heads: int,
+                           scale: float, block_tables, context_lens, kv_position, last_position,
+                           kv_metric_buffer_len, block_size: int, max_context_len: int,
+                           alibi_slopes: Optional[torch.Tensor], kv_cache_dtype: str,
+                           k_scale: float, v_scale: float, record_kv_metrics: bool) -> None:
+    """reference vllm/_custom_ops.py:135-163"""
+    torch.ops._C.kvcompress_paged_attention_v1(
+        out, kv_metric_out, query, key_cache, value_cache, num_kv_heads, scale, block_tables,
+        context_lens, kv_position, last_position, kv_metric_buffer_len, block_size,
+        max_context_len, alibi_slopes, kv_cache_dtype, k_scale, v_scale, record_kv_metrics)
+
+
+def paged_attention_kvc_v2(out, kv_metric_out, exp_sum, max_logits, tmp_out, tmp_kv_metric_out,
+                           query, key_cache, value_cache, num_kv_heads: int, scale: float,
+                           block_tables, context_lens, kv_position, last_position,
+                           kv_metric_buffer_len, block_size: int, max_context_len: int,
+                           alibi_slopes: Optional[torch.Tensor], kv_cache_dtype: str,
+                           k_scale: float, v_scale: float, record_kv_metrics: bool) -> None:
+    """reference vllm/_custom_ops.py:166-203"""
+    torch.ops._C.kvcompress_paged_attention_v2(
+        out, kv_metric_out, exp_sum, max_logits, tmp_out, tmp_kv_metric_out, query, key_cache,
+        value_cache, num_kv_heads, scale, block_tables, context_lens, kv_position, last_position,
+        kv_metric_buffer_len, block_size, max_context_len, alibi_slopes, kv_cache_dtype, k_scale,
+        v_scale, record_kv_metrics)
+
+
+def paged_attention_kvc_fused_metrics(out, kv_metrics, query, key_cache, value_cache,
+                                      num_kv_heads: int, scale: float, block_tables, context_lens,
+                                      kv_position, last_position, kv_metric_buffer_len,
+                                      block_size: int, max_context_len: int,
+                                      alibi_slopes: Optional[torch.Tensor] = None,
+                                      kv_cache_dtype: str = "auto") -> None:
+    """ADDITIVE op: attention + `metrics += sum_q p^2` in one launch; replaces
+    clear_temp_metrics / record / aggregate_decode (vllm/kvcompress/metrics.py:337-342,
+    429-439; engine call sites llm_engine.py:1621-1634)."""
+    torch.ops._C.kvcompress_paged_attention_fused_metrics(
+        out, kv_metrics, query, key_cache, value_cache, num_kv_heads, scale, block_tables,
+        context_lens, kv_position, last_position, kv_metric_buffer_len, block_size,
+        max_context_len, alibi_slopes, kv_cache_dtype)
+
+
+def reshape_and_cache_kvc(key, value, key_cache, value_cache, kv_metrics, slot_mapping,
+                          kv_metric_head_bias, kv_cache_dtype: str, k_scale: float,
+                          v_scale: float) -> None:
+    """reference vllm/_custom_ops.py:641-658"""
+    torch.ops._C_cache_ops.kvcompress_reshape_and_cache(
+        key, value, key_cache, value_cache, kv_metrics, slot_mapping, kv_metric_head_bias,
+        kv_cache_dtype, k_scale, v_scale)
+
+
+def schedule_cache_evictions(out_evicted_kv_indices, out_evicted_logical_indices,
+                             out_evicted_kv_count, out_evicted_kv_offsets, sorted_indices,
+                             seq_block_offsets, layer_by_block, head_by_block,
+                             logical_block_num_by_block, evicted_blocks_per_seq, context_lens,
+                             hanging_token_count, kv_position, last_position,
+                             protected_window_size, block_size: int, max_evicted_kv: int,
+                             null_eviction_index: int, truncate: bool,
+                             evict_evenly_per_layer: bool = False,
+                             control_layers: Optional[torch.Tensor] = None) -> None:
+    """reference vllm/_custom_ops.py:934-1006 (same pre-processing: zero the head-index
+    buffer, clone hanging counts as the scratch counter, transpose context_lens [L,S,H] ->
+    [S,L,H], cast index tensors to int32)."""
+    if evict_evenly_per_layer and block_size > 1:
+        raise RuntimeError(
+            f"cannot evict evenly across layers when block_size > 1 (got {block_size=})")
+    out_evicted_kv_indices.zero_()
+    torch.ops._C_kvc_ops.schedule_cache_evictions(
+        out_evicted_kv_indices, out_evicted_logical_indices, out_evicted_kv_count,
+        hanging_token_count.clone(), out_evicted_kv_offsets,
+        sorted_indices.type(torch.int).contiguous(), seq_block_offsets.type(torch.int).contiguous(),
+        layer_by_block.contiguous(), head_by_block.contiguous(),
+        logical_block_num_by_block.contiguous(), evicted_blocks_per_seq.contiguous(),
+        context_lens.transpose(0, 1).contiguous(), hanging_token_count.contiguous(),
+        kv_position.type(torch.int).contiguous(), last_position.type(torch.int),
+        protected_window_size, block_size, evict_evenly_per_layer, control_layers, max_evicted_kv,
+        null_eviction_index, truncate)
+
+
+def truncate_cache_evictions(evicted_kv_indices, evicted_logical_indices, evicted_kv_count,
+                             evicted_kv_offsets, hanging_token_count, block_size: int,
+                             max_evicted_kv: int, null_eviction_index: int) -> None:
+    """op csrc/torch_bindings.cpp:389-394 (the reference has no Python wrapper for it)"""
+    torch.ops._C_kvc_ops.truncate_cache_evictions(
+        evicted_kv_indices, evicted_logical_indices, evicted_kv_count, evicted_kv_offsets,
+        hanging_token_count, block_size, max_evicted_kv, null_eviction_index)
+
+
+def count_block_evictions(evicted_block_count, evicted_logical_indices, evicted_kv_offsets,
+                          hanging_token_count, block_size: int, null_value: int,
+                          evicted_blocks_per_seq: Optional[torch.Tensor] = None) -> None:
+    """reference vllm/_custom_ops.py:1065-1086.  NB: like the reference, a non-contiguous
+    evicted_logical_indices would be updated on a temporary copy."""
+    torch.ops._C_kvc_ops.count_block_evictions(
+        evicted_block_count, evicted_logical_indices.contiguous(), evicted_kv_offsets.contiguous(),
+        hanging_token_count.contiguous(), block_size, null_value)
+
+
+def schedule_cache_moves(out_cache_moves_indices, out_cache_moves_count, evicted_logical_indices,
+                         evicted_kv_count, evicted_kv_offsets, block_tables, context_lens,
+                         block_size: int) -> None:
+    """reference vllm/_custom_ops.py:1158-1179 (zero-fills the move workspace first)"""
+    out_cache_moves_indices.fill_(0)
+    torch.ops._C_kvc_ops.schedule_t1_cache_moves(
+        out_cache_moves_indices, out_cache_moves_count, evicted_logical_indices.contiguous(),
+        evicted_kv_count.contiguous(), evicted_kv_offsets.contiguous(), block_tables.contiguous(),
+        context_lens.contiguous(), block_size)
+
+
+def execute_cache_moves(k_cache, v_cache, kv_metrics, kv_position, cache_moves_indices,
+                        cache_moves_count, evicted_kv_offsets, blocks_per_head: int,
+                        threads_per_head: int) -> None:
+    """reference vllm/_custom_ops.py:1220-1256"""
+    torch.ops._C_kvc_ops.execute_cache_moves(
+        k_cache, v_cache, kv_metrics, kv_position, cache_moves_indices.contiguous(),
+        cache_moves_count.contiguous(), evicted_kv_offsets.contiguous(), blocks_per_head,
+        threads_per_head)

@@ -1,0 +1,176 @@
+"""ctypes view of the C ABI (include/kvc_b200.h) operating on torch CUDA tensors.
+
+This is the raw boundary a non-torch host (cgo / JNI / plain C) would bind; the parity
+tests call the kernels through it.  Tensors are only used for their data_ptr(), shape and
+the current CUDA stream."""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import native
+
+KVC_F16, KVC_BF16, KVC_F32, KVC_U8 = 0, 1, 2, 3
+_DT = {torch.float16: KVC_F16, torch.bfloat16: KVC_BF16, torch.float32: KVC_F32,
+       torch.uint8: KVC_U8, torch.float8_e5m2: KVC_U8}
+
+
+class KvcError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"kvc status {status}: {message}")
+        self.status = status
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise KvcError(rc, native.load_lib().kvc_last_error().decode())
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _i32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.int32 or not t.is_contiguous() or not t.is_cuda:
+        raise TypeError(f"{name} must be a contiguous int32 CUDA tensor")
+    return t
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def abi_version() -> int:
+    return int(native.load_lib().kvc_abi_version())
+
+
+def schedule_cache_evictions(evicted_kv_indices, evicted_logical_indices, evicted_kv_count,
+                             remaining_kv_count, evicted_kv_offsets, sorted_indices,
+                             seq_block_offsets, layer_by_block, head_by_block,
+                             virtual_block_num_by_block, evicted_blocks_per_seq, context_lens,
+                             hanging_token_count, kv_position, last_position,
+                             protected_window_size, block_size, evict_evenly_per_layer,
+                             control_layers, max_evicted_kv, null_eviction_index, truncate):
+    lib = native.load_lib()
+    S, L, H = evicted_kv_count.shape
+    total_blocks = layer_by_block.shape[0]
+    nbytes = lib.kvc_schedule_cache_evictions_workspace_bytes(S, L, H, total_blocks, block_size)
+    ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=evicted_kv_count.device)
+    ts = [evicted_kv_indices, evicted_logical_indices, evicted_kv_count, remaining_kv_count,
+          evicted_kv_offsets, sorted_indices, seq_block_offsets, layer_by_block, head_by_block,
+          virtual_block_num_by_block, evicted_blocks_per_seq, context_lens, hanging_token_count,
+          kv_position, last_position, protected_window_size]
+    for i, t in enumerate(ts):
+        _i32(t, f"arg{i}")
+    ncl = 0 if control_layers is None else control_layers.numel()
+    _check(lib.kvc_schedule_cache_evictions(
+        *[_ptr(t) for t in ts], S, L, H, total_blocks, block_size, int(evict_evenly_per_layer),
+        _ptr(control_layers), ncl, max_evicted_kv, null_eviction_index, int(truncate),
+        _ptr(ws), ctypes.c_size_t(ws.numel()), _stream()))
+
+
+def truncate_cache_evictions(evicted_kv_indices, evicted_logical_indices, evicted_kv_count,
+                             evicted_kv_offsets, hanging_token_count, block_size, max_evicted_kv,
+                             null_eviction_index):
+    S, L, H = evicted_kv_count.shape
+    _check(native.load_lib().kvc_truncate_cache_evictions(
+        _ptr(_i32(evicted_kv_indices, "evicted_kv_indices")),
+        _ptr(_i32(evicted_logical_indices, "evicted_logical_indices")),
+        _ptr(_i32(evicted_kv_count, "evicted_kv_count")), _ptr(_i32(evicted_kv_offsets, "evicted_kv_offsets")),
+        _ptr(_i32(hanging_token_count, "hanging_token_count")), S, L, H, block_size, max_evicted_kv,
+        null_eviction_index, _stream()))
+
+
+def count_block_evictions(evicted_block_count, evicted_logical_indices, evicted_kv_offsets,
+                          hanging_token_count, block_size, null_value):
+    S, L, H = evicted_block_count.shape
+    _check(native.load_lib().kvc_count_block_evictions(
+        _ptr(_i32(evicted_block_count, "evicted_block_count")),
+        _ptr(_i32(evicted_logical_indices, "evicted_logical_indices")),
+        _ptr(_i32(evicted_kv_offsets, "evicted_kv_offsets")),
+        _ptr(_i32(hanging_token_count, "hanging_token_count")), S, L, H,
+        evicted_logical_indices.numel(), block_size, null_value, _stream()))
+
+
+def schedule_t1_cache_moves(cache_moves_idx, cache_moves_count, evicted_logical_indices,
+                            evicted_kv_count, evicted_kv_offsets, block_tables, context_lens,
+                            block_size):
+    S, L, H = evicted_kv_count.shape
+    _check(native.load_lib().kvc_schedule_t1_cache_moves(
+        _ptr(_i32(cache_moves_idx, "cache_moves_idx")), _ptr(_i32(cache_moves_count, "cache_moves_count")),
+        _ptr(_i32(evicted_logical_indices, "evicted_logical_indices")),
+        _ptr(_i32(evicted_kv_count, "evicted_kv_count")), _ptr(_i32(evicted_kv_offsets, "evicted_kv_offsets")),
+        _ptr(_i32(block_tables, "block_tables")), _ptr(_i32(context_lens, "context_lens")), S, L, H,
+        block_tables.shape[3], block_size, _stream()))
+
+
+def execute_cache_moves(k_cache, v_cache, kv_metrics, kv_position, cache_moves_idx,
+                        cache_moves_count, evicted_kv_offsets, blocks_per_head=1,
+                        threads_per_head=16):
+    S, L, H = cache_moves_count.shape
+    NB, D, B = v_cache.shape
+    assert k_cache.is_contiguous() and v_cache.is_contiguous() and kv_metrics.dtype == torch.float32
+    _check(native.load_lib().kvc_execute_cache_moves(
+        _ptr(k_cache), _ptr(v_cache), _ptr(kv_metrics), _ptr(_i32(kv_position, "kv_position")),
+        _ptr(_i32(cache_moves_idx, "cache_moves_idx")), _ptr(_i32(cache_moves_count, "cache_moves_count")),
+        _ptr(_i32(evicted_kv_offsets, "evicted_kv_offsets")), S, L, H, ctypes.c_int64(NB), D,
+        k_cache.shape[3], B, _DT[k_cache.dtype], blocks_per_head, threads_per_head, _stream()))
+
+
+def reshape_and_cache(key, value, key_cache, value_cache, kv_metrics, slot_mapping,
+                      kv_metric_head_bias):
+    T, H, D = key.shape
+    assert slot_mapping.dtype == torch.int64 and slot_mapping.is_contiguous()
+    _check(native.load_lib().kvc_reshape_and_cache(
+        _ptr(key), _ptr(value), _ptr(key_cache), _ptr(value_cache), _ptr(kv_metrics),
+        _ptr(slot_mapping), _ptr(kv_metric_head_bias), T, H, D, key_cache.shape[2],
+        key_cache.shape[3], ctypes.c_int64(key.stride(0)), ctypes.c_int64(value.stride(0)),
+        _DT[key_cache.dtype], _stream()))
+
+
+def _attn_args(query, key_cache, value_cache, num_kv_heads, scale, block_tables, context_lens,
+               kv_position, last_position, kv_metric_buffer_len, block_size, max_context_len,
+               alibi_slopes):
+    S, Hq, D = query.shape
+    return [_ptr(query), _ptr(key_cache), _ptr(value_cache), S, Hq, num_kv_heads, D,
+            ctypes.c_float(scale), _ptr(_i32(block_tables, "block_tables")),
+            _ptr(_i32(context_lens, "context_lens")), _ptr(_i32(kv_position, "kv_position")),
+            _ptr(_i32(last_position, "last_position")),
+            _ptr(_i32(kv_metric_buffer_len, "kv_metric_buffer_len")), block_size, max_context_len,
+            block_tables.shape[2], ctypes.c_int64(query.stride(0)), ctypes.c_int64(key_cache.stride(0)),
+            _ptr(alibi_slopes), _DT[query.dtype]]
+
+
+def paged_attention_v1(out, kv_metric_out, query, key_cache, value_cache, num_kv_heads, scale,
+                       block_tables, context_lens, kv_position, last_position,
+                       kv_metric_buffer_len, block_size, max_context_len, alibi_slopes,
+                       record_kv_metrics):
+    a = _attn_args(query, key_cache, value_cache, num_kv_heads, scale, block_tables, context_lens,
+                   kv_position, last_position, kv_metric_buffer_len, block_size, max_context_len,
+                   alibi_slopes)
+    _check(native.load_lib().kvc_paged_attention_v1(_ptr(out), _ptr(kv_metric_out), *a,
+                                                    int(record_kv_metrics), _stream()))
+
+
+def paged_attention_v2(out, kv_metric_out, exp_sums, max_logits, tmp_out, tmp_kv_metric_out, query,
+                       key_cache, value_cache, num_kv_heads, scale, block_tables, context_lens,
+                       kv_position, last_position, kv_metric_buffer_len, block_size,
+                       max_context_len, alibi_slopes, record_kv_metrics):
+    a = _attn_args(query, key_cache, value_cache, num_kv_heads, scale, block_tables, context_lens,
+                   kv_position, last_position, kv_metric_buffer_len, block_size, max_context_len,
+                   alibi_slopes)
+    _check(native.load_lib().kvc_paged_attention_v2(
+        _ptr(out), _ptr(kv_metric_out), _ptr(exp_sums), _ptr(max_logits), _ptr(tmp_out),
+        _ptr(tmp_kv_metric_out), *a, int(record_kv_metrics), _stream()))
+
+
+def paged_attention_fused_metrics(out, kv_metrics, query, key_cache, value_cache, num_kv_heads,
+                                  scale, block_tables, context_lens, kv_position, last_position,
+                                  kv_metric_buffer_len, block_size, max_context_len, alibi_slopes):
+    a = _attn_args(query, key_cache, value_cache, num_kv_heads, scale, block_tables, context_lens,
+                   kv_position, last_position, kv_metric_buffer_len, block_size, max_context_len,
+                   alibi_slopes)
+    _check(native.load_lib().kvc_paged_attention_fused_metrics(_ptr(out), _ptr(kv_metrics), *a,
+                                                               _stream()))

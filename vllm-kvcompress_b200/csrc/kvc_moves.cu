@@ -1,0 +1,288 @@
+// K5 execute_cache_moves: the paged K/V gather -> compact.
+// reference: csrc/kvcompress_eviction_kernels.cu:359-435 (kernel), :858-929 (launcher)
+//
+// Layout (one physical block = B tokens of ONE kv head, B=16, D=128, 2-byte cache):
+//   K block [16 j][16 t][8 elem]  -> a token's K = 16 chunks of 16 B at 256 B stride
+//   V block [128 d][16 t]         -> a token's V = 128 x 2 B at 32 B stride, i.e. one
+//                                    element in each of the block's 128 sectors
+// so touching ONE token touches the whole 4 KB V block in DRAM.  The reference moves a
+// token with 256+ scalar 2-byte loads and stores per thread; every V store is a 2-byte
+// partial write of its own 32 B sector (128 sector writes per moved token).
+//
+// Here the unit of work is a *run*: the consecutive moves of a head that land in the
+// same destination block (schedule_t1_cache_moves emits dst ascending, so they are
+// adjacent; <= 16 per run).  One warp owns a run, no shared memory, no barriers:
+//   - V: lane <-> rows d = lane + 32 r.  The lane gathers its 4 rows of every source
+//     token of the run into registers (4 x 16 tokens x 2 B), which is exactly the
+//     destination rows it owns, and writes them back as whole 32 B rows (two 16 B
+//     stores, consecutive lanes -> consecutive rows -> 1 KB per instruction pair).
+//     Partially covered rows are written with the widest aligned pieces the run's
+//     token mask allows (8/4/2 B); only owned bytes are ever written, so there is no
+//     read-modify-write of the destination and no hazard between runs.
+//   - K: half-warp <-> the 16 chunks of one token, 16 B load + 16 B store per lane.
+//   - metric (f32) and position (i32): lanes 0-15 / 16-31, one element each.
+// Algorithmic bytes per move: 2*(2*128*2 + 4 + 4) + 8 = 1048.
+// Physical floor: >= 4 KB (whole V block) + 16 half-sectors of K per isolated source token.
+#include "kvc_common.cuh"
+
+namespace kvc {
+
+// -----------------------------------------------------------------------------
+// production layout: B=16, D=128, 2-byte elements, x=8
+// -----------------------------------------------------------------------------
+constexpr int kMovesPerSegment = 32;
+constexpr int kMoveWarps = 4;
+
+__device__ __forceinline__ void store_v_row_partial(uint16_t* __restrict__ row, const uint32_t (&w)[8],
+                                                    unsigned mask) {
+  // row: 16 tokens x 2 B of one d; write only tokens in `mask`, widest aligned pieces first
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {  // quads of tokens = 8 B
+    const unsigned mq = (mask >> (4 * q)) & 0xfu;
+    if (mq == 0xfu) {
+      *reinterpret_cast<uint2*>(row + 4 * q) = make_uint2(w[2 * q], w[2 * q + 1]);
+    } else {
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {  // pairs = 4 B
+        const unsigned mp = (mq >> (2 * p)) & 0x3u;
+        const uint32_t word = w[2 * q + p];
+        if (mp == 0x3u) {
+          *reinterpret_cast<uint32_t*>(row + 4 * q + 2 * p) = word;
+        } else if (mp == 0x1u) {
+          row[4 * q + 2 * p] = (uint16_t)(word & 0xffffu);
+        } else if (mp == 0x2u) {
+          row[4 * q + 2 * p + 1] = (uint16_t)(word >> 16);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_kernel(
+    uint16_t* __restrict__ k_cache,        // [NB, 16, 16, 8]
+    uint16_t* __restrict__ v_cache,        // [NB, 128, 16]
+    float* __restrict__ kv_metrics,        // [NB, 16]
+    int* __restrict__ kv_position,         // [NB, 16]
+    const int2* __restrict__ moves,        // [max_evicted_kv] (dst, src)
+    const int* __restrict__ move_count,    // [S*L*H]
+    const int* __restrict__ move_offsets,  // [S*L*H]
+    int total_heads) {
+  constexpr int B = 16, D = 128;
+  constexpr int kBlockElems = B * D;  // 2048 two-byte elements = 4 KB
+  const int g = blockIdx.x;
+  if (g >= total_heads) return;
+  const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int cnt = move_count[g];
+  const int off = move_offsets[g];
+  const int nseg = (cnt + kMovesPerSegment - 1) / kMovesPerSegment;
+  const int2* __restrict__ mv = moves + off;
+
+  for (int seg = blockIdx.y * kMoveWarps + wid; seg < nseg; seg += gridDim.y * kMoveWarps) {
+    const int base = seg * kMovesPerSegment;
+    // window of 48 moves: [base, base+32) in `a`, lookahead [base+32, base+48) in `la`
+    const bool a_ok = base + lane < cnt;
+    const int2 a = a_ok ? mv[base + lane] : make_int2(-1, -1);
+    const bool la_ok = (lane < 16) && (base + 32 + lane < cnt);
+    const int2 la = la_ok ? mv[base + 32 + lane] : make_int2(-1, -1);
+    const int a_blk = a_ok ? (a.x >> 4) : -1;
+    const int la_blk = la_ok ? (la.x >> 4) : -2;
+    int prev_blk = __shfl_up_sync(0xffffffffu, a_blk, 1);
+    if (lane == 0) prev_blk = (base > 0) ? (mv[base - 1].x >> 4) : -3;
+    unsigned starts = __ballot_sync(0xffffffffu, a_ok && a_blk != prev_blk);
+
+    while (starts) {  // warp-uniform loop over the runs that START in this segment
+      const int l0 = __ffs(starts) - 1;
+      starts &= starts - 1;
+      const int run_blk = __shfl_sync(0xffffffffu, a_blk, l0);
+      // contiguous members: lanes [l0, end1) of `a`, then a prefix of `la` if the run reaches lane 31
+      const unsigned same_a = __ballot_sync(0xffffffffu, a_ok && a_blk == run_blk);
+      const unsigned from_l0 = same_a >> l0;                       // bit 0 = lane l0
+      const int len1 = (from_l0 == 0xffffffffu >> l0) ? (32 - l0) : __ffs(~from_l0) - 1;
+      const bool in1 = lane >= l0 && lane < l0 + len1;
+      int len2 = 0;
+      if (l0 + len1 == 32) {
+        const unsigned same_la = __ballot_sync(0xffffffffu, la_ok && la_blk == run_blk);
+        len2 = (same_la == 0xffffffffu) ? 32 : __ffs(~same_la) - 1;
+      }
+      const bool in2 = lane < len2;
+
+      // per destination offset o: source slot (warp-uniform) or -1
+      int src[16];
+      unsigned mask = 0;
+#pragma unroll
+      for (int o = 0; o < 16; ++o) {
+        const unsigned c1 = __ballot_sync(0xffffffffu, in1 && (a.x & 15) == o);
+        const unsigned c2 = __ballot_sync(0xffffffffu, in2 && (la.x & 15) == o);
+        const int s1 = __shfl_sync(0xffffffffu, a.y, c1 ? __ffs(c1) - 1 : 0);
+        const int s2 = __shfl_sync(0xffffffffu, la.y, c2 ? __ffs(c2) - 1 : 0);
+        src[o] = c1 ? s1 : (c2 ? s2 : -1);
+        mask |= (c1 | c2) ? (1u << o) : 0u;
+      }
+
+      // ---- metric + position: lanes 0-15 metric, 16-31 position ----
+      {
+        const int o = lane & 15;
+        int s = src[0];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) s = (o == i) ? src[i] : s;
+        if (s >= 0) {
+          const int64_t dslot = (int64_t)run_blk * B + o;
+          if (lane < 16) kv_metrics[dslot] = kv_metrics[s];   // reference :410
+          else           kv_position[dslot] = kv_position[s]; // reference :411
+        }
+      }
+
+      // ---- V gather into registers: lane owns rows d = lane + 32 r ----
+      uint32_t w[4][8];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[r][i] = 0u;
+#pragma unroll
+      for (int o = 0; o < 16; ++o) {
+        const int s = src[o];
+        if (s >= 0) {  // warp-uniform
+          const uint16_t* __restrict__ sp =
+              v_cache + (int64_t)(s >> 4) * kBlockElems + (s & 15) + lane * B;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const uint32_t x = sp[r * 32 * B];  // reference :426-431, element d = lane + 32 r
+            w[r][o >> 1] |= (o & 1) ? (x << 16) : x;
+          }
+        }
+      }
+
+      // ---- K: half-warp per token, lane j copies one 16 B chunk (reference :413-424) ----
+      {
+        const int half = lane >> 4, j = lane & 15;
+        uint4 kv[8];
+        bool kp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int s = half ? src[2 * i + 1] : src[2 * i];
+          kp[i] = s >= 0;
+          if (kp[i])
+            kv[i] = ld_stream16(k_cache + (int64_t)(s >> 4) * kBlockElems + j * (B * 8) + (s & 15) * 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (kp[i])
+            st_stream16(k_cache + (int64_t)run_blk * kBlockElems + j * (B * 8) + (2 * i + half) * 8, kv[i]);
+        }
+      }
+
+      // ---- V write-back: whole rows when the run covers all 16 tokens ----
+      uint16_t* __restrict__ dp = v_cache + (int64_t)run_blk * kBlockElems + lane * B;
+      if (mask == 0xffffu) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          uint4* row = reinterpret_cast<uint4*>(dp + r * 32 * B);
+          st_stream16(row, make_uint4(w[r][0], w[r][1], w[r][2], w[r][3]));
+          st_stream16(row + 1, make_uint4(w[r][4], w[r][5], w[r][6], w[r][7]));
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) store_v_row_partial(dp + r * 32 * B, w[r], mask);
+      }
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------
+// generic shapes (the reference's test sizes: D in {1,2,4,128}, x in {1,2,8},
+// B in {1,2,4,16}, 1/2/4-byte elements): one warp per move, element-wise copy.
+// -----------------------------------------------------------------------------
+template <typename T>
+__global__ void execute_moves_generic_kernel(T* __restrict__ k_cache, T* __restrict__ v_cache,
+                                             float* __restrict__ kv_metrics,
+                                             int* __restrict__ kv_position,
+                                             const int2* __restrict__ moves,
+                                             const int* __restrict__ move_count,
+                                             const int* __restrict__ move_offsets,
+                                             int total_heads, int D, int x, int B) {
+  const int g = blockIdx.x;
+  if (g >= total_heads) return;
+  const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int nw = blockDim.x / kWarp;
+  const int cnt = move_count[g];
+  const int off = move_offsets[g];
+  const int64_t block_stride = (int64_t)B * D;
+  for (int i = blockIdx.y * nw + wid; i < cnt; i += gridDim.y * nw) {
+    const int2 m = moves[off + i];
+    const int64_t sb = (int64_t)(m.y / B) * block_stride, db = (int64_t)(m.x / B) * block_stride;
+    const int so = m.y % B, dof = m.x % B;
+    if (lane == 0) kv_metrics[m.x] = kv_metrics[m.y];
+    if (lane == 1 || kWarp == 1) kv_position[m.x] = kv_position[m.y];
+    for (int e = lane; e < D; e += kWarp) {
+      const int j = e / x, kk = e % x;
+      k_cache[db + (int64_t)j * B * x + dof * x + kk] = k_cache[sb + (int64_t)j * B * x + so * x + kk];
+      v_cache[db + (int64_t)e * B + dof] = v_cache[sb + (int64_t)e * B + so];
+    }
+  }
+}
+
+}  // namespace kvc
+
+using namespace kvc;
+
+extern "C" int kvc_execute_cache_moves(
+    void* k_cache, void* v_cache, float* kv_metrics, int* kv_position,
+    const int* cache_moves_idx, const int* cache_moves_count, const int* evicted_kv_offsets,
+    int num_seqs, int num_layers, int num_kv_heads, int64_t num_blocks, int head_size,
+    int vec_size, int block_size, int dtype, int blocks_per_head, int threads_per_head,
+    kvc_stream_t stream) {
+  (void)blocks_per_head;
+  (void)threads_per_head;  // launch hints in the reference; results never depend on them
+  (void)num_blocks;
+  // reference dispatch: head size :840-856, vec size :826-838, block size :808-824, dtype :917-927
+  KVC_REQUIRE(head_size == 1 || head_size == 2 || head_size == 4 || head_size == 128,
+              KVC_ERR_UNSUPPORTED, "Unsupported head size: %d", head_size);
+  KVC_REQUIRE(vec_size == 1 || vec_size == 2 || vec_size == 8, KVC_ERR_UNSUPPORTED,
+              "Unsupported vec size: %d", vec_size);
+  KVC_REQUIRE(block_size == 1 || block_size == 2 || block_size == 4 || block_size == 16,
+              KVC_ERR_UNSUPPORTED, "Unsupported block size: %d", block_size);
+  KVC_REQUIRE(dtype == KVC_F16 || dtype == KVC_BF16 || dtype == KVC_F32 || dtype == KVC_U8,
+              KVC_ERR_UNSUPPORTED, "Unsupported data type: %d", dtype);
+  KVC_REQUIRE(k_cache && v_cache && kv_metrics && kv_position && cache_moves_idx &&
+                  cache_moves_count && evicted_kv_offsets,
+              KVC_ERR_INVALID, "execute_cache_moves: null tensor");
+  KVC_REQUIRE((reinterpret_cast<uintptr_t>(cache_moves_idx) & 7) == 0, KVC_ERR_INVALID,
+              "execute_cache_moves: cache_moves_idx must be 8-byte aligned");
+  KVC_REQUIRE(head_size % vec_size == 0 || head_size < vec_size, KVC_ERR_INVALID,
+              "execute_cache_moves: head size %d not divisible by vec size %d", head_size, vec_size);
+  const int total_heads = num_seqs * num_layers * num_kv_heads;
+  if (total_heads <= 0) return KVC_OK;
+  cudaStream_t st = as_stream(stream);
+  const int2* mv = reinterpret_cast<const int2*>(cache_moves_idx);
+  // enough CTAs per head to fill 148 SMs several times over when there are few heads
+  int gy = (148 * 16 + total_heads - 1) / total_heads;
+  gy = gy < 1 ? 1 : (gy > 64 ? 64 : gy);
+  const bool two_byte = (dtype == KVC_F16 || dtype == KVC_BF16);
+  if (two_byte && head_size == 128 && vec_size == 8 && block_size == 16 &&
+      (reinterpret_cast<uintptr_t>(k_cache) & 15) == 0 && (reinterpret_cast<uintptr_t>(v_cache) & 15) == 0) {
+    execute_moves_b16_d128_kernel<<<dim3(total_heads, gy), kMoveWarps * kWarp, 0, st>>>(
+        reinterpret_cast<uint16_t*>(k_cache), reinterpret_cast<uint16_t*>(v_cache), kv_metrics,
+        kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads);
+    KVC_CHECK_LAUNCH("execute_moves_b16_d128_kernel");
+    return KVC_OK;
+  }
+  const dim3 grid(total_heads, gy), block(128);
+  if (two_byte) {
+    execute_moves_generic_kernel<uint16_t><<<grid, block, 0, st>>>(
+        reinterpret_cast<uint16_t*>(k_cache), reinterpret_cast<uint16_t*>(v_cache), kv_metrics,
+        kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, head_size, vec_size,
+        block_size);
+  } else if (dtype == KVC_F32) {
+    execute_moves_generic_kernel<uint32_t><<<grid, block, 0, st>>>(
+        reinterpret_cast<uint32_t*>(k_cache), reinterpret_cast<uint32_t*>(v_cache), kv_metrics,
+        kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, head_size, vec_size,
+        block_size);
+  } else {
+    execute_moves_generic_kernel<uint8_t><<<grid, block, 0, st>>>(
+        reinterpret_cast<uint8_t*>(k_cache), reinterpret_cast<uint8_t*>(v_cache), kv_metrics,
+        kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, head_size, vec_size,
+        block_size);
+  }
+  KVC_CHECK_LAUNCH("execute_moves_generic_kernel");
+  return KVC_OK;
+}

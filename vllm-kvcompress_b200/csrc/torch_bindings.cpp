@@ -1,0 +1,408 @@
+// Torch dispatcher registration for libkvc_b200: the reference's own operator surface.
+//
+// Same namespaces, op names and schemas as the reference extension
+// (csrc/torch_bindings.cpp:52-80 `_C`, :353-362 `_C_cache_ops`, :371-418 `_C_kvc_ops`;
+// C++ signatures csrc/kvcompress_eviction.h:5-78, csrc/kvcompress_cache.h:5-15,
+// csrc/ops.h:18-37, 67-90), so vllm/_custom_ops.py of the fork resolves
+// torch.ops._C.kvcompress_paged_attention_v1 etc. against this library unchanged.
+// Every op validates dtype / contiguity / device (the reference reinterpret_casts
+// blindly, csrc/kvcompress_eviction_kernels.cu:527-542), forwards raw device pointers
+// to the C ABI (include/kvc_b200.h) on the current CUDA stream, and turns a non-zero
+// status into the RuntimeError the reference's TORCH_CHECK would raise.
+// CUDA dispatch key only: there is no CPU implementation and no fallback.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/all.h>
+#include <torch/library.h>
+#include <Python.h>
+
+#include "kvc_b200.h"
+
+namespace {
+
+inline kvc_stream_t cur_stream() {
+  return reinterpret_cast<kvc_stream_t>(at::cuda::getCurrentCUDAStream().stream());
+}
+
+inline void check_status(int rc, const char* op) {
+  TORCH_CHECK(rc == KVC_OK, op, ": ", kvc_last_error());
+}
+
+inline const int* i32(const torch::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == at::kInt, name, " must be int32, got ", t.scalar_type());
+  TORCH_CHECK(t.is_contiguous(), name, " must be contiguous");
+  return t.data_ptr<int>();
+}
+inline int* i32_mut(torch::Tensor& t, const char* name) { return const_cast<int*>(i32(t, name)); }
+
+inline int cache_dtype(const torch::Tensor& t) {
+  switch (t.scalar_type()) {
+    case at::kHalf: return KVC_F16;
+    case at::kBFloat16: return KVC_BF16;
+    case at::kFloat: return KVC_F32;
+    case at::kFloat8_e5m2:
+    case at::kByte: return KVC_U8;
+    default: TORCH_CHECK(false, "Unsupported data type: ", t.scalar_type());
+  }
+  return -1;
+}
+
+// ---- _C_kvc_ops ------------------------------------------------------------
+void schedule_cache_evictions(
+    torch::Tensor& evicted_kv_indices, torch::Tensor& evicted_logical_indices,
+    torch::Tensor& evicted_kv_count, torch::Tensor& remaining_kv_count,
+    torch::Tensor& evicted_kv_offsets, torch::Tensor& sorted_indices,
+    torch::Tensor& seq_block_offsets, torch::Tensor& layer_by_block, torch::Tensor& head_by_block,
+    torch::Tensor& virtual_block_num_by_block, torch::Tensor& evicted_blocks_per_seq,
+    torch::Tensor& context_lens, torch::Tensor& hanging_token_count, torch::Tensor& kv_position,
+    torch::Tensor& last_position, torch::Tensor& protected_window_size, int64_t block_size,
+    bool evict_evenly_per_layer, const c10::optional<torch::Tensor>& control_layers,
+    int64_t max_evicted_kv, int64_t null_eviction_index, bool truncate) {
+  TORCH_CHECK(evicted_kv_count.dim() == 3, "evicted_kv_count must be [num_seqs, num_layers, num_kv_heads]");
+  const int S = evicted_kv_count.size(0), L = evicted_kv_count.size(1), H = evicted_kv_count.size(2);
+  const int total_blocks = layer_by_block.size(0);
+  const at::cuda::OptionalCUDAGuard guard(device_of(evicted_kv_indices));
+  const size_t ws_bytes = kvc_schedule_cache_evictions_workspace_bytes(S, L, H, total_blocks, (int)block_size);
+  auto ws = torch::empty({(int64_t)ws_bytes}, evicted_kv_indices.options().dtype(at::kByte));
+  const int* ctl = nullptr;
+  int nctl = 0;
+  if (control_layers) {
+    ctl = i32(control_layers.value(), "control_layers");
+    nctl = control_layers.value().numel();
+  }
+  check_status(
+      kvc_schedule_cache_evictions(
+          i32_mut(evicted_kv_indices, "evicted_kv_indices"),
+          i32_mut(evicted_logical_indices, "evicted_logical_indices"),
+          i32_mut(evicted_kv_count, "evicted_kv_count"), i32_mut(remaining_kv_count, "remaining_kv_count"),
+          i32(evicted_kv_offsets, "evicted_kv_offsets"), i32(sorted_indices, "sorted_indices"),
+          i32(seq_block_offsets, "seq_block_offsets"), i32(layer_by_block, "layer_by_block"),
+          i32(head_by_block, "head_by_block"), i32(virtual_block_num_by_block, "virtual_block_num_by_block"),
+          i32(evicted_blocks_per_seq, "evicted_blocks_per_seq"), i32(context_lens, "context_lens"),
+          i32(hanging_token_count, "hanging_token_count"), i32(kv_position, "kv_position"),
+          i32(last_position, "last_position"), i32(protected_window_size, "protected_window_size"), S, L, H,
+          total_blocks, (int)block_size, evict_evenly_per_layer ? 1 : 0, ctl, nctl, (int)max_evicted_kv,
+          (int)null_eviction_index, truncate ? 1 : 0, ws.data_ptr(), ws_bytes, cur_stream()),
+      "schedule_cache_evictions");
+}
+
+void truncate_cache_evictions(torch::Tensor& evicted_kv_indices, torch::Tensor& evicted_logical_indices,
+                              torch::Tensor& evicted_kv_count, torch::Tensor& evicted_kv_offsets,
+                              torch::Tensor& hanging_token_count, int64_t block_size,
+                              int64_t max_evicted_kv, int64_t null_eviction_index) {
+  TORCH_CHECK(evicted_kv_count.dim() == 3, "evicted_kv_count must be [num_seqs, num_layers, num_kv_heads]");
+  const at::cuda::OptionalCUDAGuard guard(device_of(evicted_logical_indices));
+  check_status(kvc_truncate_cache_evictions(
+                   i32_mut(evicted_kv_indices, "evicted_kv_indices"),
+                   i32_mut(evicted_logical_indices, "evicted_logical_indices"),
+                   i32_mut(evicted_kv_count, "evicted_kv_count"), i32(evicted_kv_offsets, "evicted_kv_offsets"),
+                   i32(hanging_token_count, "hanging_token_count"), evicted_kv_count.size(0),
+                   evicted_kv_count.size(1), evicted_kv_count.size(2), (int)block_size, (int)max_evicted_kv,
+                   (int)null_eviction_index, cur_stream()),
+               "truncate_cache_evictions");
+}
+
+void count_block_evictions(torch::Tensor& evicted_block_count, torch::Tensor& evicted_logical_indices,
+                           torch::Tensor& evicted_kv_offsets, torch::Tensor& hanging_token_count,
+                           int64_t block_size, int64_t null_value) {
+  TORCH_CHECK(evicted_block_count.dim() == 3, "evicted_block_count must be [num_seqs, num_layers, num_kv_heads]");
+  const at::cuda::OptionalCUDAGuard guard(device_of(evicted_logical_indices));
+  check_status(kvc_count_block_evictions(
+                   i32_mut(evicted_block_count, "evicted_block_count"),
+                   i32_mut(evicted_logical_indices, "evicted_logical_indices"),
+                   i32(evicted_kv_offsets, "evicted_kv_offsets"), i32(hanging_token_count, "hanging_token_count"),
+                   evicted_block_count.size(0), evicted_block_count.size(1), evicted_block_count.size(2),
+                   (int)evicted_logical_indices.numel(), (int)block_size, (int)null_value, cur_stream()),
+               "count_block_evictions");
+}
+
+void schedule_t1_cache_moves(torch::Tensor& cache_moves_idx, torch::Tensor& cache_moves_count,
+                             torch::Tensor& evicted_logical_indices, torch::Tensor& evicted_kv_count,
+                             torch::Tensor& evicted_kv_offsets, torch::Tensor& block_tables,
+                             torch::Tensor& context_lens, int64_t block_size) {
+  TORCH_CHECK(evicted_kv_count.dim() == 3, "evicted_kv_count must be [num_seqs, num_layers, num_kv_heads]");
+  TORCH_CHECK(block_tables.dim() == 4, "block_tables must be [num_layers, num_seqs, num_kv_heads, max_blocks]");
+  const at::cuda::OptionalCUDAGuard guard(device_of(evicted_logical_indices));
+  check_status(kvc_schedule_t1_cache_moves(
+                   i32_mut(cache_moves_idx, "cache_moves_idx"), i32_mut(cache_moves_count, "cache_moves_count"),
+                   i32(evicted_logical_indices, "evicted_logical_indices"),
+                   i32(evicted_kv_count, "evicted_kv_count"), i32(evicted_kv_offsets, "evicted_kv_offsets"),
+                   i32(block_tables, "block_tables"), i32(context_lens, "context_lens"),
+                   evicted_kv_count.size(0), evicted_kv_count.size(1), evicted_kv_count.size(2),
+                   block_tables.size(3), (int)block_size, cur_stream()),
+               "schedule_t1_cache_moves");
+}
+
+void execute_cache_moves(torch::Tensor& k_cache, torch::Tensor& v_cache, torch::Tensor& kv_metrics,
+                         torch::Tensor& kv_position, torch::Tensor& cache_moves_idx,
+                         torch::Tensor& cache_moves_count, torch::Tensor& evicted_kv_offsets,
+                         int64_t blocks_per_head, int64_t threads_per_head) {
+  TORCH_CHECK(k_cache.dim() == 4 && v_cache.dim() == 3, "k_cache [NB, D/x, B, x], v_cache [NB, D, B] expected");
+  TORCH_CHECK(k_cache.is_cuda() && v_cache.is_cuda() && k_cache.is_contiguous() && v_cache.is_contiguous(),
+              "k_cache / v_cache must be contiguous CUDA tensors");
+  TORCH_CHECK(k_cache.scalar_type() == v_cache.scalar_type(), "k_cache / v_cache dtype mismatch");
+  TORCH_CHECK(kv_metrics.scalar_type() == at::kFloat && kv_metrics.is_contiguous() && kv_metrics.is_cuda(),
+              "kv_metrics must be a contiguous float32 CUDA tensor");
+  TORCH_CHECK(cache_moves_count.dim() == 3, "cache_moves_count must be [num_seqs, num_layers, num_kv_heads]");
+  const at::cuda::OptionalCUDAGuard guard(device_of(cache_moves_idx));
+  check_status(kvc_execute_cache_moves(
+                   k_cache.data_ptr(), v_cache.data_ptr(), kv_metrics.data_ptr<float>(),
+                   i32_mut(kv_position, "kv_position"), i32(cache_moves_idx, "cache_moves_idx"),
+                   i32(cache_moves_count, "cache_moves_count"), i32(evicted_kv_offsets, "evicted_kv_offsets"),
+                   cache_moves_count.size(0), cache_moves_count.size(1), cache_moves_count.size(2),
+                   v_cache.size(0), v_cache.size(1), k_cache.size(3), v_cache.size(2), cache_dtype(k_cache),
+                   (int)blocks_per_head, (int)threads_per_head, cur_stream()),
+               "execute_cache_moves");
+}
+
+// ---- _C_cache_ops ----------------------------------------------------------
+void kvcompress_reshape_and_cache(torch::Tensor& key, torch::Tensor& value, torch::Tensor& key_cache,
+                                  torch::Tensor& value_cache, torch::Tensor& kv_metrics,
+                                  torch::Tensor& slot_mapping, torch::Tensor& kv_metric_head_bias,
+                                  const std::string& kv_cache_dtype, const double k_scale,
+                                  const double v_scale) {
+  (void)k_scale;
+  (void)v_scale;
+  TORCH_CHECK(kv_cache_dtype == "auto", "Unsupported data type of kv cache: ", kv_cache_dtype,
+              " (this build implements kv_cache_dtype='auto')");
+  TORCH_CHECK(key.dim() == 3 && value.dim() == 3, "key / value must be [num_tokens, num_heads, head_size]");
+  TORCH_CHECK(key.stride(2) == 1 && key.stride(1) == key.size(2) && value.stride(2) == 1 &&
+                  value.stride(1) == value.size(2),
+              "key / value heads must be dense");
+  TORCH_CHECK(key.scalar_type() == key_cache.scalar_type() && value.scalar_type() == value_cache.scalar_type() &&
+                  key.scalar_type() == value.scalar_type(),
+              "kv_cache_dtype='auto' requires key/value/cache of one dtype");
+  TORCH_CHECK(key_cache.is_contiguous() && value_cache.is_contiguous(), "caches must be contiguous");
+  TORCH_CHECK(slot_mapping.scalar_type() == at::kLong && slot_mapping.is_contiguous(), "slot_mapping must be contiguous int64");
+  TORCH_CHECK(slot_mapping.numel() == key.size(0) * key.size(1), "slot_mapping must hold num_tokens*num_heads slots");
+  TORCH_CHECK(kv_metrics.scalar_type() == at::kFloat && kv_metric_head_bias.scalar_type() == at::kFloat,
+              "kv_metrics / kv_metric_head_bias must be float32");
+  const at::cuda::OptionalCUDAGuard guard(device_of(key));
+  check_status(kvc_reshape_and_cache(key.data_ptr(), value.data_ptr(), key_cache.data_ptr(),
+                                     value_cache.data_ptr(), kv_metrics.data_ptr<float>(),
+                                     slot_mapping.data_ptr<int64_t>(), kv_metric_head_bias.data_ptr<float>(),
+                                     key.size(0), key.size(1), key.size(2), key_cache.size(2), key_cache.size(3),
+                                     key.stride(0), value.stride(0), cache_dtype(key_cache), cur_stream()),
+               "kvcompress_reshape_and_cache");
+}
+
+// ---- _C (attention) --------------------------------------------------------
+struct AttnCommon {
+  int S, Hq, D, MB;
+  int64_t q_stride, kv_block_stride;
+  const float* alibi;
+  int dtype;
+};
+
+AttnCommon attn_common(torch::Tensor& out, torch::Tensor& query, torch::Tensor& key_cache,
+                       torch::Tensor& value_cache, torch::Tensor& block_tables,
+                       const c10::optional<torch::Tensor>& alibi_slopes, const std::string& kv_cache_dtype) {
+  TORCH_CHECK(kv_cache_dtype == "auto", "Unsupported data type of kv cache: ", kv_cache_dtype,
+              " (this build implements kv_cache_dtype='auto')");
+  TORCH_CHECK(query.dim() == 3 && query.stride(2) == 1 && query.stride(1) == query.size(2),
+              "query must be [num_seqs, num_heads, head_size] with dense heads");
+  TORCH_CHECK(out.is_contiguous() && out.scalar_type() == query.scalar_type(), "out must be contiguous, query dtype");
+  TORCH_CHECK(key_cache.scalar_type() == query.scalar_type() && value_cache.scalar_type() == query.scalar_type(),
+              "kv_cache_dtype='auto' requires cache dtype == query dtype");
+  TORCH_CHECK(block_tables.dim() == 3, "block_tables must be [num_seqs, num_kv_heads, max_blocks]");
+  AttnCommon c;
+  c.S = query.size(0); c.Hq = query.size(1); c.D = query.size(2); c.MB = block_tables.size(2);
+  c.q_stride = query.stride(0);
+  c.kv_block_stride = key_cache.stride(0);
+  c.alibi = nullptr;
+  if (alibi_slopes) {
+    TORCH_CHECK(alibi_slopes.value().scalar_type() == at::kFloat && alibi_slopes.value().is_contiguous(),
+                "alibi_slopes must be contiguous float32");
+    c.alibi = alibi_slopes.value().data_ptr<float>();
+  }
+  c.dtype = cache_dtype(query);
+  return c;
+}
+
+void kvcompress_paged_attention_v1(
+    torch::Tensor& out, torch::Tensor& kv_metric_out, torch::Tensor& query, torch::Tensor& key_cache,
+    torch::Tensor& value_cache, int64_t num_kv_heads, double scale, torch::Tensor& block_tables,
+    torch::Tensor& context_lens, torch::Tensor& kv_position, torch::Tensor& last_position,
+    torch::Tensor& kv_metric_buffer_len, int64_t block_size, int64_t max_context_len,
+    const c10::optional<torch::Tensor>& alibi_slopes, const std::string& kv_cache_dtype, double k_scale,
+    double v_scale, bool record_kv_metrics) {
+  (void)k_scale; (void)v_scale;
+  AttnCommon c = attn_common(out, query, key_cache, value_cache, block_tables, alibi_slopes, kv_cache_dtype);
+  TORCH_CHECK(kv_metric_out.scalar_type() == at::kFloat && kv_metric_out.is_contiguous(), "kv_metric_out must be contiguous float32");
+  const at::cuda::OptionalCUDAGuard guard(device_of(query));
+  check_status(kvc_paged_attention_v1(
+                   out.data_ptr(), kv_metric_out.data_ptr<float>(), query.data_ptr(), key_cache.data_ptr(),
+                   value_cache.data_ptr(), c.S, c.Hq, (int)num_kv_heads, c.D, (float)scale,
+                   i32(block_tables, "block_tables"), i32(context_lens, "context_lens"),
+                   i32(kv_position, "kv_position"), i32(last_position, "last_position"),
+                   i32(kv_metric_buffer_len, "kv_metric_buffer_len"), (int)block_size, (int)max_context_len,
+                   c.MB, c.q_stride, c.kv_block_stride, c.alibi, c.dtype, record_kv_metrics ? 1 : 0, cur_stream()),
+               "kvcompress_paged_attention_v1");
+}
+
+void kvcompress_paged_attention_v2(
+    torch::Tensor& out, torch::Tensor& kv_metric_out, torch::Tensor& exp_sums, torch::Tensor& max_logits,
+    torch::Tensor& tmp_out, torch::Tensor& tmp_kv_metric_out, torch::Tensor& query, torch::Tensor& key_cache,
+    torch::Tensor& value_cache, int64_t num_kv_heads, double scale, torch::Tensor& block_tables,
+    torch::Tensor& context_lens, torch::Tensor& kv_position, torch::Tensor& last_position,
+    torch::Tensor& kv_metric_buffer_len, int64_t block_size, int64_t max_context_len,
+    const c10::optional<torch::Tensor>& alibi_slopes, const std::string& kv_cache_dtype, double k_scale,
+    double v_scale, bool record_kv_metrics) {
+  (void)k_scale; (void)v_scale;
+  AttnCommon c = attn_common(out, query, key_cache, value_cache, block_tables, alibi_slopes, kv_cache_dtype);
+  TORCH_CHECK(kv_metric_out.scalar_type() == at::kFloat && kv_metric_out.is_contiguous(), "kv_metric_out must be contiguous float32");
+  TORCH_CHECK(exp_sums.scalar_type() == at::kFloat && max_logits.scalar_type() == at::kFloat &&
+                  exp_sums.is_contiguous() && max_logits.is_contiguous(), "exp_sums / max_logits must be contiguous float32");
+  TORCH_CHECK(tmp_out.scalar_type() == query.scalar_type() && tmp_out.is_contiguous(), "tmp_out must be contiguous, query dtype");
+  const int64_t parts = (max_context_len + 511) / 512;
+  TORCH_CHECK(exp_sums.numel() >= (int64_t)c.S * c.Hq * parts && tmp_out.numel() >= (int64_t)c.S * c.Hq * parts * c.D,
+              "v2 temporaries are smaller than [num_seqs, num_heads, ceil(max_context_len/512)]");
+  const at::cuda::OptionalCUDAGuard guard(device_of(query));
+  check_status(kvc_paged_attention_v2(
+                   out.data_ptr(), kv_metric_out.data_ptr<float>(), exp_sums.data_ptr<float>(),
+                   max_logits.data_ptr<float>(), tmp_out.data_ptr(),
+                   tmp_kv_metric_out.defined() && tmp_kv_metric_out.numel() ? tmp_kv_metric_out.data_ptr<float>() : nullptr,
+                   query.data_ptr(), key_cache.data_ptr(), value_cache.data_ptr(), c.S, c.Hq, (int)num_kv_heads,
+                   c.D, (float)scale, i32(block_tables, "block_tables"), i32(context_lens, "context_lens"),
+                   i32(kv_position, "kv_position"), i32(last_position, "last_position"),
+                   i32(kv_metric_buffer_len, "kv_metric_buffer_len"), (int)block_size, (int)max_context_len,
+                   c.MB, c.q_stride, c.kv_block_stride, c.alibi, c.dtype, record_kv_metrics ? 1 : 0, cur_stream()),
+               "kvcompress_paged_attention_v2");
+}
+
+// additive op (not in the reference list): see include/kvc_b200.h kvc_paged_attention_fused_metrics
+void kvcompress_paged_attention_fused_metrics(
+    torch::Tensor& out, torch::Tensor& kv_metrics, torch::Tensor& query, torch::Tensor& key_cache,
+    torch::Tensor& value_cache, int64_t num_kv_heads, double scale, torch::Tensor& block_tables,
+    torch::Tensor& context_lens, torch::Tensor& kv_position, torch::Tensor& last_position,
+    torch::Tensor& kv_metric_buffer_len, int64_t block_size, int64_t max_context_len,
+    const c10::optional<torch::Tensor>& alibi_slopes, const std::string& kv_cache_dtype) {
+  AttnCommon c = attn_common(out, query, key_cache, value_cache, block_tables, alibi_slopes, kv_cache_dtype);
+  TORCH_CHECK(kv_metrics.scalar_type() == at::kFloat && kv_metrics.is_contiguous(), "kv_metrics must be contiguous float32");
+  const at::cuda::OptionalCUDAGuard guard(device_of(query));
+  check_status(kvc_paged_attention_fused_metrics(
+                   out.data_ptr(), kv_metrics.data_ptr<float>(), query.data_ptr(), key_cache.data_ptr(),
+                   value_cache.data_ptr(), c.S, c.Hq, (int)num_kv_heads, c.D, (float)scale,
+                   i32(block_tables, "block_tables"), i32(context_lens, "context_lens"),
+                   i32(kv_position, "kv_position"), i32(last_position, "last_position"),
+                   i32(kv_metric_buffer_len, "kv_metric_buffer_len"), (int)block_size, (int)max_context_len,
+                   c.MB, c.q_stride, c.kv_block_stride, c.alibi, c.dtype, cur_stream()),
+               "kvcompress_paged_attention_fused_metrics");
+}
+
+}  // namespace
+
+// FRAGMENT so that the library can coexist with another extension that already owns `_C`.
+TORCH_LIBRARY_FRAGMENT(_C, ops) {
+  ops.def(
+      "kvcompress_paged_attention_v1("
+      "    Tensor! out, Tensor! kv_metric_out, Tensor query,"
+      "    Tensor key_cache, Tensor value_cache,"
+      "    int num_kv_heads, float scale,"
+      "    Tensor block_tables, Tensor context_lens,"
+      "    Tensor kv_position, Tensor last_position,"
+      "    Tensor kv_metric_buffer_len, int block_size,"
+      "    int max_context_len, Tensor? alibi_slopes,"
+      "    str kv_cache_dtype, float k_scale, float v_scale,"
+      "    bool record_kv_metrics) -> ()");
+  ops.impl("kvcompress_paged_attention_v1", torch::kCUDA, &kvcompress_paged_attention_v1);
+  ops.def(
+      "kvcompress_paged_attention_v2("
+      "    Tensor! out, Tensor! kv_metric_out,"
+      "    Tensor exp_sums, Tensor max_logits,"
+      "    Tensor tmp_out, Tensor tmp_kv_metric_out,"
+      "    Tensor query, Tensor key_cache, Tensor value_cache,"
+      "    int num_kv_heads, float scale,"
+      "    Tensor block_tables, Tensor context_lens,"
+      "    Tensor kv_position, Tensor last_position,"
+      "    Tensor kv_metric_buffer_len, int block_size,"
+      "    int max_context_len, Tensor? alibi_slopes,"
+      "    str kv_cache_dtype, float k_scale, float v_scale,"
+      "    bool record_kv_metrics) -> ()");
+  ops.impl("kvcompress_paged_attention_v2", torch::kCUDA, &kvcompress_paged_attention_v2);
+  ops.def(
+      "kvcompress_paged_attention_fused_metrics("
+      "    Tensor! out, Tensor! kv_metrics, Tensor query,"
+      "    Tensor key_cache, Tensor value_cache,"
+      "    int num_kv_heads, float scale,"
+      "    Tensor block_tables, Tensor context_lens,"
+      "    Tensor kv_position, Tensor last_position,"
+      "    Tensor kv_metric_buffer_len, int block_size,"
+      "    int max_context_len, Tensor? alibi_slopes,"
+      "    str kv_cache_dtype) -> ()");
+  ops.impl("kvcompress_paged_attention_fused_metrics", torch::kCUDA, &kvcompress_paged_attention_fused_metrics);
+  // the reference wrapper calls torch.ops._C.schedule_cache_evictions although the op is
+  // registered under _C_kvc_ops (vllm/_custom_ops.py:982 vs torch_bindings.cpp:372-386):
+  // export it under both names so either resolves.
+  ops.def(
+      "schedule_cache_evictions(Tensor! evicted_kv_indices, Tensor! evicted_logical_indices,"
+      "                           Tensor! evicted_kv_count, Tensor! remaining_kv_count,"
+      "                           Tensor evicted_kv_offsets, Tensor sorted_indices,"
+      "                           Tensor seq_block_offsets, Tensor layer_by_block,"
+      "                           Tensor head_by_block, Tensor virtual_block_num_by_block,"
+      "                           Tensor evicted_blocks_per_seq, Tensor context_lens,"
+      "                           Tensor hanging_token_count, Tensor kv_position,"
+      "                           Tensor last_position, Tensor protected_window_size,"
+      "                           int block_size, bool evict_evenly_per_layer,"
+      "                           Tensor? control_layers, int max_evicted_kv,"
+      "                           int null_eviction_index, bool truncate) -> ()");
+  ops.impl("schedule_cache_evictions", torch::kCUDA, &schedule_cache_evictions);
+}
+
+TORCH_LIBRARY_FRAGMENT(_C_cache_ops, cache_ops) {
+  cache_ops.def(
+      "kvcompress_reshape_and_cache(Tensor key, Tensor value,"
+      "                             Tensor! key_cache, Tensor! value_cache,"
+      "                             Tensor kv_metrics, Tensor slot_mapping,"
+      "                             Tensor kv_metric_head_bias,"
+      "                             str kv_cache_dtype,"
+      "                             float k_scale, float v_scale) -> ()");
+  cache_ops.impl("kvcompress_reshape_and_cache", torch::kCUDA, &kvcompress_reshape_and_cache);
+}
+
+TORCH_LIBRARY_FRAGMENT(_C_kvc_ops, kvc_ops) {
+  kvc_ops.def(
+      "schedule_cache_evictions(Tensor! evicted_kv_indices, Tensor! evicted_logical_indices,"
+      "                           Tensor! evicted_kv_count, Tensor! remaining_kv_count,"
+      "                           Tensor evicted_kv_offsets, Tensor sorted_indices,"
+      "                           Tensor seq_block_offsets, Tensor layer_by_block,"
+      "                           Tensor head_by_block, Tensor virtual_block_num_by_block,"
+      "                           Tensor evicted_blocks_per_seq, Tensor context_lens,"
+      "                           Tensor hanging_token_count, Tensor kv_position,"
+      "                           Tensor last_position, Tensor protected_window_size,"
+      "                           int block_size, bool evict_evenly_per_layer,"
+      "                           Tensor? control_layers, int max_evicted_kv,"
+      "                           int null_eviction_index, bool truncate) -> ()");
+  kvc_ops.impl("schedule_cache_evictions", torch::kCUDA, &schedule_cache_evictions);
+  kvc_ops.def(
+      "truncate_cache_evictions(Tensor! evicted_kv_indices, Tensor! evicted_logical_indices,"
+      "                           Tensor! evicted_kv_count, Tensor evicted_kv_offsets,"
+      "                           Tensor hanging_token_count, int block_size,"
+      "                           int max_evicted_kv, int null_eviction_index) -> ()");
+  kvc_ops.impl("truncate_cache_evictions", torch::kCUDA, &truncate_cache_evictions);
+  kvc_ops.def(
+      "count_block_evictions(Tensor! evicted_block_count, Tensor! evicted_logical_indices,"
+      "                        Tensor evicted_kv_offsets, Tensor hanging_token_count,"
+      "                        int block_size, int null_value) -> ()");
+  kvc_ops.impl("count_block_evictions", torch::kCUDA, &count_block_evictions);
+  kvc_ops.def(
+      "schedule_t1_cache_moves(Tensor! cache_moves_idx, Tensor! cache_moves_count,"
+      "                         Tensor evicted_logical_indices, Tensor evicted_kv_count,"
+      "                         Tensor evicted_kv_offsets, Tensor block_tables,"
+      "                         Tensor context_lens, int block_size) -> ()");
+  kvc_ops.impl("schedule_t1_cache_moves", torch::kCUDA, &schedule_t1_cache_moves);
+  kvc_ops.def(
+      "execute_cache_moves(Tensor! k_cache, Tensor! v_cache, Tensor! kv_metrics,"
+      "                      Tensor! kv_position, Tensor cache_moves_idx,"
+      "                      Tensor cache_moves_count, Tensor evicted_kv_offsets,"
+      "                      int blocks_per_head, int threads_per_head) -> ()");
+  kvc_ops.impl("execute_cache_moves", torch::kCUDA, &execute_cache_moves);
+}
+
+// importable as a Python module named _C, like the reference's REGISTER_EXTENSION
+// (csrc/core/registration.h:17-27)
+PyMODINIT_FUNC PyInit__C() {
+  static struct PyModuleDef module = {PyModuleDef_HEAD_INIT, "_C", nullptr, 0, nullptr};
+  return PyModule_Create(&module);
+}
