@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- KV-Compress hot path on B200: decode tokens/s at CR=64x (Llama-3-8B shape).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl {b200,reference}]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic input: for the batch of
+256 sequences already compressed to max_cache_tokens=128 KVs per (layer, head)
+(BASELINE.json configs[1]: Llama-3-8B shape, input 6000 / output 500, CR 64, batch 256):
+  compression cycle (fused selection -> schedule_t1_cache_moves -> execute_cache_moves ->
+  free blocks) -> append one token per head -> for each of the 32 layers:
+  kvcompress_reshape_and_cache + paged attention over the per-head block tables with the
+  attention metric aggregated (sum_q p^2) -- i.e. everything LLMEngine.step does on this path
+  (vllm/engine/llm_engine.py:1556-1634) except the model's dense projections, which are
+  outside the path and replaced by synthetic Q/K/V.
+value   = batch tokens / step time, inputs resident in HBM (CUDA events, max over ranks).
+e2e     = same step through the public API (DecodeHotPath.step_host) with the step's Q/K/V
+          coming from pinned host memory and the attention output copied back, copies inside
+          the timed region.
+roofline= the dominant kernel (paged attention): algorithmic bytes / its mean launch time,
+          CUDA events on the launching stream inside the timed region.
+cpu_baseline = the oracle port of the same step on the host cores, on a bounded sample.
+N>1: request-sharded replicas (one independent cache per GPU, weak scaling); NCCL only for
+the start-up broadcast and the timing reduction.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
+    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--selection", default="fused", choices=["fused", "chain"])
+    ap.add_argument("--unfused-metrics", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-compaction", action="store_true")
+    ap.add_argument("--cpu-sample-seqs", type=int, default=4)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index),
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the oracle port of the step on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import kvc_oracle as O
+    from oracle.cpu_decode_step import CpuDecodeHotPath
+    from vllm_kvcompress_b200.engine import HotPathConfig
+    O.build()
+    ns = args.cpu_sample_seqs
+    cfg = HotPathConfig(num_seqs=ns, num_layers=args.layers)
+    eng = CpuDecodeHotPath(cfg)
+    Hq, H, D = cfg.num_kv_heads * cfg.queries_per_kv, cfg.num_kv_heads, cfg.head_size
+    qkv = (np.random.RandomState(0).rand(cfg.num_layers, ns, (Hq + 2 * H) * D).astype(np.float16) - 0.5).view(np.uint16)
+    out = np.zeros((cfg.num_layers, ns, Hq * D), np.float32)
+    for _ in range(args.warmup):
+        eng.step(qkv, out)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.step(qkv, out)
+    dt = (time.perf_counter() - t0) / args.steps
+    val = ns / dt
+    line = {
+        "impl": "reference", "metric": "decode tokens/sec at CR=64x (Llama-3-8B shape, KV-Compress hot path)",
+        "value": val, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "config": workload_config(args, ns),
+        "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": O.num_threads(), "kind": "port",
+                         "sample": f"{ns} of {args.batch} sequences per step, all {args.layers} layers, full cycle"},
+        "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, batch):
+    return {"workload": "Llama-3-8B shape (L=32, H_kv=8, Q=4, D=128, block 16), input 6000 / output 500, "
+                        "CR 64x => max_cache_tokens=128, protected_window=32, continual compression every step",
+            "global_batch": batch, "seq_len": 6000, "parallelism": "request-sharded replicas",
+            "l2": "inputs larger than L2 (per-step KV read ~4.6 GB vs 126 MB L2)",
+            "selection": args.selection, "fused_metrics": not args.unfused_metrics,
+            "launch": "one CUDA graph per step" if args.selection == "fused" else "eager"}
+
+
+def compaction_roofline(device, peak):
+    """execute_cache_moves on the post-prefill shape of BASELINE.md config 5 (S=3 sequences of
+    6000 tokens, L=32, H=8), CR in {64, 4}: algorithmic GB/s (1048 B per move) vs HBM peak."""
+    from vllm_kvcompress_b200 import _custom_ops as ops
+    from vllm_kvcompress_b200 import workload as W
+    res = {}
+    S, L, H, B, D = 3, 32, 8, 16, 128
+    for cr, keep in ((64, 128), (4, 1488)):
+        st = W.make_state(S, L, H, B, D, 6000, dtype=torch.float16, device=device, seed=cr, slack=1.0,
+                          fill_cache=False)
+        hanging = W.hanging_token_counts(st.context_lens, B).transpose(0, 1).contiguous()
+        offs = W.evicted_kv_offsets(st.context_lens, B)
+        N = int(((st.context_lens + B - 1) // B).sum()) * B
+        nblk_total = int(((st.context_lens + B - 1) // B).sum(dim=(0, 2))[0])
+        budgets = torch.full((S,), nblk_total - keep * L * H // B, dtype=torch.int32, device=device)
+        last = torch.full((S,), 5999, dtype=torch.int32, device=device)
+        prot = torch.full((S,), 32, dtype=torch.int32, device=device)
+        logical = torch.empty(N, dtype=torch.int32, device=device)
+        cnt = torch.empty((S, L, H), dtype=torch.int32, device=device)
+        blk = torch.empty_like(cnt)
+        ops.select_evictions(logical, cnt, blk, st.kv_metrics, st.kv_position, st.block_tables, st.context_lens,
+                             hanging, offs, budgets, last, prot, B, W.MAX_INT)
+        moves = torch.empty((N, 2), dtype=torch.int32, device=device)
+        mcnt = torch.empty((S, L, H), dtype=torch.int32, device=device)
+        ops.schedule_cache_moves(moves, mcnt, logical, cnt, offs, st.block_tables, st.context_lens, B)
+        nmoves = int(mcnt.sum())
+        times = []
+        for it in range(6):  # moves are idempotent on the same state (src never overwritten): re-run is valid
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.execute_cache_moves(st.k_cache, st.v_cache, st.kv_metrics, st.kv_position, moves, mcnt, offs, 1, 16)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        t = sorted(times[1:])[len(times[1:]) // 2]
+        gbs = nmoves * 1048 / (t * 1e-3) / 1e9
+        res[f"cr{cr}"] = {"moves": nmoves, "ms": t, "achieved_gbs": gbs, "frac": gbs / peak,
+                          "cache_gb": st.NB * 8192 / 1e9}
+        del st, moves
+        torch.cuda.empty_cache()
+    return res
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    from vllm_kvcompress_b200.engine import DecodeHotPath, HotPathConfig
+
+    cfg = HotPathConfig(num_seqs=args.batch, num_layers=args.layers, selection=args.selection,
+                        fused_metrics=not args.unfused_metrics, seed=rank)
+    if world > 1:
+        # the only collective on this path: one start-up broadcast (stands in for the weight
+        # broadcast of the 8-replica layout; every replica then owns an independent cache)
+        hdr = torch.tensor([cfg.num_seqs, cfg.num_layers, cfg.max_cache_tokens], device=device)
+        dist.broadcast(hdr, 0)
+    eng = DecodeHotPath(cfg, device)
+    H, Q, D, L, S = cfg.num_kv_heads, cfg.queries_per_kv, cfg.head_size, cfg.num_layers, cfg.num_seqs
+    width_in, width_out = (H * Q + 2 * H) * D, H * Q * D
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    qkv = (torch.rand((L, S, width_in), generator=g, device=device, dtype=torch.float32) - 0.5).to(cfg.dtype)
+    out = torch.empty((L, S, width_out), device=device, dtype=cfg.dtype)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ----------------
+    graphed = eng.capture(qkv, out)   # whole step as one CUDA graph (no host round trip inside)
+    run_step = eng.replay if graphed else (lambda: eng.step(qkv, out))
+    for _ in range(args.warmup):
+        run_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        run_step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (eng.launches - launches0) // args.steps
+
+    # attention kernel time: same steps, events around every attention launch (separate pass so the
+    # event records do not perturb the headline number)
+    attn_ms, attn_b = eng.profile_attention(qkv, out, steps=min(args.steps, 5))
+
+    # ---------------- end to end through the public API with host buffers ----------------
+    qkv_host = torch.empty((L, S, width_in), dtype=cfg.dtype, pin_memory=True)
+    qkv_host.copy_(qkv)
+    out_host = torch.empty((L, S, width_out), dtype=cfg.dtype, pin_memory=True)
+    for _ in range(3):
+        eng.step_host(qkv_host, out_host)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        eng.step_host(qkv_host, out_host)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+
+    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    total_tokens = S * world
+    line = {
+        "metric": "decode tokens/sec at CR=64x (Llama-3-8B shape, KV-Compress hot path)",
+        "value": total_tokens / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": workload_config(args, total_tokens),
+        "e2e": {"value": total_tokens / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": qkv_host.numel() * qkv_host.element_size(),
+                "d2h_bytes_per_step": out_host.numel() * out_host.element_size()},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "paged_attention_kernel (fused metrics), %d launches/step" % L,
+                     "achieved": attn_b / (attn_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": attn_b / (attn_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                     "bytes_per_launch": attn_b, "ms_per_launch": attn_ms, "traffic": None},
+    }
+    if not args.no_compaction:
+        try:
+            line["execute_cache_moves"] = compaction_roofline(device, peak)
+        except Exception as ex:  # pragma: no cover
+            line["execute_cache_moves"] = {"error": repr(ex)}
+    if not args.no_cpu_baseline:
+        import numpy as np
+        from oracle import kvc_oracle as O
+        from oracle.cpu_decode_step import CpuDecodeHotPath
+        O.build()
+        ns = args.cpu_sample_seqs
+        ccfg = HotPathConfig(num_seqs=ns, num_layers=L)
+        ceng = CpuDecodeHotPath(ccfg)
+        cq = (np.random.RandomState(0).rand(L, ns, width_in).astype(np.float16) - 0.5).view(np.uint16)
+        co = np.zeros((L, ns, width_out), np.float32)
+        ceng.step(cq, co)
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 3 or (time.perf_counter() - t0 < 10 and reps < 200):
+            ceng.step(cq, co)
+            reps += 1
+        cdt = (time.perf_counter() - t0) / reps
+        line["cpu_baseline"] = {"value": ns / cdt, "unit": "tokens/s", "cores": O.num_threads(), "kind": "port",
+                                "sample": f"{ns} of {S} sequences per step, all {L} layers, full cycle, "
+                                          f"{reps} steps in {cdt * reps:.1f} s"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

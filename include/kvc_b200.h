@@ -263,6 +263,37 @@ KVC_API int kvc_paged_attention_fused_metrics(
     int64_t kv_block_stride, const float* alibi_slopes,
     int dtype /* kvc_dtype */, kvc_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Additive: fused eviction selection straight from the paged metrics.
+ * replaces CompressionMetrics.schedule_evictions (vllm/kvcompress/metrics.py:441-847:
+ * mask gathers + 6 torch.sort + per-sequence host loop + count_block_evictions + final
+ * sort) and, equivalently, sort_seq_metrics (:849-966) -> schedule_cache_evictions +
+ * truncate -> host re-sort (vllm/kvcompress/scheduler.py:472-477).  Output is what
+ * schedule_t1_cache_moves consumes:
+ *   evicted_logical_indices [max_evicted_kv]: per head segment (evicted_kv_offsets)
+ *       the evicted logical indices ascending, null_eviction_index after them
+ *   evicted_kv_count [S,L,H] = (k-1)*B + hanging for k freed blocks, else 0
+ *   evicted_block_count [S,L,H] = k
+ * Inputs: kv_metrics/kv_position [NB,B]; block_tables [L,S,H,MB], context_lens [L,S,H]
+ * (batch views, as for schedule_t1_cache_moves); hanging_token_count,
+ * evicted_kv_offsets [S,L,H]; evicted_blocks_per_seq, last_position,
+ * protected_window_size [S].  Candidate rule and completion logic = K1
+ * (csrc/kvcompress_eviction_kernels.cu:136-153); ties by (metric, logical index).
+ * No head-bias / use_average / attention-sink terms (reference defaults: zero bias,
+ * use_average False, num_sinks 0).
+ * ------------------------------------------------------------------------- */
+KVC_API size_t kvc_select_evictions_workspace_bytes(int64_t max_evicted_kv, int block_size);
+
+KVC_API int kvc_select_evictions(
+    int* evicted_logical_indices, int* evicted_kv_count, int* evicted_block_count,
+    const float* kv_metrics, const int* kv_position, const int* block_tables,
+    const int* context_lens, const int* hanging_token_count,
+    const int* evicted_kv_offsets, const int* evicted_blocks_per_seq,
+    const int* last_position, const int* protected_window_size, int num_seqs,
+    int num_layers, int num_kv_heads, int max_num_blocks_per_seq, int block_size,
+    int64_t max_evicted_kv, int null_eviction_index, void* workspace,
+    size_t workspace_bytes, kvc_stream_t stream);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -520,3 +520,68 @@ def test_attention_vs_reference_cuda(capi, ref_ops, cfg, version):
     rm = rmet.cpu().numpy()
     assert ((metric == -1.0) == (rm == -1.0)).all()
     np.testing.assert_allclose(metric, rm, atol=2e-5, rtol=5e-3)
+
+
+# ---------------------------------------------------------------------------
+# D. fused selection (additive op) == sort -> K1+K2 -> re-sort chain of the reference
+# ---------------------------------------------------------------------------
+def selection_case(seed, S, L, H, B, max_blocks, prot, frac):
+    """State in engine layout (block tables + paged metrics) plus the K1 view of it."""
+    from vllm_kvcompress_b200 import workload as W
+    g = torch.Generator().manual_seed(seed)
+    ctx = torch.randint(1, max_blocks * B + 1, (L, S, H), generator=g, dtype=torch.int32)
+    st = W.make_state(S, L, H, B, 16, ctx, dtype=torch.float16, device="cpu", seed=seed, fill_cache=False)
+    # positions: a shuffled subset of [0, 2*ctx) per head, so the protected window bites unevenly
+    pos = torch.full((st.NB * B,), -1, dtype=torch.int32)
+    for l in range(L):
+        for s in range(S):
+            for h in range(H):
+                n = int(ctx[l, s, h])
+                slots = (st.block_tables[l, s, h, torch.arange(n) // B].long() * B + torch.arange(n) % B)
+                pos[slots] = torch.randperm(2 * n, generator=g)[:n].to(torch.int32)
+    st.kv_position = pos.view(st.NB, B)
+    last = torch.tensor([int(2 * ctx[:, s].max()) for s in range(S)], dtype=torch.int32)
+    protected = torch.full((S,), prot, dtype=torch.int32)
+    nblk = (ctx + B - 1) // B
+    budgets = (nblk.sum(dim=(0, 2)).float() * frac).to(torch.int32)
+    return st, ctx, last, protected, budgets
+
+
+@pytest.mark.parametrize("cfg", [
+    (71, 3, 2, 2, 4, 5, 3, 0.5),
+    (72, 4, 4, 8, 16, 10, 16, 0.4),      # <= 256 slots per head: warp-per-head path
+    (73, 2, 4, 8, 16, 40, 32, 0.7),      # > 256 slots per head: CTA-per-head path
+    (74, 3, 3, 4, 16, 9, 0, 2.0),        # budget larger than what exists
+    (75, 2, 2, 2, 1, 100, 7, 0.5),
+    (76, 2, 32, 8, 16, 9, 32, 0.12),     # Llama-3-8B head count, steady-state-like budget
+])
+def test_select_evictions_equals_reference_chain(capi, O, cfg):
+    from vllm_kvcompress_b200 import workload as W
+    seed, S, L, H, B = cfg[:5]
+    st, ctx, last, protected, budgets = selection_case(*cfg)
+    hanging = W.hanging_token_counts(ctx, B).transpose(0, 1).contiguous()
+    offs = W.evicted_kv_offsets(ctx, B)
+    N = int(((ctx + B - 1) // B).sum()) * B
+    # reference chain on the CPU: sort_seq_metrics -> K1+K2 (oracle) -> host re-sort -> K3-style counts
+    sm = W.sort_seq_metrics(st)
+    n = lambda t: t.numpy()
+    ekv, elog = np.zeros(N, np.int32), np.zeros(N, np.int32)
+    cnt = np.zeros((S, L, H), np.int32)
+    O.schedule_cache_evictions(ekv, elog, cnt, n(hanging).copy(), n(offs), n(sm.sorted_indices),
+                               n(sm.seq_block_offsets), n(sm.layer_by_block), n(sm.head_by_block),
+                               n(sm.logical_block_num_by_block), n(budgets), n(ctx.transpose(0, 1).contiguous()),
+                               n(hanging), n(sm.token_positions), n(last), n(protected), B, False, None, N,
+                               MAX_INT, True)
+    want_logical = O.sort_evictions_by_head(ekv, elog)
+    hn = n(hanging)
+    want_blocks = np.where(cnt >= hn, (cnt - hn) // B + 1, 0)
+    # fused op on the GPU
+    out_logical = torch.full((N,), -5, dtype=torch.int32, device="cuda")
+    out_cnt = torch.full((S, L, H), -5, dtype=torch.int32, device="cuda")
+    out_blk = torch.full((S, L, H), -5, dtype=torch.int32, device="cuda")
+    capi.select_evictions(out_logical, out_cnt, out_blk, st.kv_metrics.cuda(), st.kv_position.cuda(),
+                          st.block_tables.cuda(), ctx.cuda(), hanging.cuda(), offs.cuda(), budgets.cuda(),
+                          last.cuda(), protected.cuda(), B, MAX_INT)
+    np.testing.assert_array_equal(out_cnt.cpu().numpy(), cnt)
+    np.testing.assert_array_equal(out_blk.cpu().numpy(), want_blocks)
+    np.testing.assert_array_equal(out_logical.cpu().numpy(), want_logical)

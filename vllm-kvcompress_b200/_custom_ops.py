@@ -140,3 +140,22 @@ def execute_cache_moves(k_cache, v_cache, kv_metrics, kv_position, cache_moves_i
         k_cache, v_cache, kv_metrics, kv_position, cache_moves_indices.contiguous(),
         cache_moves_count.contiguous(), evicted_kv_offsets.contiguous(), blocks_per_head,
         threads_per_head)
+
+
+SELECT_EVICTIONS_LAUNCHES = 3  # rank, threshold, emit
+
+
+def select_evictions(out_evicted_logical_indices, out_evicted_kv_count, out_evicted_block_count,
+                     kv_metrics, kv_position, block_tables, context_lens, hanging_token_count,
+                     evicted_kv_offsets, evicted_blocks_per_seq, last_position, protected_window_size,
+                     block_size: int, null_eviction_index: int) -> None:
+    """ADDITIVE op: fused replacement of CompressionMetrics.schedule_evictions
+    (vllm/kvcompress/metrics.py:441-847) / the sort_seq_metrics -> schedule_cache_evictions ->
+    re-sort chain (metrics.py:849-966, scheduler.py:285-486).  Same outputs as
+    schedule_evictions returns: (evicted_logical_indices, evicted_kv_count, evicted_block_count)."""
+    torch.ops._C_kvc_ops.select_evictions(
+        out_evicted_logical_indices, out_evicted_kv_count, out_evicted_block_count, kv_metrics,
+        kv_position.contiguous(), block_tables.contiguous(), context_lens.contiguous(),
+        hanging_token_count.contiguous(), evicted_kv_offsets.contiguous(),
+        evicted_blocks_per_seq.contiguous(), last_position.type(torch.int), protected_window_size,
+        block_size, null_eviction_index)

@@ -174,3 +174,25 @@ def paged_attention_fused_metrics(out, kv_metrics, query, key_cache, value_cache
                    alibi_slopes)
     _check(native.load_lib().kvc_paged_attention_fused_metrics(_ptr(out), _ptr(kv_metrics), *a,
                                                                _stream()))
+
+
+def select_evictions(evicted_logical_indices, evicted_kv_count, evicted_block_count, kv_metrics,
+                     kv_position, block_tables, context_lens, hanging_token_count, evicted_kv_offsets,
+                     evicted_blocks_per_seq, last_position, protected_window_size, block_size,
+                     null_eviction_index):
+    lib = native.load_lib()
+    lib.kvc_select_evictions_workspace_bytes.restype = ctypes.c_size_t
+    S, L, H = evicted_kv_count.shape
+    max_kv = evicted_logical_indices.numel()
+    nbytes = lib.kvc_select_evictions_workspace_bytes(ctypes.c_int64(max_kv), block_size)
+    ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=evicted_kv_count.device)
+    assert kv_metrics.dtype == torch.float32 and kv_metrics.is_contiguous()
+    ints = [kv_position, block_tables, context_lens, hanging_token_count, evicted_kv_offsets,
+            evicted_blocks_per_seq, last_position, protected_window_size]
+    for i, t in enumerate(ints):
+        _i32(t, f"arg{i}")
+    _check(lib.kvc_select_evictions(
+        _ptr(_i32(evicted_logical_indices, "evicted_logical_indices")),
+        _ptr(_i32(evicted_kv_count, "evicted_kv_count")), _ptr(_i32(evicted_block_count, "evicted_block_count")),
+        _ptr(kv_metrics), *[_ptr(t) for t in ints], S, L, H, block_tables.shape[3], block_size,
+        ctypes.c_int64(max_kv), null_eviction_index, _ptr(ws), ctypes.c_size_t(ws.numel()), _stream()))

@@ -156,6 +156,34 @@ void execute_cache_moves(torch::Tensor& k_cache, torch::Tensor& v_cache, torch::
                "execute_cache_moves");
 }
 
+// additive op: see include/kvc_b200.h kvc_select_evictions
+void select_evictions(torch::Tensor& evicted_logical_indices, torch::Tensor& evicted_kv_count,
+                      torch::Tensor& evicted_block_count, torch::Tensor& kv_metrics,
+                      torch::Tensor& kv_position, torch::Tensor& block_tables, torch::Tensor& context_lens,
+                      torch::Tensor& hanging_token_count, torch::Tensor& evicted_kv_offsets,
+                      torch::Tensor& evicted_blocks_per_seq, torch::Tensor& last_position,
+                      torch::Tensor& protected_window_size, int64_t block_size, int64_t null_eviction_index) {
+  TORCH_CHECK(evicted_kv_count.dim() == 3, "evicted_kv_count must be [num_seqs, num_layers, num_kv_heads]");
+  TORCH_CHECK(block_tables.dim() == 4, "block_tables must be [num_layers, num_seqs, num_kv_heads, max_blocks]");
+  TORCH_CHECK(kv_metrics.scalar_type() == at::kFloat && kv_metrics.is_contiguous() && kv_metrics.is_cuda(),
+              "kv_metrics must be a contiguous float32 CUDA tensor");
+  const at::cuda::OptionalCUDAGuard guard(device_of(evicted_logical_indices));
+  const int64_t max_kv = evicted_logical_indices.numel();
+  const size_t ws_bytes = kvc_select_evictions_workspace_bytes(max_kv, (int)block_size);
+  auto ws = torch::empty({(int64_t)ws_bytes}, evicted_logical_indices.options().dtype(at::kByte));
+  check_status(kvc_select_evictions(
+                   i32_mut(evicted_logical_indices, "evicted_logical_indices"),
+                   i32_mut(evicted_kv_count, "evicted_kv_count"), i32_mut(evicted_block_count, "evicted_block_count"),
+                   kv_metrics.data_ptr<float>(), i32(kv_position, "kv_position"), i32(block_tables, "block_tables"),
+                   i32(context_lens, "context_lens"), i32(hanging_token_count, "hanging_token_count"),
+                   i32(evicted_kv_offsets, "evicted_kv_offsets"), i32(evicted_blocks_per_seq, "evicted_blocks_per_seq"),
+                   i32(last_position, "last_position"), i32(protected_window_size, "protected_window_size"),
+                   evicted_kv_count.size(0), evicted_kv_count.size(1), evicted_kv_count.size(2),
+                   block_tables.size(3), (int)block_size, max_kv, (int)null_eviction_index, ws.data_ptr(),
+                   ws_bytes, cur_stream()),
+               "select_evictions");
+}
+
 // ---- _C_cache_ops ----------------------------------------------------------
 void kvcompress_reshape_and_cache(torch::Tensor& key, torch::Tensor& value, torch::Tensor& key_cache,
                                   torch::Tensor& value_cache, torch::Tensor& kv_metrics,
@@ -398,6 +426,15 @@ TORCH_LIBRARY_FRAGMENT(_C_kvc_ops, kvc_ops) {
       "                      Tensor cache_moves_count, Tensor evicted_kv_offsets,"
       "                      int blocks_per_head, int threads_per_head) -> ()");
   kvc_ops.impl("execute_cache_moves", torch::kCUDA, &execute_cache_moves);
+  // additive (not in the reference op list)
+  kvc_ops.def(
+      "select_evictions(Tensor! evicted_logical_indices, Tensor! evicted_kv_count,"
+      "                  Tensor! evicted_block_count, Tensor kv_metrics, Tensor kv_position,"
+      "                  Tensor block_tables, Tensor context_lens, Tensor hanging_token_count,"
+      "                  Tensor evicted_kv_offsets, Tensor evicted_blocks_per_seq,"
+      "                  Tensor last_position, Tensor protected_window_size,"
+      "                  int block_size, int null_eviction_index) -> ()");
+  kvc_ops.impl("select_evictions", torch::kCUDA, &select_evictions);
 }
 
 // importable as a Python module named _C, like the reference's REGISTER_EXTENSION

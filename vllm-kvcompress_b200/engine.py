@@ -1,0 +1,291 @@
+"""Host-side driver of the KV-Compress hot path (one GPU, one independent KV cache).
+
+This is the slice of the reference engine loop that touches the hot path
+(LLMEngine.step, vllm/engine/llm_engine.py:1484-1634):
+
+    schedule_compression  -> selection, count_block_evictions, schedule_cache_moves
+                             (vllm/kvcompress/scheduler.py:184-560)
+    execute_cache_moves      (vllm/worker/cache_engine.py:139-151)
+    free_compressed_blocks   (vllm/kvcompress/block_manager.py:466-530: context_lens shrink)
+    batch_append_slots       (block_manager.py:269-294: +1 token per head, slot mapping)
+    per layer: kvcompress_reshape_and_cache + paged attention with metric recording
+                             (vllm/attention/backends/flash_attn.py:871, 1067-1091)
+    aggregate_decode         (vllm/kvcompress/metrics.py:429-439; fused into attention here)
+
+for a batch of S sequences of a Llama-shaped model (L layers, H KV heads, Q query heads
+per KV head, D=128, block size 16), with synthetic Q/K/V in place of the model's
+projections (the dense GEMMs are outside this path).  All state lives in device tensors;
+the only host<->device traffic is what the caller passes in (step_host).
+
+Block allocation: every head owns a fixed slab of `blocks_per_head` physical blocks drawn
+from a random permutation of the cache (scattered, like the reference allocator's output),
+so the block table is static and "allocate / free" reduce to context_lens growing and
+shrinking; the reference frees the trailing blocks and never rewrites table entries either
+(block.py:184-210).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _custom_ops as ops
+from . import workload as W
+
+MAX_INT = W.MAX_INT
+
+
+@dataclass
+class HotPathConfig:
+    num_seqs: int = 256
+    num_layers: int = 32
+    num_kv_heads: int = 8
+    queries_per_kv: int = 4
+    head_size: int = 128
+    block_size: int = 16
+    max_cache_tokens: int = 128       # benchmark_throughput.py:391-393 at input 6000, CR 64
+    protected_window: int = 32
+    prompt_len: int = 6000
+    blocks_per_head: int = 12          # slab: max_cache_tokens/16 + headroom for variable-rate heads
+    dtype: torch.dtype = torch.float16
+    selection: str = "fused"           # "fused" (kvc_select kernels) | "chain" (torch.sort + K1 + K2)
+    fused_metrics: bool = True         # attention accumulates sum_q p^2 itself
+    seed: int = 0
+
+
+class DecodeHotPath:
+    """One replica: owns the unified cache, per-head tables and metrics of `num_seqs` sequences
+    already compressed to `max_cache_tokens` per head (state after a post-prefill compression)."""
+
+    def __init__(self, cfg: HotPathConfig, device: torch.device):
+        self.cfg = cfg
+        self.dev = device
+        S, L, H, B, D = cfg.num_seqs, cfg.num_layers, cfg.num_kv_heads, cfg.block_size, cfg.head_size
+        self.launches = 0
+        st = W.make_state(S, L, H, B, D, cfg.max_cache_tokens, dtype=cfg.dtype, device=device,
+                          seed=cfg.seed, slack=1.0, max_blocks=cfg.blocks_per_head, fill_cache=True,
+                          blocks_per_head_alloc=cfg.blocks_per_head)
+        self.st = st
+        # token positions of the surviving KVs: a random subset of the prompt (what a CR=64 eviction
+        # leaves), newest `protected_window` tokens always present
+        g = torch.Generator(device="cpu").manual_seed(cfg.seed + 7)
+        n = cfg.max_cache_tokens
+        heads = L * S * H
+        keep = torch.rand((heads, cfg.prompt_len - cfg.protected_window), generator=g).topk(
+            n - cfg.protected_window, dim=1).indices.sort(dim=1).values
+        pos = torch.cat([keep, torch.arange(cfg.prompt_len - cfg.protected_window, cfg.prompt_len)
+                         .expand(heads, -1)], dim=1).to(torch.int32)          # [heads, n]
+        bt = st.block_tables.view(heads, -1).cpu()
+        slots = (bt[:, : n // B].long()[:, :, None] * B + torch.arange(B)[None, None]).view(heads, n)
+        kv_pos = torch.full((st.NB * B,), -1, dtype=torch.int32)
+        kv_pos[slots.flatten()] = pos.flatten()
+        st.kv_position = kv_pos.view(st.NB, B).to(device)
+        st.kv_metrics.uniform_(0.01, 1.0, generator=torch.Generator(device=device).manual_seed(cfg.seed + 9))
+        self.seq_len = torch.full((S,), cfg.prompt_len, dtype=torch.int32, device=device)  # tokens so far
+        self.head_bias = torch.zeros((L, H), dtype=torch.float32, device=device)
+        self.zeros_s = torch.zeros(S, dtype=torch.int32, device=device)
+        self.protected = torch.full((S,), cfg.protected_window, dtype=torch.int32, device=device)
+        self.scale = 1.0 / math.sqrt(D)
+        self.max_ctx = cfg.blocks_per_head * B
+        # workspaces sized once (the reference allocates them in CompressionScheduler.__init__, :75-86)
+        N = heads * cfg.blocks_per_head * B
+        self.max_kv = N
+        self.evicted_logical = torch.empty(N, dtype=torch.int32, device=device)
+        self.evicted_heads = torch.empty(N, dtype=torch.int32, device=device)
+        self.cache_moves = torch.empty((N, 2), dtype=torch.int32, device=device)
+        self.moves_count = torch.empty((S, L, H), dtype=torch.int32, device=device)
+        self.evicted_kv_count = torch.empty((S, L, H), dtype=torch.int32, device=device)
+        self.evicted_block_count = torch.empty((S, L, H), dtype=torch.int32, device=device)
+        self.slot_mapping = torch.empty((L, S, H), dtype=torch.int64, device=device)
+        self.arangeB = torch.arange(B, dtype=torch.int32, device=device)
+        if not cfg.fused_metrics:
+            self.temp_metrics = torch.zeros((st.NB, B, cfg.queries_per_kv), dtype=torch.float32, device=device)
+
+    # ------------------------------------------------------------------ compression
+    def _budgets(self) -> torch.Tensor:
+        """_schedule_seq_evictions with max_cache_tokens >= 0 (scheduler.py:131-141): blocks above
+        max_cache_tokens * L * H / B."""
+        cfg = self.cfg
+        nblk = (self.st.context_lens + cfg.block_size - 1) // cfg.block_size   # [L,S,H]
+        total = nblk.sum(dim=(0, 2))
+        max_blocks = (cfg.max_cache_tokens * cfg.num_layers * cfg.num_kv_heads + cfg.block_size - 1) // cfg.block_size
+        return (total - max_blocks).clamp_(min=0).to(torch.int32)
+
+    def compress(self) -> None:
+        cfg, st = self.cfg, self.st
+        B = cfg.block_size
+        ctx = st.context_lens                                                  # [L,S,H]
+        hanging = W.hanging_token_counts(ctx, B).transpose(0, 1).contiguous()  # [S,L,H]
+        offs = W.evicted_kv_offsets(ctx, B)
+        budgets = self._budgets()
+        last_pos = self.seq_len - 1
+        if cfg.selection == "fused":
+            ops.select_evictions(self.evicted_logical, self.evicted_kv_count, self.evicted_block_count,
+                                 st.kv_metrics, st.kv_position, st.block_tables, ctx, hanging, offs, budgets,
+                                 last_pos, self.protected, B, MAX_INT)
+            self.launches += ops.SELECT_EVICTIONS_LAUNCHES
+            logical = self.evicted_logical
+        else:
+            sm = W.sort_seq_metrics(st)                                        # torch.sort x2 (library)
+            ops.schedule_cache_evictions(self.evicted_heads, self.evicted_logical, self.evicted_kv_count, offs,
+                                         sm.sorted_indices, sm.seq_block_offsets, sm.layer_by_block,
+                                         sm.head_by_block, sm.logical_block_num_by_block, budgets, ctx, hanging,
+                                         sm.token_positions, last_pos, self.protected, B, self.max_kv, MAX_INT, True)
+            self.launches += 6
+            # host re-sort (scheduler.py:472-477)
+            order = torch.sort(self.evicted_logical, stable=True).indices
+            order = order[torch.sort(self.evicted_heads[order], stable=True).indices]
+            logical = self.evicted_logical[order].contiguous()
+            self.evicted_block_count = torch.where(self.evicted_kv_count >= hanging,
+                                                   (self.evicted_kv_count - hanging) // B + 1,
+                                                   torch.zeros_like(hanging))
+        ops.schedule_cache_moves(self.cache_moves, self.moves_count, logical, self.evicted_kv_count, offs,
+                                 st.block_tables, ctx, B)
+        ops.execute_cache_moves(st.k_cache, st.v_cache, st.kv_metrics, st.kv_position, self.cache_moves,
+                                self.moves_count, offs, 1, 16)
+        self.launches += 2
+        # free_compressed_blocks: context_lens -= max(nb*B - (B - hanging), 0)  (block.py:184-210)
+        freed = (self.evicted_block_count * B - (B - hanging)).clamp_(min=0)
+        st.context_lens.sub_(freed.transpose(0, 1))   # in place: the tensors are CUDA-graph state
+
+    # ------------------------------------------------------------------ append + forward
+    def append_slots(self) -> None:
+        """batch_append_slots: +1 token per head; slot of the new KV; its position."""
+        cfg, st = self.cfg, self.st
+        B = cfg.block_size
+        ctx = st.context_lens
+        blk = torch.gather(st.block_tables, 3, (ctx // B).long().unsqueeze(-1)).squeeze(-1)
+        slot = blk.long() * B + (ctx % B).long()
+        self.slot_mapping.copy_(slot)
+        st.kv_position.view(-1).index_put_((slot.flatten(),), self.seq_len.view(1, -1, 1).expand_as(ctx).flatten())
+        st.context_lens.add_(1)
+        self.seq_len.add_(1)
+
+    def forward_layer(self, l: int, x: torch.Tensor, o: torch.Tensor, last_pos: torch.Tensor,
+                      timing=None) -> None:
+        """x [S, (Hq + 2H) * D], o [S, Hq * D]: cache write + decode attention of layer l."""
+        cfg, st = self.cfg, self.st
+        H, Q, D, B = cfg.num_kv_heads, cfg.queries_per_kv, cfg.head_size, cfg.block_size
+        Hq = H * Q
+        q = x[:, : Hq * D].view(-1, Hq, D)
+        k = x[:, Hq * D: (Hq + H) * D].view(-1, H, D)
+        v = x[:, (Hq + H) * D:].view(-1, H, D)
+        ops.reshape_and_cache_kvc(k, v, st.k_cache, st.v_cache, st.kv_metrics,
+                                  self.slot_mapping[l].reshape(-1), self.head_bias[l], "auto", 1.0, 1.0)
+        o = o.view(-1, Hq, D)
+        if timing is not None:
+            timing[0].record()
+        if cfg.fused_metrics:
+            ops.paged_attention_kvc_fused_metrics(o, st.kv_metrics, q, st.k_cache, st.v_cache, H, self.scale,
+                                                  st.block_tables[l], st.context_lens[l], st.kv_position,
+                                                  last_pos, self.zeros_s, B, self.max_ctx)
+        else:
+            ops.paged_attention_kvc_v1(o, self.temp_metrics, q, st.k_cache, st.v_cache, H, self.scale,
+                                       st.block_tables[l], st.context_lens[l], st.kv_position, last_pos,
+                                       self.zeros_s, B, self.max_ctx, None, "auto", 1.0, 1.0, True)
+        if timing is not None:
+            timing[1].record()
+        self.launches += 2
+
+    def _aggregate_unfused(self) -> None:
+        if not self.cfg.fused_metrics:
+            # clear_temp_metrics + aggregate_decode (metrics.py:337-342, 429-439), whole-cache passes
+            self.st.kv_metrics += (self.temp_metrics ** 2).sum(dim=-1)
+            self.temp_metrics.zero_()
+
+    def forward(self, qkv: torch.Tensor, out: torch.Tensor) -> None:
+        """qkv [L, S, (Hq + 2H) * D], out [L, S, Hq * D]."""
+        last_pos = self.seq_len - 1
+        for l in range(self.cfg.num_layers):
+            self.forward_layer(l, qkv[l], out[l], last_pos)
+        self._aggregate_unfused()
+
+    def step(self, qkv: torch.Tensor, out: torch.Tensor) -> None:
+        """One decode step of the hot path with device-resident inputs (eager launches)."""
+        self.compress()
+        self.append_slots()
+        self.forward(qkv, out)
+
+    # ------------------------------------------------------------------ CUDA graph of the step
+    def capture(self, qkv: torch.Tensor, out: torch.Tensor) -> bool:
+        """Capture step(qkv, out) into a CUDA graph (the step has no host round trip when the
+        fused selection is used).  Returns False when the configuration cannot be captured."""
+        if self.cfg.selection != "fused":
+            return False
+        n0 = self.launches
+        self.step(qkv, out)                       # warm up allocator + count launches
+        self.launches_per_step = self.launches - n0
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.step(qkv, out)
+        self.launches = n0 + self.launches_per_step
+        return True
+
+    def replay(self) -> None:
+        self.graph.replay()
+        self.launches += self.launches_per_step
+
+    # ------------------------------------------------------------------ end to end with host buffers
+    def step_host(self, qkv_host: torch.Tensor, out_host: torch.Tensor) -> None:
+        """Public end-to-end call: the step's Q/K/V live in (pinned) host memory and the attention
+        output is returned to host memory.  Per-layer H2D copies run on a side stream ahead of the
+        compute, per-layer D2H copies behind it; PCIe is full duplex so both overlap the kernels."""
+        cfg = self.cfg
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_h2d"):
+            self._h2d, self._d2h = torch.cuda.Stream(), torch.cuda.Stream()
+            self._qkv_dev = torch.empty(qkv_host.shape, dtype=qkv_host.dtype, device=self.dev)
+            self._out_dev = torch.empty(out_host.shape, dtype=out_host.dtype, device=self.dev)
+            self._ev_in = [torch.cuda.Event() for _ in range(cfg.num_layers)]
+            self._ev_done = [torch.cuda.Event() for _ in range(cfg.num_layers)]
+        self._h2d.wait_stream(main)   # previous step's compute has consumed the staging buffers
+        with torch.cuda.stream(self._h2d):
+            for l in range(cfg.num_layers):
+                self._qkv_dev[l].copy_(qkv_host[l], non_blocking=True)
+                self._ev_in[l].record(self._h2d)
+        self.compress()
+        self.append_slots()
+        last_pos = self.seq_len - 1
+        for l in range(cfg.num_layers):
+            main.wait_event(self._ev_in[l])
+            self.forward_layer(l, self._qkv_dev[l], self._out_dev[l], last_pos)
+            self._ev_done[l].record(main)
+            self._d2h.wait_event(self._ev_done[l])
+            with torch.cuda.stream(self._d2h):
+                out_host[l].copy_(self._out_dev[l], non_blocking=True)
+        self._aggregate_unfused()
+        main.wait_stream(self._d2h)   # the step is complete when its results are in host memory
+
+    # ------------------------------------------------------------------ measurement helper
+    def profile_attention(self, qkv: torch.Tensor, out: torch.Tensor, steps: int = 3):
+        """Run `steps` eager steps with CUDA events around every attention launch (recorded on the
+        launching stream).  Returns (mean ms per launch, mean algorithmic bytes per launch)."""
+        L = self.cfg.num_layers
+        pairs = []
+        total_bytes = 0
+        for _ in range(steps):
+            self.compress()
+            self.append_slots()
+            total_bytes += self.attention_bytes()
+            last_pos = self.seq_len - 1
+            for l in range(L):
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                self.forward_layer(l, qkv[l], out[l], last_pos, timing=ev)
+                pairs.append(ev)
+            self._aggregate_unfused()
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in pairs) / len(pairs)
+        return ms, total_bytes / (steps * L)
+
+    @property
+    def tokens_per_step(self) -> int:
+        return self.cfg.num_seqs
+
+    def attention_bytes(self) -> int:
+        """Algorithmic bytes of one step's attention launches: K+V of every
+        context token once (2*D*2 B) + position read (4 B) + metric read-modify-write (8 B)."""
+        ctx_total = int(self.st.context_lens.sum())
+        return ctx_total * (2 * self.cfg.head_size * 2 + 4 + 8)

@@ -39,13 +39,20 @@ class KVCState:
 
 def make_state(S: int, L: int, H: int, B: int, D: int, ctx, dtype=torch.float16,
                device="cpu", seed: int = 0, slack: float = 1.25, max_blocks: Optional[int] = None,
-               fill_cache: bool = True) -> KVCState:
-    """ctx: int or int tensor [L, S, H] of per-head context lengths."""
+               fill_cache: bool = True, blocks_per_head_alloc: Optional[int] = None) -> KVCState:
+    """ctx: int or int tensor [L, S, H] of per-head context lengths.
+
+    blocks_per_head_alloc: give every head a fixed slab of that many physical blocks (its block
+    table row is fully populated) instead of exactly ceil(ctx/B); used by the decode harness
+    whose heads grow and shrink inside their slab."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     if isinstance(ctx, int):
         ctx = torch.full((L, S, H), ctx, dtype=torch.int32)
     ctx = ctx.to(torch.int32).cpu()
     nblk = (ctx + B - 1) // B                                # [L,S,H]
+    if blocks_per_head_alloc is not None:
+        assert int(nblk.max()) <= blocks_per_head_alloc
+        nblk = torch.full_like(nblk, blocks_per_head_alloc)
     total = int(nblk.sum())
     NB = int(total * slack) + 8
     MB = int(max_blocks if max_blocks is not None else int(nblk.max()) + 1)
@@ -118,7 +125,10 @@ class SortedMetrics:
 
 def sort_seq_metrics(st: KVCState) -> SortedMetrics:
     """Mask the allocated blocks (physical order), sort their slots by (seq, metric)."""
-    mask = st.seq_by_block >= 0
+    # allocated blocks = blocks below ceil(ctx/B) of their head (a slab may hold spare blocks)
+    lsh = (st.layer_by_block.long() * st.S + st.seq_by_block.long().clamp(min=0)) * st.H + st.head_by_block.long()
+    nblk_of = (st.context_lens.flatten()[lsh] + st.B - 1) // st.B
+    mask = (st.seq_by_block >= 0) & (st.logical_by_block < nblk_of)
     blocks = torch.nonzero(mask).flatten()
     m = st.kv_metrics[blocks].flatten()
     seqs = st.seq_by_block[blocks].repeat_interleave(st.B)
