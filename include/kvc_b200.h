@@ -261,7 +261,11 @@ KVC_API int kvc_paged_attention_fused_metrics(
     const int* last_position, const int* kv_metric_buffer_len, int block_size,
     int max_context_len, int max_num_blocks_per_seq, int64_t q_stride,
     int64_t kv_block_stride, const float* alibi_slopes,
-    int dtype /* kvc_dtype */, kvc_stream_t stream);
+    int dtype /* kvc_dtype */, void* workspace, size_t workspace_bytes,
+    kvc_stream_t stream);
+/* scratch for the parked raw logits: num_seqs * num_heads * ceil16(max_context_len) floats */
+KVC_API size_t kvc_paged_attention_fused_metrics_workspace_bytes(
+    int num_seqs, int num_heads, int max_context_len);
 
 /* ---------------------------------------------------------------------------
  * Additive: fused eviction selection straight from the paged metrics.

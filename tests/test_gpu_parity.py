@@ -394,6 +394,7 @@ def attn_case(seed, S, Hq, H, max_ctx, bf16, alibi, buf, min_ctx=1):
     (43, 2, 8, 8, 1500, False, True, 0),      # MHA, several partitions, alibi
     (44, 2, 24, 2, 700, False, False, 50),    # Q=12 (two n-tiles)
     (45, 4, 4, 4, 17, True, False, 0),        # tiny ragged contexts
+    (46, 3, 32, 8, 400, False, False, 5),     # streaming kernel, logits beyond the smem cap (fused: global scratch)
 ])
 def test_attention_random_vs_oracle(capi, O, cfg, version):
     c = attn_case(*cfg)

@@ -172,8 +172,12 @@ def paged_attention_fused_metrics(out, kv_metrics, query, key_cache, value_cache
     a = _attn_args(query, key_cache, value_cache, num_kv_heads, scale, block_tables, context_lens,
                    kv_position, last_position, kv_metric_buffer_len, block_size, max_context_len,
                    alibi_slopes)
-    _check(native.load_lib().kvc_paged_attention_fused_metrics(_ptr(out), _ptr(kv_metrics), *a,
-                                                               _stream()))
+    lib = native.load_lib()
+    lib.kvc_paged_attention_fused_metrics_workspace_bytes.restype = ctypes.c_size_t
+    nbytes = int(lib.kvc_paged_attention_fused_metrics_workspace_bytes(query.shape[0], query.shape[1], max_context_len))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=query.device) if nbytes else None
+    _check(lib.kvc_paged_attention_fused_metrics(_ptr(out), _ptr(kv_metrics), *a, _ptr(ws),
+                                                 ctypes.c_size_t(nbytes), _stream()))
 
 
 def select_evictions(evicted_logical_indices, evicted_kv_count, evicted_block_count, kv_metrics,

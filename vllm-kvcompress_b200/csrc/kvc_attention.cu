@@ -25,6 +25,8 @@
 //
 // v1 = one CTA sweeps the whole context.  v2 = 512-token partitions + reduce kernel,
 // same buffers as the reference.  fused = v1 + sum_q p^2 accumulated into kv_metrics.
+#include <stdlib.h>
+
 #include "kvc_common.cuh"
 
 namespace kvc {
@@ -59,19 +61,20 @@ struct AttnParams {
   int64_t q_stride, kv_block_stride;
   int record;
   int max_partitions;
+  int num_seqs;
 };
 
 template <bool BF16>
 __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2,
                                          uint32_t a3, uint32_t b0, uint32_t b1) {
   if constexpr (BF16) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
         "{%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
   } else {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
         "{%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -368,6 +371,397 @@ __global__ void __launch_bounds__(kAttnThreads) paged_attention_kernel(AttnParam
   }
 }
 
+
+// -----------------------------------------------------------------------------
+// Streaming kernel for the compressed regime (many (seq, head) items, short contexts):
+// ONE WARP owns a whole (sequence, kv head) item, so there is no cross-warp merge, no CTA
+// barrier and no partial-output traffic.  K/V blocks are staged by TMA bulk copies
+// (cp.async.bulk, 4 KB K + 4 KB V per block, completion on a per-stage mbarrier) into a
+// private ring of NSTAGE stages per warp; lane 0 runs the ring NSTAGE-1 blocks ahead of the
+// math, so each warp keeps (NSTAGE-1) * 8 KB in flight without holding registers, and the SM
+// keeps warps_per_SM * that.  MMA fragments are read from the staged blocks with the same
+// vector shapes as the direct-from-global kernel above (16 B per lane for K, 8 B for V).
+// grid = ceil(S * H / 4) CTAs of 4 independent warps.
+// -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// CTA = kConsumers consumer warps (one (seq, head) item each) + 1 producer warp.
+constexpr int kConsumers = 7;
+constexpr int kStreamThreads = (kConsumers + 1) * kWarp;
+constexpr int kUnitBytes = kB * kD;  // 2 KB: half a K block (8 of 16 chunks) or half a V block (64 rows)
+constexpr int kNUnit = 6;            // ring slots per consumer: 12 KB, 5 units (10 KB) of look-ahead
+// units of block b in consumption order: K lo, K hi, V lo, V hi
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Warp-specialised streaming kernel.  The producer warp's lane w feeds consumer w: it walks the
+// item's block table and issues one cp.async.bulk per 2 KB unit into the consumer's private ring
+// as soon as the slot's "empty" mbarrier says its fragments are in registers.  A consumer warp does
+// no address generation for global memory at all: wait(full) -> LDS fragments -> arrive(empty) ->
+// MMA.  No CTA-wide barrier, no cross-warp merge.
+template <bool BF16, int NT, int MODE, bool ALIBI>
+__global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kernel(AttnParams p, float* scratch,
+                                                                                   int scratch_tokens) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  constexpr int kPsBytes = NT * 8 * 16 * 2;
+  constexpr int kPerWarp = kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32;
+  const int H = p.num_kv_heads, Q = p.Q;
+  const int num_items = p.num_kv_heads * p.num_seqs;
+  auto ring_of = [&](int w) { return smem_raw + (size_t)w * kPerWarp; };
+  auto full_of = [&](int w) { return smem_u32(ring_of(w) + kNUnit * kUnitBytes + kPsBytes); };
+  auto empty_of = [&](int w) { return full_of(w) + kNUnit * 8; };
+
+  if (wid < kConsumers && lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kNUnit; ++i) {
+      mbar_init(full_of(wid) + 8 * i, 1);
+      mbar_init(empty_of(wid) + 8 * i, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // =========================== producer warp ===========================
+  if (wid == kConsumers) {
+    const int item = blockIdx.x * kConsumers + lane;
+    if (lane >= kConsumers || item >= num_items) return;
+    const int* __restrict__ bt = p.block_tables + (int64_t)item * p.max_num_blocks_per_seq;
+    const int bt0 = bt[0];                 // speculative: issued together with the context length
+    const int ctx = p.context_lens[item];  // item == s * H + h
+    const int nblk = (ctx + kB - 1) / kB;
+    if (nblk == 0) return;
+    const uint16_t* __restrict__ kc = reinterpret_cast<const uint16_t*>(p.k_cache);
+    const uint16_t* __restrict__ vc = reinterpret_cast<const uint16_t*>(p.v_cache);
+    const uint32_t ring = smem_u32(ring_of(lane)), full = full_of(lane), empty = empty_of(lane);
+    int slot = 0, round = 0;  // unit u = round * kNUnit + slot
+    int phys = bt0;
+    for (int b = 0; b < nblk; ++b) {
+      const int next_phys = (b + 1 < nblk) ? bt[b + 1] : 0;  // prefetch the next table entry
+      const uint16_t* kp = kc + (int64_t)phys * p.kv_block_stride;
+      const uint16_t* vp = vc + (int64_t)phys * p.kv_block_stride;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (round > 0) mbar_wait(empty + 8 * slot, (round - 1) & 1);  // consumer drained this slot
+        mbar_expect_tx(full + 8 * slot, kUnitBytes);
+        bulk_g2s(ring + slot * kUnitBytes, ((r & 2) ? vp : kp) + (r & 1) * (kUnitBytes / 2), kUnitBytes, full + 8 * slot);
+        if (++slot == kNUnit) { slot = 0; ++round; }
+      }
+      phys = next_phys;
+    }
+    return;
+  }
+
+  // =========================== consumer warps ===========================
+  const int g = lane >> 2, c = lane & 3;
+  const int item = blockIdx.x * kConsumers + wid;
+  if (item >= num_items) return;
+  const int s = item / H, h = item - s * H;
+  const int ctx = p.context_lens[item];
+  const int nblk = (ctx + kB - 1) / kB;
+  uint16_t* outp = reinterpret_cast<uint16_t*>(p.out) + ((int64_t)s * p.num_heads + h * Q) * kD;
+  if (ctx <= 0) {
+    for (int i = lane; i < Q * kD; i += kWarp) outp[i] = 0;
+    return;
+  }
+  unsigned char* ring = ring_of(wid);
+  uint16_t* psw = reinterpret_cast<uint16_t*>(ring + kNUnit * kUnitBytes);
+  const uint32_t full = full_of(wid), empty = empty_of(wid);
+  const int* __restrict__ bt = p.block_tables + (int64_t)item * p.max_num_blocks_per_seq;
+  const int max_pos = p.last_position[s] - p.kv_metric_buffer_len[s];
+  // fused mode parks raw logits transposed, [q][token], in an L2-resident scratch row of this item;
+  // v1 mode parks them in kv_metric_out itself
+  float* lg0 = nullptr;
+  float* lg1 = nullptr;
+  if (MODE == kModeFused) {
+    lg0 = scratch + ((int64_t)item * Q + 2 * c) * scratch_tokens;  // column q = 2c (nt = 0)
+    lg1 = lg0 + scratch_tokens;
+  }
+
+  uint4 qf[NT][4];
+  float slope[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int ql = nt * 8 + g;
+    const uint16_t* qp = reinterpret_cast<const uint16_t*>(p.q) + (int64_t)s * p.q_stride + (int64_t)(h * Q + ql) * kD;
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4)
+      qf[nt][s4] = (ql < Q) ? *reinterpret_cast<const uint4*>(qp + (4 * s4 + c) * 8) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int qc = nt * 8 + 2 * c + i;
+      slope[nt][i] = (ALIBI && qc < Q) ? p.alibi_slopes[h * Q + qc] : 0.f;
+    }
+  }
+  float m_run[NT][2], l_part[NT][2];  // running max per column; per-lane PARTIAL sums (reduced at the end)
+  float oacc[NT][8][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    m_run[nt][0] = m_run[nt][1] = -INFINITY;
+    l_part[nt][0] = l_part[nt][1] = 0.f;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) oacc[nt][dt][i] = 0.f;
+  }
+  // per-lane fragment offsets inside a unit (bytes): K chunk c of token g; V row g, tokens 4c..4c+3
+  const int koff = c * (kB * 16) + g * 16;
+  const int voff = g * (kB * 2) + c * 8;
+  int slot = 0;
+  uint32_t phase = 0;
+  auto next_unit = [&]() -> const unsigned char* {  // wait for the next unit of the ring
+    mbar_wait(full + 8 * slot, phase);
+    return ring + slot * kUnitBytes;
+  };
+  auto release_unit = [&]() {  // fragments of the current unit are in registers on every lane
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + 8 * slot);
+    if (++slot == kNUnit) { slot = 0; phase ^= 1u; }
+  };
+
+  for (int b = 0; b < nblk; ++b) {
+    const int tok0 = b * kB + g, tok1 = tok0 + 8;
+    const bool last = (b == nblk - 1);
+    bool rec0 = false, rec1 = false;
+    int64_t slot0 = 0, slot1 = 0;
+    if (MODE == kModeV1 && p.record) {  // independent of the staged data: issued before the waits
+      const int64_t phys = bt[b];
+      slot0 = phys * kB + g;
+      slot1 = slot0 + 8;
+      rec0 = tok0 < ctx && p.kv_position[slot0] <= max_pos;
+      rec1 = tok1 < ctx && p.kv_position[slot1] <= max_pos;
+    }
+    // ---- S^T = K Q^T: two independent chains (K halves) ----
+    float sacc[2][NT][4];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const unsigned char* kS = next_unit() + koff;
+      uint4 ka[2], kb[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {  // chunk 4*(2*hf+j) + c of the block = chunk 4*j + c of this half
+        ka[j] = *reinterpret_cast<const uint4*>(kS + j * (4 * kB * 16));
+        kb[j] = *reinterpret_cast<const uint4*>(kS + j * (4 * kB * 16) + 8 * 16);
+      }
+      release_unit();
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        sacc[hf][nt][0] = sacc[hf][nt][1] = sacc[hf][nt][2] = sacc[hf][nt][3] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int s4 = 2 * hf + j;
+          mma16816<BF16>(sacc[hf][nt], ka[j].x, kb[j].x, ka[j].y, kb[j].y, qf[nt][s4].x, qf[nt][s4].y);
+          mma16816<BF16>(sacc[hf][nt], ka[j].z, kb[j].z, ka[j].w, kb[j].w, qf[nt][s4].z, qf[nt][s4].w);
+        }
+      }
+    }
+    // ---- logits + online softmax ----
+    bool rescale = false;
+    float alpha[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float pexp[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float s0 = (sacc[0][nt][i] + sacc[1][nt][i]) * p.scale;
+        float s1 = (sacc[0][nt][2 + i] + sacc[1][nt][2 + i]) * p.scale;
+        if (ALIBI) {
+          s0 += slope[nt][i] * (float)(tok0 - ctx + 1);
+          s1 += slope[nt][i] * (float)(tok1 - ctx + 1);
+        }
+        if (last) {
+          if (tok0 >= ctx) s0 = -INFINITY;
+          if (tok1 >= ctx) s1 = -INFINITY;
+        }
+        const int qc = nt * 8 + 2 * c + i;
+        if (qc < Q) {
+          if (MODE == kModeFused) {
+            float* lg = (i ? lg1 : lg0) + nt * 8 * scratch_tokens;
+            lg[tok0] = s0;  // slots beyond ctx exist in the scratch row (padded to a block multiple)
+            lg[tok1] = s1;
+          } else {
+            if (rec0) p.metric[slot0 * Q + qc] = s0;
+            if (rec1) p.metric[slot1 * Q + qc] = s1;
+          }
+        }
+        float mx = fmaxf(s0, s1);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+        const float m_new = fmaxf(m_run[nt][i], mx);
+        alpha[nt][i] = __expf(m_run[nt][i] - m_new);
+        rescale |= (m_new != m_run[nt][i]);
+        const float p0 = __expf(s0 - m_new), p1 = __expf(s1 - m_new);
+        l_part[nt][i] = l_part[nt][i] * alpha[nt][i] + (p0 + p1);
+        m_run[nt][i] = m_new;
+        pexp[i] = p0;
+        pexp[2 + i] = p1;
+      }
+      uint16_t* pq = psw + nt * 8 * 16 + (2 * c) * 16 + g;
+      pq[0] = to_bits16<BF16>(pexp[0]);
+      pq[16] = to_bits16<BF16>(pexp[1]);
+      pq[8] = to_bits16<BF16>(pexp[2]);
+      pq[24] = to_bits16<BF16>(pexp[3]);
+    }
+    // the running max rarely moves after the first blocks: skip the 64 multiplies when it did not
+    if (__any_sync(0xffffffffu, rescale)) {
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+          oacc[nt][dt][0] *= alpha[nt][0];
+          oacc[nt][dt][1] *= alpha[nt][1];
+          oacc[nt][dt][2] *= alpha[nt][0];
+          oacc[nt][dt][3] *= alpha[nt][1];
+        }
+    }
+    // ---- O^T += V^T P^T, one V half (four d-tiles) at a time ----
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const unsigned char* vS = next_unit() + voff;
+      uint2 va[4], vb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // rows 16*(4*hf+j) + g (+8) of the block = rows 16*j + g (+8) of this half
+        va[j] = *reinterpret_cast<const uint2*>(vS + j * (16 * kB * 2));
+        vb[j] = *reinterpret_cast<const uint2*>(vS + j * (16 * kB * 2) + 8 * kB * 2);
+      }
+      release_unit();  // its __syncwarp also orders this block's P stores before the P loads below
+      if (last && (ctx & (kB - 1)) != 0) {  // tokens beyond the context may hold NaNs (reference :370-379)
+        const int vcnt = ctx - b * kB;
+        const int t0 = 4 * c;
+        const uint32_t mlo = (t0 < vcnt ? 0xffffu : 0u) | (t0 + 1 < vcnt ? 0xffff0000u : 0u);
+        const uint32_t mhi = (t0 + 2 < vcnt ? 0xffffu : 0u) | (t0 + 3 < vcnt ? 0xffff0000u : 0u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          va[j].x &= mlo; va[j].y &= mhi;
+          vb[j].x &= mlo; vb[j].y &= mhi;
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const uint2 pb = *reinterpret_cast<const uint2*>(psw + nt * 8 * 16 + g * 16 + 4 * c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          mma16816<BF16>(oacc[nt][4 * hf + j], va[j].x, vb[j].x, va[j].y, vb[j].y, pb.x, pb.y);
+      }
+    }
+    __syncwarp();  // P buffer is rewritten next iteration
+  }
+
+  // ---- output: O / (L + 1e-6); lane (g,c) holds O[d = 16 dt + g (+8)][q = 2c, 2c+1] ----
+  float inv[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float l = l_part[nt][i];
+      l += __shfl_xor_sync(0xffffffffu, l, 4);
+      l += __shfl_xor_sync(0xffffffffu, l, 8);
+      l += __shfl_xor_sync(0xffffffffu, l, 16);
+      inv[nt][i] = __fdividef(1.f, l + 1e-6f);
+      const int qc = nt * 8 + 2 * c + i;
+      if (qc < Q) {
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+          outp[qc * kD + 16 * dt + g] = to_bits16<BF16>(oacc[nt][dt][i] * inv[nt][i]);
+          outp[qc * kD + 16 * dt + g + 8] = to_bits16<BF16>(oacc[nt][dt][2 + i] * inv[nt][i]);
+        }
+      }
+    }
+  if (MODE == kModeFused || (MODE == kModeV1 && p.record)) {
+    // per-q max / inverse sum to every lane: column q lives in lanes with c == (q % 8) / 2
+    __syncwarp();
+    float* mi = reinterpret_cast<float*>(psw);  // reuse the P buffer: [NT*8][2] = (M, inv)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (g == 0) {
+          mi[(nt * 8 + 2 * c + i) * 2] = m_run[nt][i];
+          mi[(nt * 8 + 2 * c + i) * 2 + 1] = inv[nt][i];
+        }
+    __syncwarp();
+    constexpr int U = 8;  // loads are issued in batches of U per lane so that their latencies overlap
+    if (MODE == kModeV1) {
+      const int n = ctx * Q;
+      for (int i0 = 0; i0 < n; i0 += U * kWarp) {
+        int64_t idx[U];
+        int pos[U];
+        float lg[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * kWarp + lane;
+          idx[u] = -1;
+          if (i < n) {
+            const int t = i / Q;
+            idx[u] = ((int64_t)bt[t / kB] * kB + t % kB) * Q + i % Q;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          pos[u] = (idx[u] >= 0) ? p.kv_position[idx[u] / Q] : 0x7fffffff;
+          lg[u] = (idx[u] >= 0) ? p.metric[idx[u]] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (idx[u] >= 0 && pos[u] <= max_pos) {
+            const int q = (i0 + u * kWarp + lane) % Q;
+            p.metric[idx[u]] = __expf(lg[u] - mi[q * 2]) * mi[q * 2 + 1];
+          }
+        }
+      }
+    } else {
+      const float* lgi = scratch + (int64_t)item * Q * scratch_tokens;
+      for (int t0 = 0; t0 < ctx; t0 += U * kWarp) {
+        int64_t sl[U];
+        int pos[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int t = t0 + u * kWarp + lane;
+          sl[u] = (t < ctx) ? (int64_t)bt[t / kB] * kB + t % kB : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) pos[u] = (sl[u] >= 0) ? p.kv_position[sl[u]] : 0x7fffffff;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (sl[u] >= 0 && pos[u] <= max_pos) {
+            const int t = t0 + u * kWarp + lane;
+            float acc = 0.f;
+            for (int q = 0; q < Q; ++q) {
+              const float pr = __expf(lgi[q * scratch_tokens + t] - mi[q * 2]) * mi[q * 2 + 1];
+              acc += pr * pr;
+            }
+            // every slot belongs to exactly one warp: a fire-and-forget reduction, no read-back
+            atomicAdd(&p.metric[sl[u]], acc);
+          }
+        }
+      }
+    }
+  }
+}
+
 // -----------------------------------------------------------------------------
 // v2 reduce.  grid (num_kv_heads, num_seqs), 128 threads.  reference :525-652.
 // -----------------------------------------------------------------------------
@@ -465,6 +859,46 @@ static int dispatch_attention(const AttnParams& p, int num_seqs, int partitions,
   KVC_FAIL(KVC_ERR_UNSUPPORTED, "paged attention: %d query heads per kv head (max 16)", p.Q);
 }
 
+
+template <bool BF16, int NT, int MODE>
+static int launch_stream(const AttnParams& p, int num_seqs, float* scratch, int scratch_tokens, cudaStream_t st) {
+  const size_t smem = (size_t)kConsumers * (kNUnit * kUnitBytes + NT * 8 * 16 * 2 + 2 * kNUnit * 8 + 32);
+  const int items = num_seqs * p.num_kv_heads;
+  const dim3 grid((items + kConsumers - 1) / kConsumers);
+  cudaError_t e;
+  if (p.alibi_slopes) {
+    auto kern = paged_attention_stream_kernel<BF16, NT, MODE, true>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) kern<<<grid, kStreamThreads, smem, st>>>(p, scratch, scratch_tokens);
+  } else {
+    auto kern = paged_attention_stream_kernel<BF16, NT, MODE, false>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) kern<<<grid, kStreamThreads, smem, st>>>(p, scratch, scratch_tokens);
+  }
+  if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "paged attention (stream) smem attr: %s", cudaGetErrorString(e));
+  KVC_CHECK_LAUNCH("paged_attention_stream_kernel");
+  return KVC_OK;
+}
+
+template <int MODE>
+static int dispatch_stream(const AttnParams& p, int num_seqs, float* scratch, int scratch_tokens, int dtype,
+                           cudaStream_t st) {
+  const int nt = (p.Q + 7) / 8;
+  if (dtype == KVC_F16) {
+    if (nt == 1) return launch_stream<false, 1, MODE>(p, num_seqs, scratch, scratch_tokens, st);
+    if (nt == 2) return launch_stream<false, 2, MODE>(p, num_seqs, scratch, scratch_tokens, st);
+  } else {
+    if (nt == 1) return launch_stream<true, 1, MODE>(p, num_seqs, scratch, scratch_tokens, st);
+    if (nt == 2) return launch_stream<true, 2, MODE>(p, num_seqs, scratch, scratch_tokens, st);
+  }
+  KVC_FAIL(KVC_ERR_UNSUPPORTED, "paged attention: %d query heads per kv head (max 16)", p.Q);
+}
+
+// one warp per (seq, head) pays off when there are enough items to fill the machine
+static bool use_stream_kernel(int num_seqs, int num_kv_heads, int max_context_len) {
+  return (long long)num_seqs * num_kv_heads >= 148 * 4 || max_context_len <= 512;
+}
+
 static int fill_params(AttnParams& p, void* out, float* metric, const void* query,
                        const void* key_cache, const void* value_cache, int num_seqs, int num_heads,
                        int num_kv_heads, int head_size, float scale, const int* block_tables,
@@ -494,13 +928,15 @@ static int fill_params(AttnParams& p, void* out, float* metric, const void* quer
   p.num_heads = num_heads; p.num_kv_heads = num_kv_heads; p.Q = num_heads / num_kv_heads;
   p.scale = scale; p.max_num_blocks_per_seq = max_num_blocks_per_seq;
   p.q_stride = q_stride; p.kv_block_stride = kv_block_stride;
-  p.record = record ? 1 : 0; p.max_partitions = 1;
+  p.record = record ? 1 : 0; p.max_partitions = 1; p.num_seqs = num_seqs;
   return KVC_OK;
 }
 
 }  // namespace kvc
 
 using namespace kvc;
+
+extern "C" size_t kvc_paged_attention_fused_metrics_workspace_bytes(int num_seqs, int num_heads, int max_context_len);
 
 extern "C" int kvc_paged_attention_v1(
     void* out, float* kv_metric_out, const void* query, const void* key_cache,
@@ -517,6 +953,8 @@ extern "C" int kvc_paged_attention_v1(
                        q_stride, kv_block_stride, alibi_slopes, dtype, record_kv_metrics);
   if (rc != KVC_OK) return rc;
   if (num_seqs == 0) return KVC_OK;
+  if (use_stream_kernel(num_seqs, num_kv_heads, max_context_len))
+    return dispatch_stream<kModeV1>(p, num_seqs, nullptr, 0, dtype, as_stream(stream));
   return dispatch_attention<kModeV1>(p, num_seqs, 1, 0, dtype, as_stream(stream));
 }
 
@@ -558,7 +996,7 @@ extern "C" int kvc_paged_attention_fused_metrics(
     const int* block_tables, const int* context_lens, const int* kv_position,
     const int* last_position, const int* kv_metric_buffer_len, int block_size, int max_context_len,
     int max_num_blocks_per_seq, int64_t q_stride, int64_t kv_block_stride,
-    const float* alibi_slopes, int dtype, kvc_stream_t stream) {
+    const float* alibi_slopes, int dtype, void* workspace, size_t workspace_bytes, kvc_stream_t stream) {
   AttnParams p;
   int rc = fill_params(p, out, kv_metrics, query, key_cache, value_cache, num_seqs, num_heads,
                        num_kv_heads, head_size, scale, block_tables, context_lens, kv_position,
@@ -568,5 +1006,19 @@ extern "C" int kvc_paged_attention_fused_metrics(
   KVC_REQUIRE(max_context_len > 0, KVC_ERR_INVALID, "fused attention: max_context_len <= 0");
   if (num_seqs == 0) return KVC_OK;
   const int padded = (max_context_len + kB - 1) / kB * kB;
+  if (use_stream_kernel(num_seqs, num_kv_heads, max_context_len)) {
+    const size_t need = kvc_paged_attention_fused_metrics_workspace_bytes(num_seqs, num_heads, max_context_len);
+    KVC_REQUIRE(workspace && workspace_bytes >= need, KVC_ERR_WORKSPACE,
+                "fused attention: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+    return dispatch_stream<kModeFused>(p, num_seqs, reinterpret_cast<float*>(workspace), padded, dtype,
+                                       as_stream(stream));
+  }
   return dispatch_attention<kModeFused>(p, num_seqs, 1, padded, dtype, as_stream(stream));
+}
+
+extern "C" size_t kvc_paged_attention_fused_metrics_workspace_bytes(int num_seqs, int num_heads,
+                                                                    int max_context_len) {
+  const int padded = (max_context_len + kB - 1) / kB * kB;
+  if (num_seqs <= 0) return 0;
+  return (size_t)num_seqs * num_heads * padded * sizeof(float);  // raw logits [S, Hq, padded]
 }

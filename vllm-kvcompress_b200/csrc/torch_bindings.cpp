@@ -309,13 +309,16 @@ void kvcompress_paged_attention_fused_metrics(
   AttnCommon c = attn_common(out, query, key_cache, value_cache, block_tables, alibi_slopes, kv_cache_dtype);
   TORCH_CHECK(kv_metrics.scalar_type() == at::kFloat && kv_metrics.is_contiguous(), "kv_metrics must be contiguous float32");
   const at::cuda::OptionalCUDAGuard guard(device_of(query));
+  const size_t ws_bytes = kvc_paged_attention_fused_metrics_workspace_bytes(c.S, c.Hq, (int)max_context_len);
+  auto ws = torch::empty({(int64_t)ws_bytes}, query.options().dtype(at::kByte));
   check_status(kvc_paged_attention_fused_metrics(
                    out.data_ptr(), kv_metrics.data_ptr<float>(), query.data_ptr(), key_cache.data_ptr(),
                    value_cache.data_ptr(), c.S, c.Hq, (int)num_kv_heads, c.D, (float)scale,
                    i32(block_tables, "block_tables"), i32(context_lens, "context_lens"),
                    i32(kv_position, "kv_position"), i32(last_position, "last_position"),
                    i32(kv_metric_buffer_len, "kv_metric_buffer_len"), (int)block_size, (int)max_context_len,
-                   c.MB, c.q_stride, c.kv_block_stride, c.alibi, c.dtype, cur_stream()),
+                   c.MB, c.q_stride, c.kv_block_stride, c.alibi, c.dtype, ws_bytes ? ws.data_ptr() : nullptr,
+                   ws_bytes, cur_stream()),
                "kvcompress_paged_attention_fused_metrics");
 }
 

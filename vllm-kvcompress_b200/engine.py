@@ -260,32 +260,44 @@ class DecodeHotPath:
         main.wait_stream(self._d2h)   # the step is complete when its results are in host memory
 
     # ------------------------------------------------------------------ measurement helper
-    def profile_attention(self, qkv: torch.Tensor, out: torch.Tensor, steps: int = 3):
-        """Run `steps` eager steps with CUDA events around every attention launch (recorded on the
-        launching stream).  Returns (mean ms per launch, mean algorithmic bytes per launch)."""
-        L = self.cfg.num_layers
-        pairs = []
-        total_bytes = 0
-        for _ in range(steps):
-            self.compress()
-            self.append_slots()
-            total_bytes += self.attention_bytes()
-            last_pos = self.seq_len - 1
+    def profile_attention(self, qkv: torch.Tensor, out: torch.Tensor, steps: int = 5):
+        """Device time of the attention launches alone: the L launches of one step (current state)
+        are captured in a CUDA graph, so no host launch gap sits between the two CUDA events that
+        bracket each replay (events recorded on the launching stream).  Returns (mean ms per
+        launch, mean algorithmic bytes per launch)."""
+        cfg, st = self.cfg, self.st
+        L = cfg.num_layers
+        H, Q, D, B = cfg.num_kv_heads, cfg.queries_per_kv, cfg.head_size, cfg.block_size
+        Hq = H * Q
+        last_pos = self.seq_len - 1
+
+        def attn_only():
             for l in range(L):
-                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                self.forward_layer(l, qkv[l], out[l], last_pos, timing=ev)
-                pairs.append(ev)
-            self._aggregate_unfused()
+                q = qkv[l][:, : Hq * D].view(-1, Hq, D)
+                o = out[l].view(-1, Hq, D)
+                if cfg.fused_metrics:
+                    ops.paged_attention_kvc_fused_metrics(o, st.kv_metrics, q, st.k_cache, st.v_cache, H,
+                                                          self.scale, st.block_tables[l], st.context_lens[l],
+                                                          st.kv_position, last_pos, self.zeros_s, B, self.max_ctx)
+                else:
+                    ops.paged_attention_kvc_v1(o, self.temp_metrics, q, st.k_cache, st.v_cache, H, self.scale,
+                                               st.block_tables[l], st.context_lens[l], st.kv_position, last_pos,
+                                               self.zeros_s, B, self.max_ctx, None, "auto", 1.0, 1.0, True)
+
+        attn_only()
         torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b in pairs) / len(pairs)
-        return ms, total_bytes / (steps * L)
-
-    @property
-    def tokens_per_step(self) -> int:
-        return self.cfg.num_seqs
-
-    def attention_bytes(self) -> int:
-        """Algorithmic bytes of one step's attention launches: K+V of every
-        context token once (2*D*2 B) + position read (4 B) + metric read-modify-write (8 B)."""
-        ctx_total = int(self.st.context_lens.sum())
-        return ctx_total * (2 * self.cfg.head_size * 2 + 4 + 8)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            attn_only()
+        graph.replay()
+        torch.cuda.synchronize()
+        pairs = []
+        for _ in range(steps):
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+            graph.replay()
+            ev[1].record()
+            pairs.append(ev)
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b in pairs) / (len(pairs) * L)
+        return ms, self.attention_bytes() / L
