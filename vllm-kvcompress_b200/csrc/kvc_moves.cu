@@ -69,15 +69,17 @@ __global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_ker
     int total_heads) {
   constexpr int B = 16, D = 128;
   constexpr int kBlockElems = B * D;  // 2048 two-byte elements = 4 KB
-  const int g = blockIdx.x;
-  if (g >= total_heads) return;
+  // one WARP per head (steady-state compression schedules ~1 run per head: a CTA per head would
+  // leave three of its four warps idle); blockIdx.y strides over the head's 32-move segments
   const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int g = blockIdx.x * kMoveWarps + wid;
+  if (g >= total_heads) return;
   const int cnt = move_count[g];
   const int off = move_offsets[g];
   const int nseg = (cnt + kMovesPerSegment - 1) / kMovesPerSegment;
   const int2* __restrict__ mv = moves + off;
 
-  for (int seg = blockIdx.y * kMoveWarps + wid; seg < nseg; seg += gridDim.y * kMoveWarps) {
+  for (int seg = blockIdx.y; seg < nseg; seg += gridDim.y) {
     const int base = seg * kMovesPerSegment;
     // window of 48 moves: [base, base+32) in `a`, lookahead [base+32, base+48) in `la`
     const bool a_ok = base + lane < cnt;
@@ -254,13 +256,13 @@ extern "C" int kvc_execute_cache_moves(
   if (total_heads <= 0) return KVC_OK;
   cudaStream_t st = as_stream(stream);
   const int2* mv = reinterpret_cast<const int2*>(cache_moves_idx);
-  // enough CTAs per head to fill 148 SMs several times over when there are few heads
-  int gy = (148 * 16 + total_heads - 1) / total_heads;
-  gy = gy < 1 ? 1 : (gy > 64 ? 64 : gy);
+  // enough warps (one per (head, segment stride)) to fill 148 SMs several times over
+  int gy = (148 * 64 + total_heads - 1) / total_heads;
+  gy = gy < 1 ? 1 : (gy > 256 ? 256 : gy);
   const bool two_byte = (dtype == KVC_F16 || dtype == KVC_BF16);
   if (two_byte && head_size == 128 && vec_size == 8 && block_size == 16 &&
       (reinterpret_cast<uintptr_t>(k_cache) & 15) == 0 && (reinterpret_cast<uintptr_t>(v_cache) & 15) == 0) {
-    execute_moves_b16_d128_kernel<<<dim3(total_heads, gy), kMoveWarps * kWarp, 0, st>>>(
+    execute_moves_b16_d128_kernel<<<dim3((total_heads + kMoveWarps - 1) / kMoveWarps, gy), kMoveWarps * kWarp, 0, st>>>(
         reinterpret_cast<uint16_t*>(k_cache), reinterpret_cast<uint16_t*>(v_cache), kv_metrics,
         kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads);
     KVC_CHECK_LAUNCH("execute_moves_b16_d128_kernel");

@@ -22,14 +22,16 @@
 // keys evicts its (k-1)*B + r0 lowest-metric candidates.
 //
 // Three launches, no host round trip:
-//   1. rank:   one warp (ctx <= 256) or one CTA per head; keys staged in shared memory, rank by
-//              counting (n^2/threads compares, n ~ 144 in steady state); completion keys and
-//              per-slot ranks to workspace.
+//   1. keys:   ctx <= 256: one warp per head, 8 consecutive slots per lane (two 16 B loads of
+//              metrics and of positions), a 256-key bitonic sort in registers (warp shuffles), the
+//              completion keys = sorted ranks r0-1+kB go to the workspace.  Longer contexts: one CTA
+//              per head, keys staged in shared memory, rank by counting.
 //   2. select: one CTA per sequence; 4-pass radix select of the E-th smallest completion key,
 //              then per-head lower/upper bounds + an exclusive scan for deterministic ties.
-//   3. emit:   same grouping as 1; ordered compaction of slots with rank < count.
-// All of it is int32/fp32 gather traffic: 8 B read per slot in (1), 4 B written + read for the
-// rank, 4 B per evicted index; HBM/L2-bound, no tensor-core shapes.
+//   3. emit:   same grouping as 1; a slot is evicted iff its key is below the head's last granted
+//              completion key (ties at that key in logical order); ordered compaction by prefix sums.
+// All of it is int32/fp32 gather traffic: 2 x 8 B read per slot, 4 B per evicted index, 4 B per
+// block of completion keys; HBM/L2-bound, no tensor-core shapes.
 #include "kvc_common.cuh"
 
 namespace kvc {
@@ -55,70 +57,267 @@ struct SelectParams {
   const int* last_position;  // [S]
   const int* protected_window;  // [S]
   int S, L, H, MB, B, null_index;
-  int* ranks;        // [total slots] workspace
   unsigned* events;  // [total slots / B] workspace
 };
 
-// group = GT threads cooperating on one head (32 = a warp, 128 = the whole CTA)
-template <int GT>
-__device__ __forceinline__ void group_sync() {
-  if (GT == kWarp) __syncwarp(); else __syncthreads();
+// load the (up to) 8 consecutive logical slots i0..i0+7 of a head as orderable keys
+// (kInfKey for non-candidates and for i >= n); i0 is a multiple of 8 so the slots are half a block
+template <int B>
+__device__ __forceinline__ void load_keys8(const SelectParams& p, const int* __restrict__ bt, int i0, int n,
+                                           int max_pos, unsigned (&k)[8]) {
+  if (B == 16) {
+    if (i0 < n) {
+      const int64_t slot = (int64_t)bt[i0 >> 4] * 16 + (i0 & 15);
+      const float4 m0 = *reinterpret_cast<const float4*>(p.kv_metrics + slot);
+      const float4 m1 = *reinterpret_cast<const float4*>(p.kv_metrics + slot + 4);
+      const int4 q0 = *reinterpret_cast<const int4*>(p.kv_position + slot);
+      const int4 q1 = *reinterpret_cast<const int4*>(p.kv_position + slot + 4);
+      const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      const int q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+      for (int r = 0; r < 8; ++r) k[r] = (i0 + r < n && q[r] <= max_pos) ? orderable(m[r]) : kInfKey;
+    } else {
+#pragma unroll
+      for (int r = 0; r < 8; ++r) k[r] = kInfKey;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int i = i0 + r;
+      unsigned key = kInfKey;
+      if (i < n) {
+        const int64_t slot = (int64_t)bt[i / B] * B + i % B;
+        if (p.kv_position[slot] <= max_pos) key = orderable(p.kv_metrics[slot]);
+      }
+      k[r] = key;
+    }
+  }
 }
 
-template <int GT>
-__global__ void __launch_bounds__(128) select_rank_kernel(SelectParams p, int max_slots) {
-  extern __shared__ unsigned sk[];  // [groups][max_slots]
-  constexpr int GROUPS = 128 / GT;
-  const int grp = threadIdx.x / GT, t = threadIdx.x % GT;
-  const int g = blockIdx.x * GROUPS + grp;  // (s,l,h) flat
-  const int total = p.S * p.L * p.H;
-  const bool active = g < total;
-  unsigned* keys = sk + grp * max_slots;
-  __shared__ int s_ncand[GROUPS];
-  if (t == 0) s_ncand[grp] = 0;
-  group_sync<GT>();
-  int n = 0, off = 0, r0 = 0, nblk = 0;
-  if (active) {
-    const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
-    const int lsh = (l * p.S + s) * p.H + h;
-    n = p.context_lens[lsh];
-    nblk = (n + p.B - 1) / p.B;
-    off = p.offsets[g];
-    r0 = p.hanging[g];
-    const int max_pos = p.last_position[s] - p.protected_window[s];
-    const int* __restrict__ bt = p.block_tables + (int64_t)lsh * p.MB;
-    int local = 0;
-    for (int i = t; i < n; i += GT) {
-      const int64_t slot = (int64_t)bt[i / p.B] * p.B + i % p.B;
-      const bool cand = p.kv_position[slot] <= max_pos;  // K1 :136-139 (i < ctx by construction)
-      unsigned k = orderable(p.kv_metrics[slot]);
-      if (!cand || k == kInfKey) k = kInfKey;
-      else ++local;
-      keys[i] = k;
+// ---- warp-per-head path (ctx <= 256): bitonic sort of 256 keys, 8 per lane ----
+// element e = lane * 8 + r  <->  logical slot e.
+template <int B>
+__global__ void __launch_bounds__(128) select_sort_kernel(SelectParams p) {
+  const int lane = threadIdx.x % kWarp;
+  const int g = blockIdx.x * 4 + threadIdx.x / kWarp;
+  if (g >= p.S * p.L * p.H) return;
+  const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
+  const int lsh = (l * p.S + s) * p.H + h;
+  const int n = p.context_lens[lsh];
+  const int nblk = (n + B - 1) / B;
+  const int off = p.offsets[g];
+  const int r0 = p.hanging[g];
+  const int max_pos = p.last_position[s] - p.protected_window[s];
+  unsigned k[8];
+  load_keys8<B>(p, p.block_tables + (int64_t)lsh * p.MB, lane * 8, n, max_pos, k);
+  int local = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) local += (k[r] != kInfKey);
+  int ncand = local;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, d);
+  // bitonic sort, ascending over e = lane*8 + r
+#pragma unroll
+  for (int kk = 2; kk <= 256; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j >= 1; j >>= 1) {
+      if (j >= 8) {
+        const int lj = j >> 3;
+        const bool up = ((lane * 8) & kk) == 0;      // ascending segment (kk >= 16 here)
+        const bool lower = (lane & lj) == 0;         // this lane holds the lower index of the pair
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const unsigned o = __shfl_xor_sync(0xffffffffu, k[r], lj);
+          const unsigned mn = min(k[r], o), mx = max(k[r], o);
+          k[r] = (up == lower) ? mn : mx;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int pr = r ^ j;
+          if (pr > r) {
+            const bool up = (((lane * 8 + r) & kk) == 0);
+            const unsigned a = k[r], b = k[pr];
+            const unsigned mn = min(a, b), mx = max(a, b);
+            k[r] = up ? mn : mx;
+            k[pr] = up ? mx : mn;
+          }
+        }
+      }
     }
-    if (local) atomicAdd(&s_ncand[grp], local);
   }
-  group_sync<GT>();
-  if (!active) return;
-  const int ncand = s_ncand[grp];
+  // completion keys: sorted rank e = r0-1 + kB for k < nev
+  const int nev = (r0 >= 1 && ncand >= r0) ? (ncand - r0) / B + 1 : 0;
+  unsigned* ev = p.events + off / B;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int e = lane * 8 + r;
+    const int d = e - (r0 - 1);
+    if (d >= 0 && d % B == 0 && d / B < nev) ev[d / B] = k[r];
+  }
+  for (int q = nev + lane; q < nblk; q += kWarp) ev[q] = kInfKey;
+}
+
+template <int B>
+__global__ void __launch_bounds__(128) select_emit_warp_kernel(SelectParams p) {
+  const int lane = threadIdx.x % kWarp;
+  const int g = blockIdx.x * 4 + threadIdx.x / kWarp;
+  if (g >= p.S * p.L * p.H) return;
+  const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
+  const int lsh = (l * p.S + s) * p.H + h;
+  const int n = p.context_lens[lsh];
+  const int nblk = (n + B - 1) / B;
+  const int off = p.offsets[g];
+  const int cnt = p.evicted_kv_count[g];
+  const int kblk = p.evicted_block_count[g];
+  int* __restrict__ out = p.evicted_logical_indices + off;
+  if (cnt > 0) {
+    const int max_pos = p.last_position[s] - p.protected_window[s];
+    unsigned k[8];
+    load_keys8<B>(p, p.block_tables + (int64_t)lsh * p.MB, lane * 8, n, max_pos, k);
+    const unsigned T = p.events[off / B + kblk - 1];  // key of the last evicted rank
+    int nless = 0, neq = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      nless += (k[r] < T);
+      neq += (k[r] == T);
+    }
+    int tot_less = nless;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) tot_less += __shfl_xor_sync(0xffffffffu, tot_less, d);
+    int eq_incl = neq;  // ties at T are granted in logical order
+#pragma unroll
+    for (int d = 1; d < kWarp; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, eq_incl, d);
+      if (lane >= d) eq_incl += v;
+    }
+    int eq_seen = eq_incl - neq;
+    const int allowed = cnt - tot_less;
+    bool evict[8];
+    int nev = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      evict[r] = (k[r] < T) || (k[r] == T && eq_seen < allowed);
+      eq_seen += (k[r] == T);
+      nev += evict[r];
+    }
+    int incl = nev;
+#pragma unroll
+    for (int d = 1; d < kWarp; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    int pos = incl - nev;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (evict[r]) out[pos++] = lane * 8 + r;
+  }
+  for (int i = cnt + lane; i < nblk * B; i += kWarp) out[i] = p.null_index;
+}
+
+// ---- CTA-per-head path (long contexts): rank by counting over keys staged in shared memory ----
+__global__ void __launch_bounds__(128) select_rank_kernel(SelectParams p, int max_slots) {
+  extern __shared__ unsigned keys[];  // [max_slots]
+  __shared__ int s_ncand;
+  const int t = threadIdx.x;
+  const int g = blockIdx.x;
+  const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
+  const int lsh = (l * p.S + s) * p.H + h;
+  const int n = p.context_lens[lsh];
+  const int nblk = (n + p.B - 1) / p.B;
+  const int off = p.offsets[g];
+  const int r0 = p.hanging[g];
+  const int max_pos = p.last_position[s] - p.protected_window[s];
+  const int* __restrict__ bt = p.block_tables + (int64_t)lsh * p.MB;
+  if (t == 0) s_ncand = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = t; i < n; i += 128) {
+    const int64_t slot = (int64_t)bt[i / p.B] * p.B + i % p.B;
+    unsigned k = kInfKey;
+    if (p.kv_position[slot] <= max_pos) k = orderable(p.kv_metrics[slot]);
+    local += (k != kInfKey);
+    keys[i] = k;
+  }
+  if (local) atomicAdd(&s_ncand, local);
+  __syncthreads();
+  const int ncand = s_ncand;
   const int nev = (r0 >= 1 && ncand >= r0) ? (ncand - r0) / p.B + 1 : 0;
   unsigned* ev = p.events + off / p.B;
-  for (int i = t; i < n; i += GT) {
+  for (int i = t; i < n; i += 128) {
     const unsigned ki = keys[i];
-    int rank = -1;
-    if (ki != kInfKey) {
-      int r = 0;
-      for (int j = 0; j < n; ++j) {
-        const unsigned kj = keys[j];
-        r += (kj < ki) || (kj == ki && j < i);
-      }
-      rank = r;
-      if (r0 >= 1 && r >= r0 - 1 && (r - (r0 - 1)) % p.B == 0) ev[(r - (r0 - 1)) / p.B] = ki;
+    if (ki == kInfKey) continue;
+    int r = 0;
+    for (int j = 0; j < n; ++j) {
+      const unsigned kj = keys[j];
+      r += (kj < ki) || (kj == ki && j < i);
     }
-    p.ranks[off + i] = rank;
+    const int d = r - (r0 - 1);
+    if (r0 >= 1 && d >= 0 && d % p.B == 0) ev[d / p.B] = ki;
   }
-  for (int i = n + t; i < nblk * p.B; i += GT) p.ranks[off + i] = -1;
-  for (int k = nev + t; k < nblk; k += GT) ev[k] = kInfKey;
+  for (int k = nev + t; k < nblk; k += 128) ev[k] = kInfKey;
+}
+
+__global__ void __launch_bounds__(128) select_emit_cta_kernel(SelectParams p) {
+  __shared__ int s_less, s_w[4], s_w2[4];
+  const int t = threadIdx.x, lane = t % kWarp, w = t / kWarp;
+  const int g = blockIdx.x;
+  const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
+  const int lsh = (l * p.S + s) * p.H + h;
+  const int n = p.context_lens[lsh];
+  const int nblk = (n + p.B - 1) / p.B;
+  const int off = p.offsets[g];
+  const int cnt = p.evicted_kv_count[g];
+  const int kblk = p.evicted_block_count[g];
+  const int max_pos = p.last_position[s] - p.protected_window[s];
+  const int* __restrict__ bt = p.block_tables + (int64_t)lsh * p.MB;
+  int* __restrict__ out = p.evicted_logical_indices + off;
+  if (cnt > 0) {  // CTA-uniform
+    const unsigned T = p.events[off / p.B + kblk - 1];
+    auto key_of = [&](int i) -> unsigned {
+      const int64_t slot = (int64_t)bt[i / p.B] * p.B + i % p.B;
+      return (p.kv_position[slot] <= max_pos) ? orderable(p.kv_metrics[slot]) : kInfKey;
+    };
+    if (t == 0) s_less = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = t; i < n; i += 128) local += (key_of(i) < T);
+    if (local) atomicAdd(&s_less, local);
+    __syncthreads();
+    const int allowed = cnt - s_less;
+    int eq_base = 0, written = 0;
+    for (int i0 = 0; i0 < n; i0 += 128) {
+      const int i = i0 + t;
+      const unsigned k = (i < n) ? key_of(i) : kInfKey;
+      const bool less = k < T, eq = (k == T) && (k != kInfKey || T != kInfKey) && i < n;
+      const unsigned em = __ballot_sync(0xffffffffu, eq);
+      if (lane == 0) s_w[w] = __popc(em);
+      __syncthreads();
+      int eq_before = eq_base + __popc(em & lanemask_lt());
+      int eq_tot = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q < w) eq_before += s_w[q];
+        eq_tot += s_w[q];
+      }
+      const bool ev = (i < n) && (less || (eq && eq_before < allowed));
+      const unsigned vm = __ballot_sync(0xffffffffu, ev);
+      if (lane == 0) s_w2[w] = __popc(vm);
+      __syncthreads();
+      int pos = written + __popc(vm & lanemask_lt());
+      int tot = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (q < w) pos += s_w2[q];
+        tot += s_w2[q];
+      }
+      if (ev) out[pos] = i;
+      written += tot;
+      eq_base += eq_tot;
+      __syncthreads();
+    }
+  }
+  for (int i = cnt + t; i < nblk * p.B; i += 128) out[i] = p.null_index;
 }
 
 // one CTA per sequence
@@ -221,66 +420,13 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(SelectParams p) {
   }
 }
 
-template <int GT>
-__global__ void __launch_bounds__(128) select_emit_kernel(SelectParams p) {
-  constexpr int GROUPS = 128 / GT;
-  constexpr int GW = GT / kWarp;  // warps per group
-  __shared__ int s_wcnt[GROUPS][GW > 0 ? GW : 1];
-  const int grp = threadIdx.x / GT, t = threadIdx.x % GT;
-  const int lane = threadIdx.x % kWarp, gw = t / kWarp;
-  const int g = blockIdx.x * GROUPS + grp;
-  const int total = p.S * p.L * p.H;
-  const bool active = g < total;
-  int n = 0, off = 0, cnt = 0, nblk = 0;
-  if (active) {
-    const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
-    n = p.context_lens[(l * p.S + s) * p.H + h];
-    nblk = (n + p.B - 1) / p.B;
-    off = p.offsets[g];
-    cnt = p.evicted_kv_count[g];
-  }
-  int* __restrict__ out = p.evicted_logical_indices + off;
-  int written = 0;
-  const int iters = (n + GT - 1) / GT;
-  // all threads of a CTA-wide group must take the same trip count (n is group-uniform)
-  for (int it = 0; it < iters; ++it) {
-    const int i = it * GT + t;
-    bool ev = false;
-    if (active && i < n) {
-      const int r = p.ranks[off + i];
-      ev = (r >= 0 && r < cnt);
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, ev);
-    int base = 0;
-    if (GW > 1) {
-      if (lane == 0) s_wcnt[grp][gw] = __popc(m);
-      __syncthreads();
-      int tot = 0;
-#pragma unroll
-      for (int w = 0; w < GW; ++w) {
-        if (w < gw) base += s_wcnt[grp][w];
-        tot += s_wcnt[grp][w];
-      }
-      if (ev) out[written + base + __popc(m & lanemask_lt())] = i;
-      written += tot;
-      __syncthreads();
-    } else {
-      if (ev) out[written + __popc(m & lanemask_lt())] = i;
-      written += __popc(m);
-    }
-  }
-  if (active) {
-    for (int i = cnt + t; i < nblk * p.B; i += GT) out[i] = p.null_index;
-  }
-}
-
 }  // namespace kvc
 
 using namespace kvc;
 
 extern "C" size_t kvc_select_evictions_workspace_bytes(int64_t max_evicted_kv, int block_size) {
   if (max_evicted_kv <= 0 || block_size <= 0) return 0;
-  return (size_t)max_evicted_kv * sizeof(int) + ((size_t)max_evicted_kv / block_size + 1) * sizeof(unsigned) + 512;
+  return ((size_t)max_evicted_kv / block_size + 1) * sizeof(unsigned) + 512;  // completion keys
 }
 
 extern "C" int kvc_select_evictions(
@@ -313,29 +459,38 @@ extern "C" int kvc_select_evictions(
   p.S = num_seqs; p.L = num_layers; p.H = num_kv_heads; p.MB = max_num_blocks_per_seq;
   p.B = block_size; p.null_index = null_eviction_index;
   uintptr_t w = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
-  p.ranks = reinterpret_cast<int*>(w);
-  p.events = reinterpret_cast<unsigned*>(w + (size_t)max_evicted_kv * sizeof(int));
+  p.events = reinterpret_cast<unsigned*>(w);
   cudaStream_t st = as_stream(stream);
   const int total = num_seqs * num_layers * num_kv_heads;
   const int max_slots = max_num_blocks_per_seq * block_size;
-  if (max_slots <= 256) {  // steady-state compressed contexts: one warp per head
-    const size_t smem = (size_t)4 * max_slots * sizeof(unsigned);
-    select_rank_kernel<32><<<ceil_div(total, 4), 128, smem, st>>>(p, max_slots);
+  const bool warp_path = max_slots <= 256;  // steady-state compressed contexts: one warp per head
+  if (warp_path) {
+    if (block_size == 16) select_sort_kernel<16><<<ceil_div(total, 4), 128, 0, st>>>(p);
+    else if (block_size == 4) select_sort_kernel<4><<<ceil_div(total, 4), 128, 0, st>>>(p);
+    else if (block_size == 2) select_sort_kernel<2><<<ceil_div(total, 4), 128, 0, st>>>(p);
+    else select_sort_kernel<1><<<ceil_div(total, 4), 128, 0, st>>>(p);
+    KVC_CHECK_LAUNCH("select_sort_kernel");
   } else {
     const size_t smem = (size_t)max_slots * sizeof(unsigned);
     KVC_REQUIRE(smem <= 220 * 1024, KVC_ERR_UNSUPPORTED,
                 "select_evictions: %d slots per head exceed the shared-memory staging limit", max_slots);
     if (smem > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(select_rank_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(select_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "select_rank smem attr: %s", cudaGetErrorString(e));
     }
-    select_rank_kernel<128><<<total, 128, smem, st>>>(p, max_slots);
+    select_rank_kernel<<<total, 128, smem, st>>>(p, max_slots);
+    KVC_CHECK_LAUNCH("select_rank_kernel");
   }
-  KVC_CHECK_LAUNCH("select_rank_kernel");
   select_threshold_kernel<<<num_seqs, 256, 0, st>>>(p);
   KVC_CHECK_LAUNCH("select_threshold_kernel");
-  if (max_slots <= 256) select_emit_kernel<32><<<ceil_div(total, 4), 128, 0, st>>>(p);
-  else select_emit_kernel<128><<<total, 128, 0, st>>>(p);
+  if (warp_path) {
+    if (block_size == 16) select_emit_warp_kernel<16><<<ceil_div(total, 4), 128, 0, st>>>(p);
+    else if (block_size == 4) select_emit_warp_kernel<4><<<ceil_div(total, 4), 128, 0, st>>>(p);
+    else if (block_size == 2) select_emit_warp_kernel<2><<<ceil_div(total, 4), 128, 0, st>>>(p);
+    else select_emit_warp_kernel<1><<<ceil_div(total, 4), 128, 0, st>>>(p);
+  } else {
+    select_emit_cta_kernel<<<total, 128, 0, st>>>(p);
+  }
   KVC_CHECK_LAUNCH("select_emit_kernel");
   return KVC_OK;
 }

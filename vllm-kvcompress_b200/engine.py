@@ -301,3 +301,13 @@ class DecodeHotPath:
         torch.cuda.synchronize()
         ms = sum(a.elapsed_time(b) for a, b in pairs) / (len(pairs) * L)
         return ms, self.attention_bytes() / L
+
+    @property
+    def tokens_per_step(self) -> int:
+        return self.cfg.num_seqs
+
+    def attention_bytes(self) -> int:
+        """Algorithmic bytes of one step's attention launches: K+V of every
+        context token once (2*D*2 B) + position read (4 B) + metric read-modify-write (8 B)."""
+        ctx_total = int(self.st.context_lens.sum())
+        return ctx_total * (2 * self.cfg.head_size * 2 + 4 + 8)
