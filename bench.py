@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--unfused-metrics", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-compaction", action="store_true")
-    ap.add_argument("--cpu-sample-seqs", type=int, default=4)
+    ap.add_argument("--cpu-sample-seqs", type=int, default=16)
     return ap.parse_args()
 
 
@@ -130,7 +130,7 @@ def run_reference(args, rank, world):
         "value": val, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
-        "config": workload_config(args, ns),
+        "config": workload_config(args, args.batch * args.gpus),
         "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": O.num_threads(), "kind": "port",
                          "sample": f"{ns} of {args.batch} sequences per step, all {args.layers} layers, full cycle"},
         "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -210,11 +210,13 @@ def main():
 
     cfg = HotPathConfig(num_seqs=args.batch, num_layers=args.layers, selection=args.selection,
                         fused_metrics=not args.unfused_metrics, seed=rank)
-    if world > 1:
-        # the only collective on this path: one start-up broadcast (stands in for the weight
-        # broadcast of the 8-replica layout; every replica then owns an independent cache)
-        hdr = torch.tensor([cfg.num_seqs, cfg.num_layers, cfg.max_cache_tokens], device=device)
-        dist.broadcast(hdr, 0)
+    from vllm_kvcompress_b200 import sharding
+    # the only collective on this path: one start-up broadcast (stands in for the weight broadcast
+    # of the 8-replica layout); every replica then owns an independent cache for its own requests
+    hdr = sharding.broadcast_config([cfg.num_seqs, cfg.num_layers, cfg.max_cache_tokens], device)
+    assert hdr == [cfg.num_seqs, cfg.num_layers, cfg.max_cache_tokens]
+    my_requests = sharding.shard_requests(cfg.num_seqs * world, world, rank)  # ids of this replica's batch
+    assert len(my_requests) == cfg.num_seqs
     eng = DecodeHotPath(cfg, device)
     H, Q, D, L, S = cfg.num_kv_heads, cfg.queries_per_kv, cfg.head_size, cfg.num_layers, cfg.num_seqs
     width_in, width_out = (H * Q + 2 * H) * D, H * Q * D
@@ -265,10 +267,7 @@ def main():
     barrier()
     ms_e2e = e0.elapsed_time(e1) / args.steps
 
-    t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e = sharding.max_over_ranks([ms, ms_e2e], device)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
