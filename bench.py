@@ -257,12 +257,14 @@ def main():
     qkv_host = torch.empty((L, S, width_in), dtype=cfg.dtype, pin_memory=True)
     qkv_host.copy_(qkv)
     out_host = torch.empty((L, S, width_out), dtype=cfg.dtype, pin_memory=True)
+    host_graphed = eng.capture_host(qkv_host, out_host)
+    run_host = eng.replay_host if host_graphed else (lambda: eng.step_host(qkv_host, out_host))
     for _ in range(3):
-        eng.step_host(qkv_host, out_host)
+        run_host()
     barrier()
     e0.record()
     for _ in range(args.steps):
-        eng.step_host(qkv_host, out_host)
+        run_host()
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / args.steps

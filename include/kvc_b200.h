@@ -298,6 +298,31 @@ KVC_API int kvc_select_evictions(
     int64_t max_evicted_kv, int null_eviction_index, void* workspace,
     size_t workspace_bytes, kvc_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Additive: block-state device ops around a compression cycle (the reference does these
+ * with ~30 small torch launches, vllm/kvcompress/block.py:184-210, 275-335;
+ * block_manager.py:269-294; scheduler.py:131-141, 263-280).
+ * kvc_prepare_compression: from context_lens [L,S,H] compute hanging_token_count [S,L,H]
+ *   (ctx % B or B), evicted_kv_offsets [S,L,H] (exclusive cumsum of ceil(ctx/B)*B in
+ *   (s,l,h) order) and, if evicted_blocks_per_seq != NULL, the per-sequence budget
+ *   max(0, allocated blocks - max_cache_blocks_per_seq).  seq_slots_workspace: [S] ints.
+ * kvc_free_and_append_slots: per head, context_lens -= max(evicted_block_count*B -
+ *   (B - hanging), 0) (skipped when evicted_block_count == NULL), then if `append`:
+ *   slot = block_tables[.., ctx / B] * B + ctx % B -> slot_mapping [L,S,H] (int64),
+ *   kv_position[slot] = seq_len[s], ctx += 1.
+ * ------------------------------------------------------------------------- */
+KVC_API int kvc_prepare_compression(
+    const int* context_lens, int* hanging_token_count, int* evicted_kv_offsets,
+    int* evicted_blocks_per_seq, int* seq_slots_workspace, int num_seqs,
+    int num_layers, int num_kv_heads, int block_size,
+    int max_cache_blocks_per_seq, kvc_stream_t stream);
+
+KVC_API int kvc_free_and_append_slots(
+    int* context_lens, const int* block_tables, const int* evicted_block_count,
+    const int* hanging_token_count, const int* seq_len, int64_t* slot_mapping,
+    int* kv_position, int num_seqs, int num_layers, int num_kv_heads,
+    int max_num_blocks_per_seq, int block_size, int append, kvc_stream_t stream);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -586,3 +586,41 @@ def test_select_evictions_equals_reference_chain(capi, O, cfg):
     np.testing.assert_array_equal(out_cnt.cpu().numpy(), cnt)
     np.testing.assert_array_equal(out_blk.cpu().numpy(), want_blocks)
     np.testing.assert_array_equal(out_logical.cpu().numpy(), want_logical)
+
+
+def test_block_state_ops_match_reference_formulas(capi):
+    """prepare_compression / free_and_append_slots vs the reference's torch formulas
+    (block.py:184-210, 275-335; scheduler.py:131-141, 274-280) evaluated on the CPU."""
+    from vllm_kvcompress_b200 import _custom_ops as ops
+    from vllm_kvcompress_b200 import workload as W
+    g = torch.Generator().manual_seed(5)
+    S, L, H, B, MB = 37, 5, 8, 16, 12
+    ctx = torch.randint(1, MB * B - 20, (L, S, H), generator=g, dtype=torch.int32)
+    st = W.make_state(S, L, H, B, 16, ctx, device="cpu", seed=5, fill_cache=False, max_blocks=MB,
+                      blocks_per_head_alloc=MB, slack=1.0)
+    want_hang = W.hanging_token_counts(ctx, B).transpose(0, 1).contiguous()
+    want_off = W.evicted_kv_offsets(ctx, B)
+    nblk = (ctx + B - 1) // B
+    max_blocks = 200
+    want_budget = (nblk.sum(dim=(0, 2)) - max_blocks).clamp(min=0).to(torch.int32)
+    dctx = ctx.cuda()
+    hang = torch.empty((S, L, H), dtype=torch.int32, device="cuda")
+    off = torch.empty_like(hang)
+    bud = torch.empty(S, dtype=torch.int32, device="cuda")
+    ops.prepare_compression(dctx, hang, off, bud, B, max_blocks)
+    assert torch.equal(hang.cpu(), want_hang) and torch.equal(off.cpu(), want_off) and torch.equal(bud.cpu(), want_budget)
+    # free + append
+    ev = torch.randint(0, 3, (S, L, H), generator=g, dtype=torch.int32)
+    ev = torch.minimum(ev, ((ctx.transpose(0, 1) - 1) // B).to(torch.int32))
+    freed = (ev * B - (B - want_hang)).clamp(min=0)
+    ctx_after = ctx - freed.transpose(0, 1)
+    blk = torch.gather(st.block_tables, 3, (ctx_after // B).long().unsqueeze(-1)).squeeze(-1)
+    want_slot = blk.long() * B + (ctx_after % B).long()
+    seq_len = torch.randint(100, 9000, (S,), generator=g, dtype=torch.int32)
+    want_pos = st.kv_position.clone()
+    want_pos.view(-1)[want_slot.flatten()] = seq_len.view(1, -1, 1).expand_as(ctx).flatten()
+    slot = torch.empty((L, S, H), dtype=torch.int64, device="cuda")
+    pos = st.kv_position.cuda()
+    ops.free_and_append_slots(dctx, st.block_tables.cuda(), ev.cuda(), hang, seq_len.cuda(), slot, pos, B, True)
+    assert torch.equal(dctx.cpu(), ctx_after + 1)
+    assert torch.equal(slot.cpu(), want_slot) and torch.equal(pos.cpu(), want_pos)

@@ -159,3 +159,20 @@ def select_evictions(out_evicted_logical_indices, out_evicted_kv_count, out_evic
         hanging_token_count.contiguous(), evicted_kv_offsets.contiguous(),
         evicted_blocks_per_seq.contiguous(), last_position.type(torch.int), protected_window_size,
         block_size, null_eviction_index)
+
+
+def prepare_compression(context_lens, out_hanging_token_count, out_evicted_kv_offsets,
+                        out_evicted_blocks_per_seq, block_size: int, max_cache_blocks_per_seq: int) -> None:
+    """ADDITIVE op: hanging counts, segment offsets and per-sequence block budgets in two launches
+    (reference: block.py:330-335, scheduler.py:131-141, 274-280 as torch ops)."""
+    torch.ops._C_kvc_ops.prepare_compression(context_lens, out_hanging_token_count, out_evicted_kv_offsets,
+                                             out_evicted_blocks_per_seq, block_size, max_cache_blocks_per_seq)
+
+
+def free_and_append_slots(context_lens, block_tables, evicted_block_count, hanging_token_count, seq_len,
+                          out_slot_mapping, kv_position, block_size: int, append: bool = True) -> None:
+    """ADDITIVE op: free the compressed trailing blocks (block.py:184-210) and append one token per head
+    (block_manager.py:269-294, block.py:275-321) in one launch."""
+    torch.ops._C_kvc_ops.free_and_append_slots(context_lens, block_tables, evicted_block_count,
+                                               hanging_token_count, seq_len, out_slot_mapping, kv_position,
+                                               block_size, append)

@@ -184,6 +184,38 @@ void select_evictions(torch::Tensor& evicted_logical_indices, torch::Tensor& evi
                "select_evictions");
 }
 
+// additive ops: see include/kvc_b200.h kvc_prepare_compression / kvc_free_and_append_slots
+void prepare_compression(torch::Tensor& context_lens, torch::Tensor& hanging_token_count,
+                         torch::Tensor& evicted_kv_offsets, torch::Tensor& evicted_blocks_per_seq,
+                         int64_t block_size, int64_t max_cache_blocks_per_seq) {
+  TORCH_CHECK(context_lens.dim() == 3, "context_lens must be [num_layers, num_seqs, num_kv_heads]");
+  const int L = context_lens.size(0), S = context_lens.size(1), H = context_lens.size(2);
+  const at::cuda::OptionalCUDAGuard guard(device_of(context_lens));
+  auto ws = torch::empty({S}, context_lens.options());
+  check_status(kvc_prepare_compression(i32(context_lens, "context_lens"), i32_mut(hanging_token_count, "hanging_token_count"),
+                                       i32_mut(evicted_kv_offsets, "evicted_kv_offsets"),
+                                       i32_mut(evicted_blocks_per_seq, "evicted_blocks_per_seq"), ws.data_ptr<int>(), S, L,
+                                       H, (int)block_size, (int)max_cache_blocks_per_seq, cur_stream()),
+               "prepare_compression");
+}
+
+void free_and_append_slots(torch::Tensor& context_lens, torch::Tensor& block_tables,
+                           const c10::optional<torch::Tensor>& evicted_block_count,
+                           const c10::optional<torch::Tensor>& hanging_token_count, torch::Tensor& seq_len,
+                           torch::Tensor& slot_mapping, torch::Tensor& kv_position, int64_t block_size, bool append) {
+  TORCH_CHECK(context_lens.dim() == 3 && block_tables.dim() == 4, "context_lens [L,S,H], block_tables [L,S,H,MB] expected");
+  TORCH_CHECK(slot_mapping.scalar_type() == at::kLong && slot_mapping.is_contiguous(), "slot_mapping must be contiguous int64");
+  const int L = context_lens.size(0), S = context_lens.size(1), H = context_lens.size(2);
+  const at::cuda::OptionalCUDAGuard guard(device_of(context_lens));
+  check_status(kvc_free_and_append_slots(
+                   i32_mut(context_lens, "context_lens"), i32(block_tables, "block_tables"),
+                   evicted_block_count ? i32(evicted_block_count.value(), "evicted_block_count") : nullptr,
+                   hanging_token_count ? i32(hanging_token_count.value(), "hanging_token_count") : nullptr,
+                   i32(seq_len, "seq_len"), slot_mapping.data_ptr<int64_t>(), i32_mut(kv_position, "kv_position"), S, L, H,
+                   block_tables.size(3), (int)block_size, append ? 1 : 0, cur_stream()),
+               "free_and_append_slots");
+}
+
 // ---- _C_cache_ops ----------------------------------------------------------
 void kvcompress_reshape_and_cache(torch::Tensor& key, torch::Tensor& value, torch::Tensor& key_cache,
                                   torch::Tensor& value_cache, torch::Tensor& kv_metrics,
@@ -438,6 +470,15 @@ TORCH_LIBRARY_FRAGMENT(_C_kvc_ops, kvc_ops) {
       "                  Tensor last_position, Tensor protected_window_size,"
       "                  int block_size, int null_eviction_index) -> ()");
   kvc_ops.impl("select_evictions", torch::kCUDA, &select_evictions);
+  kvc_ops.def(
+      "prepare_compression(Tensor context_lens, Tensor! hanging_token_count, Tensor! evicted_kv_offsets,"
+      "                     Tensor! evicted_blocks_per_seq, int block_size, int max_cache_blocks_per_seq) -> ()");
+  kvc_ops.impl("prepare_compression", torch::kCUDA, &prepare_compression);
+  kvc_ops.def(
+      "free_and_append_slots(Tensor! context_lens, Tensor block_tables, Tensor? evicted_block_count,"
+      "                       Tensor? hanging_token_count, Tensor seq_len, Tensor! slot_mapping,"
+      "                       Tensor! kv_position, int block_size, bool append) -> ()");
+  kvc_ops.impl("free_and_append_slots", torch::kCUDA, &free_and_append_slots);
 }
 
 // importable as a Python module named _C, like the reference's REGISTER_EXTENSION

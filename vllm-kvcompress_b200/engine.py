@@ -99,6 +99,9 @@ class DecodeHotPath:
         self.evicted_kv_count = torch.empty((S, L, H), dtype=torch.int32, device=device)
         self.evicted_block_count = torch.empty((S, L, H), dtype=torch.int32, device=device)
         self.slot_mapping = torch.empty((L, S, H), dtype=torch.int64, device=device)
+        self.hanging = torch.empty((S, L, H), dtype=torch.int32, device=device)
+        self.offs = torch.empty((S, L, H), dtype=torch.int32, device=device)
+        self.budgets = torch.empty((S,), dtype=torch.int32, device=device)
         self.arangeB = torch.arange(B, dtype=torch.int32, device=device)
         if not cfg.fused_metrics:
             self.temp_metrics = torch.zeros((st.NB, B, cfg.queries_per_kv), dtype=torch.float32, device=device)
@@ -114,20 +117,23 @@ class DecodeHotPath:
         return (total - max_blocks).clamp_(min=0).to(torch.int32)
 
     def compress(self) -> None:
+        """Compression cycle + append, device-side end to end (no host round trip)."""
         cfg, st = self.cfg, self.st
         B = cfg.block_size
         ctx = st.context_lens                                                  # [L,S,H]
-        hanging = W.hanging_token_counts(ctx, B).transpose(0, 1).contiguous()  # [S,L,H]
-        offs = W.evicted_kv_offsets(ctx, B)
-        budgets = self._budgets()
         last_pos = self.seq_len - 1
         if cfg.selection == "fused":
+            max_blocks = (cfg.max_cache_tokens * cfg.num_layers * cfg.num_kv_heads + B - 1) // B
+            ops.prepare_compression(ctx, self.hanging, self.offs, self.budgets, B, max_blocks)
             ops.select_evictions(self.evicted_logical, self.evicted_kv_count, self.evicted_block_count,
-                                 st.kv_metrics, st.kv_position, st.block_tables, ctx, hanging, offs, budgets,
-                                 last_pos, self.protected, B, MAX_INT)
-            self.launches += ops.SELECT_EVICTIONS_LAUNCHES
-            logical = self.evicted_logical
+                                 st.kv_metrics, st.kv_position, st.block_tables, ctx, self.hanging, self.offs,
+                                 self.budgets, last_pos, self.protected, B, MAX_INT)
+            self.launches += 2 + ops.SELECT_EVICTIONS_LAUNCHES
+            logical, hanging, offs = self.evicted_logical, self.hanging, self.offs
         else:
+            hanging = W.hanging_token_counts(ctx, B).transpose(0, 1).contiguous()  # [S,L,H]
+            offs = W.evicted_kv_offsets(ctx, B)
+            budgets = self._budgets()
             sm = W.sort_seq_metrics(st)                                        # torch.sort x2 (library)
             ops.schedule_cache_evictions(self.evicted_heads, self.evicted_logical, self.evicted_kv_count, offs,
                                          sm.sorted_indices, sm.seq_block_offsets, sm.layer_by_block,
@@ -138,30 +144,27 @@ class DecodeHotPath:
             order = torch.sort(self.evicted_logical, stable=True).indices
             order = order[torch.sort(self.evicted_heads[order], stable=True).indices]
             logical = self.evicted_logical[order].contiguous()
-            self.evicted_block_count = torch.where(self.evicted_kv_count >= hanging,
-                                                   (self.evicted_kv_count - hanging) // B + 1,
-                                                   torch.zeros_like(hanging))
-        ops.schedule_cache_moves(self.cache_moves, self.moves_count, logical, self.evicted_kv_count, offs,
-                                 st.block_tables, ctx, B)
+            self.evicted_block_count.copy_(torch.where(self.evicted_kv_count >= hanging,
+                                                       (self.evicted_kv_count - hanging) // B + 1,
+                                                       torch.zeros_like(hanging)))
+            self.hanging.copy_(hanging)
+        # the op itself, not the reference wrapper: that one zero-fills the whole [max_kv, 2] workspace
+        # first (vllm/_custom_ops.py:1168, 100 MB per call here); only [0, count) per head is ever read
+        torch.ops._C_kvc_ops.schedule_t1_cache_moves(self.cache_moves, self.moves_count, logical,
+                                                     self.evicted_kv_count, offs, st.block_tables, ctx, B)
         ops.execute_cache_moves(st.k_cache, st.v_cache, st.kv_metrics, st.kv_position, self.cache_moves,
                                 self.moves_count, offs, 1, 16)
         self.launches += 2
-        # free_compressed_blocks: context_lens -= max(nb*B - (B - hanging), 0)  (block.py:184-210)
-        freed = (self.evicted_block_count * B - (B - hanging)).clamp_(min=0)
-        st.context_lens.sub_(freed.transpose(0, 1))   # in place: the tensors are CUDA-graph state
 
     # ------------------------------------------------------------------ append + forward
     def append_slots(self) -> None:
-        """batch_append_slots: +1 token per head; slot of the new KV; its position."""
+        """free_compressed_blocks (block.py:184-210) + batch_append_slots (block_manager.py:269-294):
+        one launch; then the sequence length advances."""
         cfg, st = self.cfg, self.st
-        B = cfg.block_size
-        ctx = st.context_lens
-        blk = torch.gather(st.block_tables, 3, (ctx // B).long().unsqueeze(-1)).squeeze(-1)
-        slot = blk.long() * B + (ctx % B).long()
-        self.slot_mapping.copy_(slot)
-        st.kv_position.view(-1).index_put_((slot.flatten(),), self.seq_len.view(1, -1, 1).expand_as(ctx).flatten())
-        st.context_lens.add_(1)
+        ops.free_and_append_slots(st.context_lens, st.block_tables, self.evicted_block_count, self.hanging,
+                                  self.seq_len, self.slot_mapping, st.kv_position, cfg.block_size, True)
         self.seq_len.add_(1)
+        self.launches += 1
 
     def forward_layer(self, l: int, x: torch.Tensor, o: torch.Tensor, last_pos: torch.Tensor,
                       timing=None) -> None:
@@ -258,6 +261,24 @@ class DecodeHotPath:
                 out_host[l].copy_(self._out_dev[l], non_blocking=True)
         self._aggregate_unfused()
         main.wait_stream(self._d2h)   # the step is complete when its results are in host memory
+
+    def capture_host(self, qkv_host: torch.Tensor, out_host: torch.Tensor) -> bool:
+        """Capture step_host (copies on side streams included) into one CUDA graph bound to these
+        pinned host buffers: the per-layer H2D / compute / D2H pipeline then costs one graph launch."""
+        if self.cfg.selection != "fused":
+            return False
+        self.step_host(qkv_host, out_host)  # creates streams / staging buffers, warms the allocator
+        torch.cuda.synchronize()
+        self.host_graph = torch.cuda.CUDAGraph()
+        n0 = self.launches
+        with torch.cuda.graph(self.host_graph):
+            self.step_host(qkv_host, out_host)
+        self.launches = n0
+        return True
+
+    def replay_host(self) -> None:
+        self.host_graph.replay()
+        self.launches += getattr(self, "launches_per_step", 0)
 
     # ------------------------------------------------------------------ measurement helper
     def profile_attention(self, qkv: torch.Tensor, out: torch.Tensor, steps: int = 5):
