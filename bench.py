@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--selection", default="fused", choices=["fused", "chain"])
     ap.add_argument("--unfused-metrics", action="store_true")
+    ap.add_argument("--separate-cache-write", action="store_true", help="K6 as its own launch per layer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-compaction", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=16)
@@ -145,6 +146,7 @@ def workload_config(args, batch):
             "global_batch": batch, "seq_len": 6000, "parallelism": "request-sharded replicas",
             "l2": "inputs larger than L2 (per-step KV read ~4.6 GB vs 126 MB L2)",
             "selection": args.selection, "fused_metrics": not args.unfused_metrics,
+            "fused_cache_write": not getattr(args, "separate_cache_write", False),
             "launch": "one CUDA graph per step" if args.selection == "fused" else "eager"}
 
 
@@ -209,7 +211,8 @@ def main():
     from vllm_kvcompress_b200.engine import DecodeHotPath, HotPathConfig
 
     cfg = HotPathConfig(num_seqs=args.batch, num_layers=args.layers, selection=args.selection,
-                        fused_metrics=not args.unfused_metrics, seed=rank)
+                        fused_metrics=not args.unfused_metrics,
+                        fused_cache_write=not args.separate_cache_write, seed=rank)
     from vllm_kvcompress_b200 import sharding
     # the only collective on this path: one start-up broadcast (stands in for the weight broadcast
     # of the 8-replica layout); every replica then owns an independent cache for its own requests
@@ -288,7 +291,7 @@ def main():
                 "d2h_bytes_per_step": out_host.numel() * out_host.element_size()},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "paged_attention_kernel (fused metrics), %d launches/step" % L,
+        "roofline": {"bound": "hbm", "kernel": "paged_attention_stream_kernel (cache write + attention + metric aggregation), %d launches/step" % L,
                      "achieved": attn_b / (attn_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": attn_b / (attn_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
                      "bytes_per_launch": attn_b, "ms_per_launch": attn_ms, "traffic": None},

@@ -268,6 +268,28 @@ KVC_API size_t kvc_paged_attention_fused_metrics_workspace_bytes(
     int num_seqs, int num_heads, int max_context_len);
 
 /* ---------------------------------------------------------------------------
+ * Additive: one decode layer of the hot path in ONE launch = kvcompress_reshape_and_cache
+ * (csrc/kvcompress_cache_kernels.cu:27-89: write the step's new K/V of every (seq, kv head)
+ * to its slot, metric := head bias) + paged attention + `metrics += sum_q p^2`
+ * (call sites vllm/attention/backends/flash_attn.py:871 and :1067-1091,
+ * vllm/kvcompress/metrics.py:429-439).  context_lens must already count the new token
+ * (batch_append_slots ran).  key/value [S, H, D] with token strides key_stride/value_stride;
+ * slot_mapping [S, H] int64 for THIS layer (< 0 = no new token).  Workspace as for
+ * kvc_paged_attention_fused_metrics.
+ * ------------------------------------------------------------------------- */
+KVC_API int kvc_paged_attention_fused_step(
+    void* out, float* kv_metrics, const void* query, const void* key,
+    const void* value, void* key_cache, void* value_cache,
+    const int64_t* slot_mapping, const float* kv_metric_head_bias, int num_seqs,
+    int num_heads, int num_kv_heads, int head_size, float scale,
+    const int* block_tables, const int* context_lens, const int* kv_position,
+    const int* last_position, const int* kv_metric_buffer_len, int block_size,
+    int max_context_len, int max_num_blocks_per_seq, int64_t q_stride,
+    int64_t key_stride, int64_t value_stride, int64_t kv_block_stride,
+    const float* alibi_slopes, int dtype /* kvc_dtype */, void* workspace,
+    size_t workspace_bytes, kvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Additive: fused eviction selection straight from the paged metrics.
  * replaces CompressionMetrics.schedule_evictions (vllm/kvcompress/metrics.py:441-847:
  * mask gathers + 6 torch.sort + per-sequence host loop + count_block_evictions + final

@@ -624,3 +624,41 @@ def test_block_state_ops_match_reference_formulas(capi):
     ops.free_and_append_slots(dctx, st.block_tables.cuda(), ev.cuda(), hang, seq_len.cuda(), slot, pos, B, True)
     assert torch.equal(dctx.cpu(), ctx_after + 1)
     assert torch.equal(slot.cpu(), want_slot) and torch.equal(pos.cpu(), want_pos)
+
+
+@pytest.mark.parametrize("cfg", [(81, 6, 32, 8, 160, False), (82, 3, 64, 8, 300, True), (83, 4, 8, 8, 33, False)])
+def test_fused_step_equals_cache_write_then_attention(capi, cfg):
+    """kvcompress_paged_attention_fused_step == reshape_and_cache_kvc followed by the fused-metrics
+    attention (bit-exact caches, identical recording rule, outputs within the attention tolerance)."""
+    from vllm_kvcompress_b200 import _custom_ops as ops
+    seed, S, Hq, H, max_ctx, bf = cfg
+    c = attn_case(seed, S, Hq, H, max_ctx, bf, False, 0, min_ctx=1)
+    D, B = 128, 16
+    q, kc, vc = cu16(c["query"], bf), cu16(c["key_cache"], bf), cu16(c["value_cache"], bf)
+    NB = kc.shape[0]
+    bt, cl = cu(c["block_tables"], torch.int32), cu(c["context_lens"], torch.int32)
+    kp, lp, bl = (cu(c[k], torch.int32) for k in ("kv_position", "last_position", "kv_metric_buffer_len"))
+    g = torch.Generator().manual_seed(seed)
+    newk = ((torch.rand((S, H, D), generator=g) - 0.5) * 0.3).to(q.dtype).cuda()
+    newv = ((torch.rand((S, H, D), generator=g) - 0.5) * 0.3).to(q.dtype).cuda()
+    # the new token is the LAST token of every head (context_lens already counts it)
+    last_idx = (cl - 1).long()
+    slot = (torch.gather(bt, 2, (last_idx // B).unsqueeze(-1)).squeeze(-1).long() * B + last_idx % B).contiguous()
+    slot[0, 0] = -1 if S > 3 else slot[0, 0]   # a head without a new token (padding)
+    bias = torch.rand(H, generator=g).cuda()
+    metrics0 = torch.rand((NB, B), generator=g).cuda()
+    max_c = int(c["context_lens"].max())
+    # reference order: cache write, then attention with fused metrics
+    k1, v1, m1 = kc.clone(), vc.clone(), metrics0.clone()
+    out1 = torch.zeros((S, Hq, D), dtype=q.dtype, device="cuda")
+    ops.reshape_and_cache_kvc(newk, newv, k1, v1, m1, slot.flatten(), bias, "auto", 1.0, 1.0)
+    ops.paged_attention_kvc_fused_metrics(out1, m1, q, k1, v1, H, float(c["scale"]), bt, cl, kp, lp, bl, B, max_c)
+    k2, v2, m2 = kc.clone(), vc.clone(), metrics0.clone()
+    out2 = torch.zeros_like(out1)
+    ops.paged_attention_kvc_fused_step(out2, m2, q, newk, newv, k2, v2, slot.flatten(), bias, H, float(c["scale"]),
+                                       bt, cl, kp, lp, bl, B, max_c)
+    torch.cuda.synchronize()
+    assert torch.equal(k1.view(torch.int16), k2.view(torch.int16))
+    assert torch.equal(v1.view(torch.int16), v2.view(torch.int16))
+    torch.testing.assert_close(out2.float(), out1.float(), atol=1e-3, rtol=1e-2)
+    torch.testing.assert_close(m2, m1, atol=1e-6, rtol=1e-4)

@@ -176,3 +176,17 @@ def free_and_append_slots(context_lens, block_tables, evicted_block_count, hangi
     torch.ops._C_kvc_ops.free_and_append_slots(context_lens, block_tables, evicted_block_count,
                                                hanging_token_count, seq_len, out_slot_mapping, kv_position,
                                                block_size, append)
+
+
+def paged_attention_kvc_fused_step(out, kv_metrics, query, key, value, key_cache, value_cache, slot_mapping,
+                                   kv_metric_head_bias, num_kv_heads: int, scale: float, block_tables,
+                                   context_lens, kv_position, last_position, kv_metric_buffer_len,
+                                   block_size: int, max_context_len: int,
+                                   alibi_slopes: Optional[torch.Tensor] = None,
+                                   kv_cache_dtype: str = "auto") -> None:
+    """ADDITIVE op: one decode layer of the hot path in one launch = reshape_and_cache_kvc (cache
+    write + metric init, flash_attn.py:871) + paged attention + aggregate_decode."""
+    torch.ops._C.kvcompress_paged_attention_fused_step(
+        out, kv_metrics, query, key, value, key_cache, value_cache, slot_mapping, kv_metric_head_bias,
+        num_kv_heads, scale, block_tables, context_lens, kv_position, last_position, kv_metric_buffer_len,
+        block_size, max_context_len, alibi_slopes, kv_cache_dtype)

@@ -38,7 +38,7 @@ constexpr int kB = 16;
 constexpr int kPartition = 512;  // reference PARTITION_SIZE, :866
 constexpr int kOStride = 132;    // padded d-stride of the cross-warp merge buffer (bank-conflict free)
 
-enum AttnMode { kModeV1 = 0, kModeV2 = 1, kModeFused = 2 };
+enum AttnMode { kModeV1 = 0, kModeV2 = 1, kModeFused = 2, kModeFusedWrite = 3 };
 
 struct AttnParams {
   void* out;
@@ -62,6 +62,12 @@ struct AttnParams {
   int record;
   int max_partitions;
   int num_seqs;
+  // fused cache write (kModeFusedWrite): the step's new token per (seq, kv head)
+  const void* new_k;            // [S, H, D] token stride new_k_stride (elements)
+  const void* new_v;
+  int64_t new_k_stride, new_v_stride;
+  const int64_t* slot_mapping;  // [S, H]; < 0 = no new token for this head
+  const float* head_bias;       // [H]
 };
 
 template <bool BF16>
@@ -496,9 +502,30 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   // v1 mode parks them in kv_metric_out itself
   float* lg0 = nullptr;
   float* lg1 = nullptr;
-  if (MODE == kModeFused) {
+  constexpr bool kFusedMetrics = (MODE == kModeFused || MODE == kModeFusedWrite);
+  if (kFusedMetrics) {
     lg0 = scratch + ((int64_t)item * Q + 2 * c) * scratch_tokens;  // column q = 2c (nt = 0)
     lg1 = lg0 + scratch_tokens;
+  }
+
+  // fused cache write (kvcompress_reshape_and_cache folded in, csrc/kvcompress_cache_kernels.cu:44-88):
+  // the step's new token of this head is stored to the cache for later steps, and patched into the
+  // staged copy of the last block below (the TMA read of that block may race with the store).
+  uint4 newk = make_uint4(0, 0, 0, 0);   // lane j < 16: chunk j of the new K
+  uint16_t newv[4] = {0, 0, 0, 0};       // rows d = lane + 32 r of the new V
+  int new_o = -1;                        // block offset of the new token, -1 = none
+  int64_t new_slot = -1;
+  if (MODE == kModeFusedWrite) {
+    const int64_t nslot = p.slot_mapping[item];
+    if (nslot >= 0) {
+      new_o = (int)(nslot & (kB - 1));
+      const uint16_t* nk = reinterpret_cast<const uint16_t*>(p.new_k) + (int64_t)s * p.new_k_stride + h * kD;
+      const uint16_t* nv = reinterpret_cast<const uint16_t*>(p.new_v) + (int64_t)s * p.new_v_stride + h * kD;
+      if (lane < 16) newk = *reinterpret_cast<const uint4*>(nk + lane * 8);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) newv[r] = nv[lane + 32 * r];
+      new_slot = nslot;  // the stores to the cache are issued after the sweep (nothing here waits on them)
+    }
   }
 
   uint4 qf[NT][4];
@@ -558,7 +585,14 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     float sacc[2][NT][4];
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      const unsigned char* kS = next_unit() + koff;
+      const unsigned char* kU = next_unit();
+      if (MODE == kModeFusedWrite && last && new_o >= 0) {  // patch the new token into the staged K half
+        if ((lane >> 3) == hf && lane < 16)
+          *reinterpret_cast<uint4*>(const_cast<unsigned char*>(kU) + (lane & 7) * (kB * 16) + new_o * 16) = newk;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic write, slot later refilled by TMA
+        __syncwarp();
+      }
+      const unsigned char* kS = kU + koff;
       uint4 ka[2], kb[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {  // chunk 4*(2*hf+j) + c of the block = chunk 4*j + c of this half
@@ -597,7 +631,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
         }
         const int qc = nt * 8 + 2 * c + i;
         if (qc < Q) {
-          if (MODE == kModeFused) {
+          if (kFusedMetrics) {
             float* lg = (i ? lg1 : lg0) + nt * 8 * scratch_tokens;
             lg[tok0] = s0;  // slots beyond ctx exist in the scratch row (padded to a block multiple)
             lg[tok1] = s1;
@@ -640,7 +674,15 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     // ---- O^T += V^T P^T, one V half (four d-tiles) at a time ----
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      const unsigned char* vS = next_unit() + voff;
+      const unsigned char* vU = next_unit();
+      if (MODE == kModeFusedWrite && last && new_o >= 0) {  // rows 64*hf + lane, 64*hf + 32 + lane of the new V
+        uint16_t* vw = reinterpret_cast<uint16_t*>(const_cast<unsigned char*>(vU));
+        vw[lane * kB + new_o] = newv[2 * hf];
+        vw[(lane + 32) * kB + new_o] = newv[2 * hf + 1];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+      }
+      const unsigned char* vS = vU + voff;
       uint2 va[4], vb[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {  // rows 16*(4*hf+j) + g (+8) of the block = rows 16*j + g (+8) of this half
@@ -690,7 +732,16 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
         }
       }
     }
-  if (MODE == kModeFused || (MODE == kModeV1 && p.record)) {
+  if (MODE == kModeFusedWrite && new_slot >= 0) {
+    // reference csrc/kvcompress_cache_kernels.cu:55-88: K chunks, V elements, metric := head bias
+    uint16_t* kcw = reinterpret_cast<uint16_t*>(const_cast<void*>(p.k_cache)) + (new_slot >> 4) * p.kv_block_stride;
+    uint16_t* vcw = reinterpret_cast<uint16_t*>(const_cast<void*>(p.v_cache)) + (new_slot >> 4) * p.kv_block_stride;
+    if (lane < 16) *reinterpret_cast<uint4*>(kcw + lane * (kB * 8) + new_o * 8) = newk;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) vcw[(lane + 32 * r) * kB + new_o] = newv[r];
+    if (lane == 0) p.metric[new_slot] = p.head_bias[h];  // ordered before the reductions below by __syncwarp
+  }
+  if (kFusedMetrics || (MODE == kModeV1 && p.record)) {
     // per-q max / inverse sum to every lane: column q lives in lanes with c == (q % 8) / 2
     __syncwarp();
     float* mi = reinterpret_cast<float*>(psw);  // reuse the P buffer: [NT*8][2] = (M, inv)
@@ -929,6 +980,8 @@ static int fill_params(AttnParams& p, void* out, float* metric, const void* quer
   p.scale = scale; p.max_num_blocks_per_seq = max_num_blocks_per_seq;
   p.q_stride = q_stride; p.kv_block_stride = kv_block_stride;
   p.record = record ? 1 : 0; p.max_partitions = 1; p.num_seqs = num_seqs;
+  p.new_k = nullptr; p.new_v = nullptr; p.new_k_stride = 0; p.new_v_stride = 0;
+  p.slot_mapping = nullptr; p.head_bias = nullptr;
   return KVC_OK;
 }
 
@@ -1021,4 +1074,34 @@ extern "C" size_t kvc_paged_attention_fused_metrics_workspace_bytes(int num_seqs
   const int padded = (max_context_len + kB - 1) / kB * kB;
   if (num_seqs <= 0) return 0;
   return (size_t)num_seqs * num_heads * padded * sizeof(float);  // raw logits [S, Hq, padded]
+}
+
+extern "C" int kvc_paged_attention_fused_step(
+    void* out, float* kv_metrics, const void* query, const void* key, const void* value, void* key_cache,
+    void* value_cache, const int64_t* slot_mapping, const float* kv_metric_head_bias, int num_seqs,
+    int num_heads, int num_kv_heads, int head_size, float scale, const int* block_tables,
+    const int* context_lens, const int* kv_position, const int* last_position,
+    const int* kv_metric_buffer_len, int block_size, int max_context_len, int max_num_blocks_per_seq,
+    int64_t q_stride, int64_t key_stride, int64_t value_stride, int64_t kv_block_stride,
+    const float* alibi_slopes, int dtype, void* workspace, size_t workspace_bytes, kvc_stream_t stream) {
+  AttnParams p;
+  int rc = fill_params(p, out, kv_metrics, query, key_cache, value_cache, num_seqs, num_heads,
+                       num_kv_heads, head_size, scale, block_tables, context_lens, kv_position,
+                       last_position, kv_metric_buffer_len, block_size, max_num_blocks_per_seq,
+                       q_stride, kv_block_stride, alibi_slopes, dtype, 1);
+  if (rc != KVC_OK) return rc;
+  KVC_REQUIRE(key && value && slot_mapping && kv_metric_head_bias, KVC_ERR_INVALID,
+              "fused attention step: null key / value / slot_mapping / head bias");
+  KVC_REQUIRE(key_stride % 8 == 0 && value_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(key) & 15) == 0,
+              KVC_ERR_INVALID, "fused attention step: key must be 16-byte aligned");
+  KVC_REQUIRE(max_context_len > 0, KVC_ERR_INVALID, "fused attention step: max_context_len <= 0");
+  if (num_seqs == 0) return KVC_OK;
+  p.new_k = key; p.new_v = value; p.new_k_stride = key_stride; p.new_v_stride = value_stride;
+  p.slot_mapping = slot_mapping; p.head_bias = kv_metric_head_bias;
+  const int padded = (max_context_len + kB - 1) / kB * kB;
+  const size_t need = kvc_paged_attention_fused_metrics_workspace_bytes(num_seqs, num_heads, max_context_len);
+  KVC_REQUIRE(workspace && workspace_bytes >= need, KVC_ERR_WORKSPACE,
+              "fused attention step: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+  return dispatch_stream<kModeFusedWrite>(p, num_seqs, reinterpret_cast<float*>(workspace), padded, dtype,
+                                          as_stream(stream));
 }

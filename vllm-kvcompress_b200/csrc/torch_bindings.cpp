@@ -354,6 +354,37 @@ void kvcompress_paged_attention_fused_metrics(
                "kvcompress_paged_attention_fused_metrics");
 }
 
+// additive op: see include/kvc_b200.h kvc_paged_attention_fused_step
+void kvcompress_paged_attention_fused_step(
+    torch::Tensor& out, torch::Tensor& kv_metrics, torch::Tensor& query, torch::Tensor& key, torch::Tensor& value,
+    torch::Tensor& key_cache, torch::Tensor& value_cache, torch::Tensor& slot_mapping,
+    torch::Tensor& kv_metric_head_bias, int64_t num_kv_heads, double scale, torch::Tensor& block_tables,
+    torch::Tensor& context_lens, torch::Tensor& kv_position, torch::Tensor& last_position,
+    torch::Tensor& kv_metric_buffer_len, int64_t block_size, int64_t max_context_len,
+    const c10::optional<torch::Tensor>& alibi_slopes, const std::string& kv_cache_dtype) {
+  AttnCommon c = attn_common(out, query, key_cache, value_cache, block_tables, alibi_slopes, kv_cache_dtype);
+  TORCH_CHECK(kv_metrics.scalar_type() == at::kFloat && kv_metrics.is_contiguous(), "kv_metrics must be contiguous float32");
+  TORCH_CHECK(key.dim() == 3 && value.dim() == 3 && key.stride(2) == 1 && key.stride(1) == key.size(2) &&
+                  value.stride(2) == 1 && value.stride(1) == value.size(2),
+              "key / value must be [num_seqs, num_kv_heads, head_size] with dense heads");
+  TORCH_CHECK(key.scalar_type() == query.scalar_type() && value.scalar_type() == query.scalar_type(), "key/value dtype");
+  TORCH_CHECK(slot_mapping.scalar_type() == at::kLong && slot_mapping.is_contiguous() &&
+                  slot_mapping.numel() == key.size(0) * key.size(1), "slot_mapping must be contiguous int64 [num_seqs*num_kv_heads]");
+  TORCH_CHECK(kv_metric_head_bias.scalar_type() == at::kFloat, "kv_metric_head_bias must be float32");
+  const at::cuda::OptionalCUDAGuard guard(device_of(query));
+  const size_t ws_bytes = kvc_paged_attention_fused_metrics_workspace_bytes(c.S, c.Hq, (int)max_context_len);
+  auto ws = torch::empty({(int64_t)ws_bytes}, query.options().dtype(at::kByte));
+  check_status(kvc_paged_attention_fused_step(
+                   out.data_ptr(), kv_metrics.data_ptr<float>(), query.data_ptr(), key.data_ptr(), value.data_ptr(),
+                   key_cache.data_ptr(), value_cache.data_ptr(), slot_mapping.data_ptr<int64_t>(),
+                   kv_metric_head_bias.data_ptr<float>(), c.S, c.Hq, (int)num_kv_heads, c.D, (float)scale,
+                   i32(block_tables, "block_tables"), i32(context_lens, "context_lens"), i32(kv_position, "kv_position"),
+                   i32(last_position, "last_position"), i32(kv_metric_buffer_len, "kv_metric_buffer_len"),
+                   (int)block_size, (int)max_context_len, c.MB, c.q_stride, key.stride(0), value.stride(0),
+                   c.kv_block_stride, c.alibi, c.dtype, ws.data_ptr(), ws_bytes, cur_stream()),
+               "kvcompress_paged_attention_fused_step");
+}
+
 }  // namespace
 
 // FRAGMENT so that the library can coexist with another extension that already owns `_C`.
@@ -395,6 +426,17 @@ TORCH_LIBRARY_FRAGMENT(_C, ops) {
       "    int max_context_len, Tensor? alibi_slopes,"
       "    str kv_cache_dtype) -> ()");
   ops.impl("kvcompress_paged_attention_fused_metrics", torch::kCUDA, &kvcompress_paged_attention_fused_metrics);
+  ops.def(
+      "kvcompress_paged_attention_fused_step("
+      "    Tensor! out, Tensor! kv_metrics, Tensor query, Tensor key, Tensor value,"
+      "    Tensor! key_cache, Tensor! value_cache, Tensor slot_mapping,"
+      "    Tensor kv_metric_head_bias, int num_kv_heads, float scale,"
+      "    Tensor block_tables, Tensor context_lens,"
+      "    Tensor kv_position, Tensor last_position,"
+      "    Tensor kv_metric_buffer_len, int block_size,"
+      "    int max_context_len, Tensor? alibi_slopes,"
+      "    str kv_cache_dtype) -> ()");
+  ops.impl("kvcompress_paged_attention_fused_step", torch::kCUDA, &kvcompress_paged_attention_fused_step);
   // the reference wrapper calls torch.ops._C.schedule_cache_evictions although the op is
   // registered under _C_kvc_ops (vllm/_custom_ops.py:982 vs torch_bindings.cpp:372-386):
   // export it under both names so either resolves.

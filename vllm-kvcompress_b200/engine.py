@@ -52,6 +52,7 @@ class HotPathConfig:
     dtype: torch.dtype = torch.float16
     selection: str = "fused"           # "fused" (kvc_select kernels) | "chain" (torch.sort + K1 + K2)
     fused_metrics: bool = True         # attention accumulates sum_q p^2 itself
+    fused_cache_write: bool = True     # ... and writes the step's new K/V (one launch per layer)
     seed: int = 0
 
 
@@ -175,9 +176,16 @@ class DecodeHotPath:
         q = x[:, : Hq * D].view(-1, Hq, D)
         k = x[:, Hq * D: (Hq + H) * D].view(-1, H, D)
         v = x[:, (Hq + H) * D:].view(-1, H, D)
+        o = o.view(-1, Hq, D)
+        if cfg.fused_metrics and cfg.fused_cache_write:
+            ops.paged_attention_kvc_fused_step(o, st.kv_metrics, q, k, v, st.k_cache, st.v_cache,
+                                               self.slot_mapping[l].reshape(-1), self.head_bias[l], H, self.scale,
+                                               st.block_tables[l], st.context_lens[l], st.kv_position, last_pos,
+                                               self.zeros_s, B, self.max_ctx)
+            self.launches += 1
+            return
         ops.reshape_and_cache_kvc(k, v, st.k_cache, st.v_cache, st.kv_metrics,
                                   self.slot_mapping[l].reshape(-1), self.head_bias[l], "auto", 1.0, 1.0)
-        o = o.view(-1, Hq, D)
         if timing is not None:
             timing[0].record()
         if cfg.fused_metrics:
@@ -296,7 +304,14 @@ class DecodeHotPath:
             for l in range(L):
                 q = qkv[l][:, : Hq * D].view(-1, Hq, D)
                 o = out[l].view(-1, Hq, D)
-                if cfg.fused_metrics:
+                if cfg.fused_metrics and cfg.fused_cache_write:
+                    k = qkv[l][:, Hq * D: (Hq + H) * D].view(-1, H, D)
+                    v = qkv[l][:, (Hq + H) * D:].view(-1, H, D)
+                    ops.paged_attention_kvc_fused_step(o, st.kv_metrics, q, k, v, st.k_cache, st.v_cache,
+                                                       self.slot_mapping[l].reshape(-1), self.head_bias[l], H,
+                                                       self.scale, st.block_tables[l], st.context_lens[l],
+                                                       st.kv_position, last_pos, self.zeros_s, B, self.max_ctx)
+                elif cfg.fused_metrics:
                     ops.paged_attention_kvc_fused_metrics(o, st.kv_metrics, q, st.k_cache, st.v_cache, H,
                                                           self.scale, st.block_tables[l], st.context_lens[l],
                                                           st.kv_position, last_pos, self.zeros_s, B, self.max_ctx)
