@@ -430,12 +430,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // MMA.  No CTA-wide barrier, no cross-warp merge.
 template <bool BF16, int NT, int MODE, bool ALIBI>
 __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kernel(AttnParams p, float* scratch,
-                                                                                   int scratch_tokens) {
+                                                                                   int scratch_tokens,
+                                                                                   int smem_logit_tokens) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
   constexpr int kPsBytes = NT * 8 * 16 * 2;
-  constexpr int kPerWarp = kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32;
   const int H = p.num_kv_heads, Q = p.Q;
+  // per-warp smem: ring | P^T | full/empty barriers | (fused, short contexts) raw logits [Q][smem_logit_tokens]
+  const int kPerWarp = kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32 + smem_logit_tokens * Q * 4;
   const int num_items = p.num_kv_heads * p.num_seqs;
   auto ring_of = [&](int w) { return smem_raw + (size_t)w * kPerWarp; };
   auto full_of = [&](int w) { return smem_u32(ring_of(w) + kNUnit * kUnitBytes + kPsBytes); };
@@ -453,30 +455,49 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
 
   // =========================== producer warp ===========================
   if (wid == kConsumers) {
-    const int item = blockIdx.x * kConsumers + lane;
-    if (lane >= kConsumers || item >= num_items) return;
+    // four producer lanes per consumer ring: lane (w, j) issues units u = j, j+4, j+8, ... of ring w, so up
+    // to 28 bulk copies go out per polling pass and no lane ever blocks (test_wait, not try_wait).
+    const int w = lane >> 2, j = lane & 3;
+    const int item = blockIdx.x * kConsumers + w;
+    if (w >= kConsumers || item >= num_items) return;
     const int* __restrict__ bt = p.block_tables + (int64_t)item * p.max_num_blocks_per_seq;
-    const int bt0 = bt[0];                 // speculative: issued together with the context length
+    const int bt_spec0 = bt[0], bt_spec1 = (p.max_num_blocks_per_seq > 1) ? bt[1] : 0;  // speculative, with ctx
     const int ctx = p.context_lens[item];  // item == s * H + h
     const int nblk = (ctx + kB - 1) / kB;
     if (nblk == 0) return;
     const uint16_t* __restrict__ kc = reinterpret_cast<const uint16_t*>(p.k_cache);
     const uint16_t* __restrict__ vc = reinterpret_cast<const uint16_t*>(p.v_cache);
-    const uint32_t ring = smem_u32(ring_of(lane)), full = full_of(lane), empty = empty_of(lane);
-    int slot = 0, round = 0;  // unit u = round * kNUnit + slot
-    int phys = bt0;
-    for (int b = 0; b < nblk; ++b) {
-      const int next_phys = (b + 1 < nblk) ? bt[b + 1] : 0;  // prefetch the next table entry
-      const uint16_t* kp = kc + (int64_t)phys * p.kv_block_stride;
-      const uint16_t* vp = vc + (int64_t)phys * p.kv_block_stride;
-#pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        if (round > 0) mbar_wait(empty + 8 * slot, (round - 1) & 1);  // consumer drained this slot
-        mbar_expect_tx(full + 8 * slot, kUnitBytes);
-        bulk_g2s(ring + slot * kUnitBytes, ((r & 2) ? vp : kp) + (r & 1) * (kUnitBytes / 2), kUnitBytes, full + 8 * slot);
-        if (++slot == kNUnit) { slot = 0; ++round; }
+    const uint32_t ring = smem_u32(ring_of(w)), full = full_of(w), empty = empty_of(w);
+    const unsigned lanes = __activemask();
+    const int nunits = 4 * nblk;
+    // Unit order = the consumer's software pipeline: K(0) lo/hi; then per block b: K(b+1) lo/hi (if any), V(b) lo/hi.
+    auto decode = [&](int u, int& isv, int& hf, int& blk) {
+      if (u < 2) { isv = 0; hf = u; blk = 0; return; }
+      const int t = u - 2, b = t >> 2, r = t & 3;
+      if (b < nblk - 1) { isv = r >> 1; hf = r & 1; blk = isv ? b : b + 1; }
+      else { isv = 1; hf = (t - 4 * (nblk - 1)) & 1; blk = nblk - 1; }
+    };
+    int u = j;
+    int isv = 0, hf = 0, blk = 0, phys = 0;
+    if (u < nunits) { decode(u, isv, hf, blk); phys = (blk == 0) ? bt_spec0 : bt_spec1; }  // first unit: blk <= 1
+    while (__any_sync(lanes, u < nunits)) {
+      if (u < nunits) {
+        const int slot = u % kNUnit, round = u / kNUnit;
+        bool ready = true;
+        if (round > 0) {
+          uint32_t ok;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(empty + 8 * slot), "r"((uint32_t)((round - 1) & 1)) : "memory");
+          ready = ok != 0;
+        }
+        if (ready) {
+          const uint16_t* src = (isv ? vc : kc) + (int64_t)phys * p.kv_block_stride + hf * (kUnitBytes / 2);
+          mbar_expect_tx(full + 8 * slot, kUnitBytes);
+          bulk_g2s(ring + slot * kUnitBytes, src, kUnitBytes, full + 8 * slot);
+          u += 4;
+          if (u < nunits) { decode(u, isv, hf, blk); phys = bt[blk]; }  // table entry of the lane's next unit
+        }
       }
-      phys = next_phys;
     }
     return;
   }
@@ -503,9 +524,17 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   float* lg0 = nullptr;
   float* lg1 = nullptr;
   constexpr bool kFusedMetrics = (MODE == kModeFused || MODE == kModeFusedWrite);
+  // short contexts: logits stay in this warp's shared memory and the recording rule is evaluated
+  // block by block during the sweep (bit 2b / 2b+1 of `passbits`), so the epilogue has no dependent
+  // global loads; long contexts park them in the global scratch row instead
+  const bool smem_logits = kFusedMetrics && smem_logit_tokens > 0;
+  const int lg_stride = smem_logits ? smem_logit_tokens : scratch_tokens;
+  unsigned long long passbits = 0ull;
   if (kFusedMetrics) {
-    lg0 = scratch + ((int64_t)item * Q + 2 * c) * scratch_tokens;  // column q = 2c (nt = 0)
-    lg1 = lg0 + scratch_tokens;
+    float* base = smem_logits ? reinterpret_cast<float*>(ring + kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32)
+                              : scratch + (int64_t)item * Q * scratch_tokens;
+    lg0 = base + (2 * c) * lg_stride;  // column q = 2c (nt = 0)
+    lg1 = lg0 + lg_stride;
   }
 
   // fused cache write (kvcompress_reshape_and_cache folded in, csrc/kvcompress_cache_kernels.cu:44-88):
@@ -528,15 +557,19 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     }
   }
 
-  uint4 qf[NT][4];
+  // Q as the B operand of S^T = K Q^T in the standard m16n8k16 layout: k-step ks covers d = 16 ks .. 16 ks + 15,
+  // b0 = Q[g][16 ks + 2c, +1], b1 = Q[g][16 ks + 8 + 2c, +1]
+  uint32_t qf[NT][8][2];
   float slope[NT][2];
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     const int ql = nt * 8 + g;
     const uint16_t* qp = reinterpret_cast<const uint16_t*>(p.q) + (int64_t)s * p.q_stride + (int64_t)(h * Q + ql) * kD;
 #pragma unroll
-    for (int s4 = 0; s4 < 4; ++s4)
-      qf[nt][s4] = (ql < Q) ? *reinterpret_cast<const uint4*>(qp + (4 * s4 + c) * 8) : make_uint4(0, 0, 0, 0);
+    for (int ks = 0; ks < 8; ++ks) {
+      qf[nt][ks][0] = (ql < Q) ? *reinterpret_cast<const uint32_t*>(qp + 16 * ks + 2 * c) : 0u;
+      qf[nt][ks][1] = (ql < Q) ? *reinterpret_cast<const uint32_t*>(qp + 16 * ks + 8 + 2 * c) : 0u;
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int qc = nt * 8 + 2 * c + i;
@@ -555,7 +588,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
       for (int i = 0; i < 4; ++i) oacc[nt][dt][i] = 0.f;
   }
   // per-lane fragment offsets inside a unit (bytes): K chunk c of token g; V row g, tokens 4c..4c+3
-  const int koff = c * (kB * 16) + g * 16;
+  // ldmatrix.x4 row address of this lane inside a K half: matrix m = lane / 8 -> chunk (m >> 1), tokens 8 * (m & 1) + lane % 8
+  const int koff = (lane >> 4) * (kB * 16) + (((lane >> 3) & 1) * 8 + (lane & 7)) * 16;
   const int voff = g * (kB * 2) + c * 8;
   int slot = 0;
   uint32_t phase = 0;
@@ -569,6 +603,40 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     if (++slot == kNUnit) { slot = 0; phase ^= 1u; }
   };
 
+  // S^T(kblk) = K Q^T: consume the two K halves of block kblk, issue two independent MMA chains
+  auto consume_k = [&](int kblk, float (&sacc)[2][NT][4]) {
+    const bool klast = (kblk == nblk - 1);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const unsigned char* kU = next_unit();
+      if (MODE == kModeFusedWrite && klast && new_o >= 0) {  // patch the new token into the staged K half
+        if ((lane >> 3) == hf && lane < 16)
+          *reinterpret_cast<uint4*>(const_cast<unsigned char*>(kU) + (lane & 7) * (kB * 16) + new_o * 16) = newk;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic write, slot later refilled by TMA
+        __syncwarp();
+      }
+      // four k-steps per half; one conflict-free ldmatrix.x4 per step: (chunk 2j, tok 0-7), (chunk 2j, tok 8-15),
+      // (chunk 2j+1, tok 0-7), (chunk 2j+1, tok 8-15) = a0..a3 of the m16n8k16 A fragment
+      const uint32_t kaddr = smem_u32(kU) + koff;
+      uint32_t ka[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(ka[j][0]), "=r"(ka[j][1]), "=r"(ka[j][2]), "=r"(ka[j][3])
+                     : "r"(kaddr + j * (2 * kB * 16)));
+      release_unit();
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        sacc[hf][nt][0] = sacc[hf][nt][1] = sacc[hf][nt][2] = sacc[hf][nt][3] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          mma16816<BF16>(sacc[hf][nt], ka[j][0], ka[j][1], ka[j][2], ka[j][3], qf[nt][4 * hf + j][0], qf[nt][4 * hf + j][1]);
+      }
+    }
+  };
+
+  float sacc[2][NT][4];  // logits of the block whose softmax is next
+  consume_k(0, sacc);
   for (int b = 0; b < nblk; ++b) {
     const int tok0 = b * kB + g, tok1 = tok0 + 8;
     const bool last = (b == nblk - 1);
@@ -581,36 +649,15 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
       rec0 = tok0 < ctx && p.kv_position[slot0] <= max_pos;
       rec1 = tok1 < ctx && p.kv_position[slot1] <= max_pos;
     }
-    // ---- S^T = K Q^T: two independent chains (K halves) ----
-    float sacc[2][NT][4];
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const unsigned char* kU = next_unit();
-      if (MODE == kModeFusedWrite && last && new_o >= 0) {  // patch the new token into the staged K half
-        if ((lane >> 3) == hf && lane < 16)
-          *reinterpret_cast<uint4*>(const_cast<unsigned char*>(kU) + (lane & 7) * (kB * 16) + new_o * 16) = newk;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic write, slot later refilled by TMA
-        __syncwarp();
-      }
-      const unsigned char* kS = kU + koff;
-      uint4 ka[2], kb[2];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {  // chunk 4*(2*hf+j) + c of the block = chunk 4*j + c of this half
-        ka[j] = *reinterpret_cast<const uint4*>(kS + j * (4 * kB * 16));
-        kb[j] = *reinterpret_cast<const uint4*>(kS + j * (4 * kB * 16) + 8 * 16);
-      }
-      release_unit();
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) {
-        sacc[hf][nt][0] = sacc[hf][nt][1] = sacc[hf][nt][2] = sacc[hf][nt][3] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int s4 = 2 * hf + j;
-          mma16816<BF16>(sacc[hf][nt], ka[j].x, kb[j].x, ka[j].y, kb[j].y, qf[nt][s4].x, qf[nt][s4].y);
-          mma16816<BF16>(sacc[hf][nt], ka[j].z, kb[j].z, ka[j].w, kb[j].w, qf[nt][s4].z, qf[nt][s4].w);
-        }
-      }
+    int pos0 = 0x7fffffff, pos1 = 0x7fffffff;
+    if (smem_logits) {  // recording rule of this block's two tokens (loads overlap the math below)
+      const int64_t phys = bt[b];
+      if (tok0 < ctx) pos0 = p.kv_position[phys * kB + g];
+      if (tok1 < ctx) pos1 = p.kv_position[phys * kB + g + 8];
     }
+    // software pipeline: the next block's QK^T chains are in flight while this block's softmax runs
+    float snext[2][NT][4];
+    if (!last) consume_k(b + 1, snext);
     // ---- logits + online softmax ----
     bool rescale = false;
     float alpha[NT][2];
@@ -632,7 +679,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
         const int qc = nt * 8 + 2 * c + i;
         if (qc < Q) {
           if (kFusedMetrics) {
-            float* lg = (i ? lg1 : lg0) + nt * 8 * scratch_tokens;
+            float* lg = (i ? lg1 : lg0) + nt * 8 * lg_stride;
             lg[tok0] = s0;  // slots beyond ctx exist in the scratch row (padded to a block multiple)
             lg[tok1] = s1;
           } else {
@@ -710,6 +757,18 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
       }
     }
     __syncwarp();  // P buffer is rewritten next iteration
+    if (smem_logits) {
+      passbits |= (unsigned long long)(pos0 <= max_pos) << (2 * (b & 31));
+      passbits |= (unsigned long long)(pos1 <= max_pos) << (2 * (b & 31) + 1);
+    }
+    if (!last) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sacc[hf][nt][i] = snext[hf][nt][i];
+    }
   }
 
   // ---- output: O / (L + 1e-6); lane (g,c) holds O[d = 16 dt + g (+8)][q = 2c, 2c+1] ----
@@ -741,7 +800,37 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     for (int r = 0; r < 4; ++r) vcw[(lane + 32 * r) * kB + new_o] = newv[r];
     if (lane == 0) p.metric[new_slot] = p.head_bias[h];  // ordered before the reductions below by __syncwarp
   }
-  if (kFusedMetrics || (MODE == kModeV1 && p.record)) {
+  if (smem_logits) {
+    // metrics[slot] += sum_q p^2 from the warp's own shared-memory logits; every lane finalises the two
+    // tokens x two columns it produced, the column sum runs over the 4 lanes of a token (c = 0..3)
+    __syncwarp();
+    for (int b = 0; b < nblk; ++b) {
+      const int tok0 = b * kB + g, tok1 = tok0 + 8;
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          if (nt * 8 + 2 * c + i < Q) {
+            const float* lg = (i ? lg1 : lg0) + nt * 8 * lg_stride;
+            const float p0 = __expf(lg[tok0] - m_run[nt][i]) * inv[nt][i];
+            const float p1 = __expf(lg[tok1] - m_run[nt][i]) * inv[nt][i];
+            a0 += p0 * p0;
+            a1 += p1 * p1;
+          }
+        }
+      a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+      a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+      if (c == 0) {
+        const int64_t phys = bt[b];
+        // every slot belongs to exactly one warp: a fire-and-forget reduction, no read-back
+        if ((passbits >> (2 * (b & 31))) & 1ull) atomicAdd(&p.metric[phys * kB + g], a0);
+        if ((passbits >> (2 * (b & 31) + 1)) & 1ull) atomicAdd(&p.metric[phys * kB + g + 8], a1);
+      }
+    }
+  } else if (kFusedMetrics || (MODE == kModeV1 && p.record)) {
     // per-q max / inverse sum to every lane: column q lives in lanes with c == (q % 8) / 2
     __syncwarp();
     float* mi = reinterpret_cast<float*>(psw);  // reuse the P buffer: [NT*8][2] = (M, inv)
@@ -913,18 +1002,25 @@ static int dispatch_attention(const AttnParams& p, int num_seqs, int partitions,
 
 template <bool BF16, int NT, int MODE>
 static int launch_stream(const AttnParams& p, int num_seqs, float* scratch, int scratch_tokens, cudaStream_t st) {
-  const size_t smem = (size_t)kConsumers * (kNUnit * kUnitBytes + NT * 8 * 16 * 2 + 2 * kNUnit * 8 + 32);
+  // fused modes: keep the raw logits in shared memory when [Q][padded ctx] fits next to the ring
+  // (<= 32 blocks so the recording bits fit one 64-bit register, and <= 3.5 KB per warp)
+  int smem_logit_tokens = 0;
+  if ((MODE == kModeFused || MODE == kModeFusedWrite) && scratch_tokens <= 32 * kB &&
+      (size_t)scratch_tokens * p.Q * 4 <= 3584)
+    smem_logit_tokens = scratch_tokens;
+  const size_t smem = (size_t)kConsumers * (kNUnit * kUnitBytes + NT * 8 * 16 * 2 + 2 * kNUnit * 8 + 32 +
+                                            (size_t)smem_logit_tokens * p.Q * 4);
   const int items = num_seqs * p.num_kv_heads;
   const dim3 grid((items + kConsumers - 1) / kConsumers);
   cudaError_t e;
   if (p.alibi_slopes) {
     auto kern = paged_attention_stream_kernel<BF16, NT, MODE, true>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) kern<<<grid, kStreamThreads, smem, st>>>(p, scratch, scratch_tokens);
+    if (e == cudaSuccess) kern<<<grid, kStreamThreads, smem, st>>>(p, scratch, scratch_tokens, smem_logit_tokens);
   } else {
     auto kern = paged_attention_stream_kernel<BF16, NT, MODE, false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) kern<<<grid, kStreamThreads, smem, st>>>(p, scratch, scratch_tokens);
+    if (e == cudaSuccess) kern<<<grid, kStreamThreads, smem, st>>>(p, scratch, scratch_tokens, smem_logit_tokens);
   }
   if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "paged attention (stream) smem attr: %s", cudaGetErrorString(e));
   KVC_CHECK_LAUNCH("paged_attention_stream_kernel");
