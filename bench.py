@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
     ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama3-70b"],
+                    help="shape preset: 8b = L32 H8 Q4 CR64 (max_cache_tokens 128); 70b = L80 H8 Q8 CR16 (368)")
     ap.add_argument("--selection", default="fused", choices=["fused", "chain"])
     ap.add_argument("--unfused-metrics", action="store_true")
     ap.add_argument("--separate-cache-write", action="store_true", help="K6 as its own launch per layer")
@@ -141,8 +143,12 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, batch):
-    return {"workload": "Llama-3-8B shape (L=32, H_kv=8, Q=4, D=128, block 16), input 6000 / output 500, "
-                        "CR 64x => max_cache_tokens=128, protected_window=32, continual compression every step",
+    wl = ("Llama-3-8B shape (L=32, H_kv=8, Q=4, D=128, block 16), input 6000 / output 500, "
+          "CR 64x => max_cache_tokens=128, protected_window=32, continual compression every step")
+    if getattr(args, "model", "llama3-8b") == "llama3-70b":
+        wl = ("Llama-3-70B shape (L=80, H_kv=8, Q=8, D=128, block 16), input 6000 / output 500, "
+              "CR 16x => max_cache_tokens=368, protected_window=32, continual compression every step")
+    return {"workload": wl,
             "global_batch": batch, "seq_len": 6000, "parallelism": "request-sharded replicas",
             "l2": "inputs larger than L2 (per-step KV read ~4.6 GB vs 126 MB L2)",
             "selection": args.selection, "fused_metrics": not args.unfused_metrics,
@@ -210,8 +216,12 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from vllm_kvcompress_b200.engine import DecodeHotPath, HotPathConfig
 
+    preset = {}
+    if args.model == "llama3-70b":  # BASELINE.json configs[3]
+        args.layers = 80
+        preset = dict(queries_per_kv=8, max_cache_tokens=368, blocks_per_head=28)
     cfg = HotPathConfig(num_seqs=args.batch, num_layers=args.layers, selection=args.selection,
-                        fused_metrics=not args.unfused_metrics,
+                        fused_metrics=not args.unfused_metrics, **preset,
                         fused_cache_write=not args.separate_cache_write, seed=rank)
     from vllm_kvcompress_b200 import sharding
     # the only collective on this path: one start-up broadcast (stands in for the weight broadcast

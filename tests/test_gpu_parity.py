@@ -551,7 +551,8 @@ def selection_case(seed, S, L, H, B, max_blocks, prot, frac):
 @pytest.mark.parametrize("cfg", [
     (71, 3, 2, 2, 4, 5, 3, 0.5),
     (72, 4, 4, 8, 16, 10, 16, 0.4),      # <= 256 slots per head: warp-per-head path
-    (73, 2, 4, 8, 16, 40, 32, 0.7),      # > 256 slots per head: CTA-per-head path
+    (77, 3, 4, 8, 16, 28, 32, 0.6),      # 257..512 slots per head: warp path with 16 keys per lane
+    (73, 2, 4, 8, 16, 40, 32, 0.7),      # > 512 slots per head: CTA-per-head path
     (74, 3, 3, 4, 16, 9, 0, 2.0),        # budget larger than what exists
     (75, 2, 2, 2, 1, 100, 7, 0.5),
     (76, 2, 32, 8, 16, 9, 32, 0.12),     # Llama-3-8B head count, steady-state-like budget

@@ -22,8 +22,8 @@
 // keys evicts its (k-1)*B + r0 lowest-metric candidates.
 //
 // Three launches, no host round trip:
-//   1. keys:   ctx <= 256: one warp per head, 8 consecutive slots per lane (two 16 B loads of
-//              metrics and of positions), a 256-key bitonic sort in registers (warp shuffles), the
+//   1. keys:   ctx <= 512: one warp per head, 8 or 16 consecutive slots per lane (two 16 B loads of
+//              metrics and of positions), a 256/512-key bitonic sort in registers (warp shuffles), the
 //              completion keys = sorted ranks r0-1+kB go to the workspace.  Longer contexts: one CTA
 //              per head, keys staged in shared memory, rank by counting.
 //   2. select: one CTA per sequence; 4-pass radix select of the E-th smallest completion key,
@@ -96,7 +96,7 @@ __device__ __forceinline__ void load_keys8(const SelectParams& p, const int* __r
 
 // ---- warp-per-head path (ctx <= 256): bitonic sort of 256 keys, 8 per lane ----
 // element e = lane * 8 + r  <->  logical slot e.
-template <int B>
+template <int B, int KPL>
 __global__ void __launch_bounds__(128) select_sort_kernel(SelectParams p) {
   const int lane = threadIdx.x % kWarp;
   const int g = blockIdx.x * 4 + threadIdx.x / kWarp;
@@ -108,35 +108,42 @@ __global__ void __launch_bounds__(128) select_sort_kernel(SelectParams p) {
   const int off = p.offsets[g];
   const int r0 = p.hanging[g];
   const int max_pos = p.last_position[s] - p.protected_window[s];
-  unsigned k[8];
-  load_keys8<B>(p, p.block_tables + (int64_t)lsh * p.MB, lane * 8, n, max_pos, k);
+  constexpr int N = 32 * KPL;  // keys sorted by the warp (256 or 512)
+  unsigned k[KPL];
+#pragma unroll
+  for (int q = 0; q < KPL / 8; ++q) {
+    unsigned t8[8];
+    load_keys8<B>(p, p.block_tables + (int64_t)lsh * p.MB, lane * KPL + 8 * q, n, max_pos, t8);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) k[8 * q + r] = t8[r];
+  }
   int local = 0;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) local += (k[r] != kInfKey);
+  for (int r = 0; r < KPL; ++r) local += (k[r] != kInfKey);
   int ncand = local;
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, d);
-  // bitonic sort, ascending over e = lane*8 + r
+  // bitonic sort, ascending over e = lane*KPL + r
 #pragma unroll
-  for (int kk = 2; kk <= 256; kk <<= 1) {
+  for (int kk = 2; kk <= N; kk <<= 1) {
 #pragma unroll
     for (int j = kk >> 1; j >= 1; j >>= 1) {
-      if (j >= 8) {
-        const int lj = j >> 3;
-        const bool up = ((lane * 8) & kk) == 0;      // ascending segment (kk >= 16 here)
+      if (j >= KPL) {
+        const int lj = j / KPL;
+        const bool up = ((lane * KPL) & kk) == 0;    // ascending segment (kk >= 2*KPL here)
         const bool lower = (lane & lj) == 0;         // this lane holds the lower index of the pair
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < KPL; ++r) {
           const unsigned o = __shfl_xor_sync(0xffffffffu, k[r], lj);
           const unsigned mn = min(k[r], o), mx = max(k[r], o);
           k[r] = (up == lower) ? mn : mx;
         }
       } else {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
+        for (int r = 0; r < KPL; ++r) {
           const int pr = r ^ j;
           if (pr > r) {
-            const bool up = (((lane * 8 + r) & kk) == 0);
+            const bool up = (((lane * KPL + r) & kk) == 0);
             const unsigned a = k[r], b = k[pr];
             const unsigned mn = min(a, b), mx = max(a, b);
             k[r] = up ? mn : mx;
@@ -150,15 +157,15 @@ __global__ void __launch_bounds__(128) select_sort_kernel(SelectParams p) {
   const int nev = (r0 >= 1 && ncand >= r0) ? (ncand - r0) / B + 1 : 0;
   unsigned* ev = p.events + off / B;
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int e = lane * 8 + r;
+  for (int r = 0; r < KPL; ++r) {
+    const int e = lane * KPL + r;
     const int d = e - (r0 - 1);
     if (d >= 0 && d % B == 0 && d / B < nev) ev[d / B] = k[r];
   }
   for (int q = nev + lane; q < nblk; q += kWarp) ev[q] = kInfKey;
 }
 
-template <int B>
+template <int B, int KPL>
 __global__ void __launch_bounds__(128) select_emit_warp_kernel(SelectParams p) {
   const int lane = threadIdx.x % kWarp;
   const int g = blockIdx.x * 4 + threadIdx.x / kWarp;
@@ -173,12 +180,18 @@ __global__ void __launch_bounds__(128) select_emit_warp_kernel(SelectParams p) {
   int* __restrict__ out = p.evicted_logical_indices + off;
   if (cnt > 0) {
     const int max_pos = p.last_position[s] - p.protected_window[s];
-    unsigned k[8];
-    load_keys8<B>(p, p.block_tables + (int64_t)lsh * p.MB, lane * 8, n, max_pos, k);
+    unsigned k[KPL];
+#pragma unroll
+    for (int q = 0; q < KPL / 8; ++q) {
+      unsigned t8[8];
+      load_keys8<B>(p, p.block_tables + (int64_t)lsh * p.MB, lane * KPL + 8 * q, n, max_pos, t8);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) k[8 * q + r] = t8[r];
+    }
     const unsigned T = p.events[off / B + kblk - 1];  // key of the last evicted rank
     int nless = 0, neq = 0;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < KPL; ++r) {
       nless += (k[r] < T);
       neq += (k[r] == T);
     }
@@ -193,10 +206,10 @@ __global__ void __launch_bounds__(128) select_emit_warp_kernel(SelectParams p) {
     }
     int eq_seen = eq_incl - neq;
     const int allowed = cnt - tot_less;
-    bool evict[8];
+    bool evict[KPL];
     int nev = 0;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < KPL; ++r) {
       evict[r] = (k[r] < T) || (k[r] == T && eq_seen < allowed);
       eq_seen += (k[r] == T);
       nev += evict[r];
@@ -209,8 +222,8 @@ __global__ void __launch_bounds__(128) select_emit_warp_kernel(SelectParams p) {
     }
     int pos = incl - nev;
 #pragma unroll
-    for (int r = 0; r < 8; ++r)
-      if (evict[r]) out[pos++] = lane * 8 + r;
+    for (int r = 0; r < KPL; ++r)
+      if (evict[r]) out[pos++] = lane * KPL + r;
   }
   for (int i = cnt + lane; i < nblk * B; i += kWarp) out[i] = p.null_index;
 }
@@ -463,12 +476,24 @@ extern "C" int kvc_select_evictions(
   cudaStream_t st = as_stream(stream);
   const int total = num_seqs * num_layers * num_kv_heads;
   const int max_slots = max_num_blocks_per_seq * block_size;
-  const bool warp_path = max_slots <= 256;  // steady-state compressed contexts: one warp per head
+  const bool warp_path = max_slots <= 512;  // compressed contexts: one warp per head, 8 or 16 keys per lane
+  const dim3 wgrid(ceil_div(total, 4));
+#define KVC_SEL_WARP(KERNEL)                                                     \
+  do {                                                                           \
+    if (max_slots <= 256) {                                                      \
+      if (block_size == 16) KERNEL<16, 8><<<wgrid, 128, 0, st>>>(p);             \
+      else if (block_size == 4) KERNEL<4, 8><<<wgrid, 128, 0, st>>>(p);          \
+      else if (block_size == 2) KERNEL<2, 8><<<wgrid, 128, 0, st>>>(p);          \
+      else KERNEL<1, 8><<<wgrid, 128, 0, st>>>(p);                               \
+    } else {                                                                     \
+      if (block_size == 16) KERNEL<16, 16><<<wgrid, 128, 0, st>>>(p);            \
+      else if (block_size == 4) KERNEL<4, 16><<<wgrid, 128, 0, st>>>(p);         \
+      else if (block_size == 2) KERNEL<2, 16><<<wgrid, 128, 0, st>>>(p);         \
+      else KERNEL<1, 16><<<wgrid, 128, 0, st>>>(p);                              \
+    }                                                                            \
+  } while (0)
   if (warp_path) {
-    if (block_size == 16) select_sort_kernel<16><<<ceil_div(total, 4), 128, 0, st>>>(p);
-    else if (block_size == 4) select_sort_kernel<4><<<ceil_div(total, 4), 128, 0, st>>>(p);
-    else if (block_size == 2) select_sort_kernel<2><<<ceil_div(total, 4), 128, 0, st>>>(p);
-    else select_sort_kernel<1><<<ceil_div(total, 4), 128, 0, st>>>(p);
+    KVC_SEL_WARP(select_sort_kernel);
     KVC_CHECK_LAUNCH("select_sort_kernel");
   } else {
     const size_t smem = (size_t)max_slots * sizeof(unsigned);
@@ -484,13 +509,11 @@ extern "C" int kvc_select_evictions(
   select_threshold_kernel<<<num_seqs, 256, 0, st>>>(p);
   KVC_CHECK_LAUNCH("select_threshold_kernel");
   if (warp_path) {
-    if (block_size == 16) select_emit_warp_kernel<16><<<ceil_div(total, 4), 128, 0, st>>>(p);
-    else if (block_size == 4) select_emit_warp_kernel<4><<<ceil_div(total, 4), 128, 0, st>>>(p);
-    else if (block_size == 2) select_emit_warp_kernel<2><<<ceil_div(total, 4), 128, 0, st>>>(p);
-    else select_emit_warp_kernel<1><<<ceil_div(total, 4), 128, 0, st>>>(p);
+    KVC_SEL_WARP(select_emit_warp_kernel);
   } else {
     select_emit_cta_kernel<<<total, 128, 0, st>>>(p);
   }
+#undef KVC_SEL_WARP
   KVC_CHECK_LAUNCH("select_emit_kernel");
   return KVC_OK;
 }
