@@ -158,12 +158,12 @@ def workload_config(args, batch):
 
 def compaction_roofline(device, peak):
     """execute_cache_moves on the post-prefill shape of BASELINE.md config 5 (S=3 sequences of
-    6000 tokens, L=32, H=8), CR in {64, 4}: algorithmic GB/s (1048 B per move) vs HBM peak."""
+    6000 tokens, L=32, H=8), CR in {64, 16, 8, 4}: algorithmic GB/s (1048 B per move) vs HBM peak."""
     from vllm_kvcompress_b200 import _custom_ops as ops
     from vllm_kvcompress_b200 import workload as W
     res = {}
     S, L, H, B, D = 3, 32, 8, 16, 128
-    for cr, keep in ((64, 128), (4, 1488)):
+    for cr, keep in ((64, 128), (16, 368), (8, 736), (4, 1488)):  # BASELINE.md config 5: max_cache_tokens per CR
         st = W.make_state(S, L, H, B, D, 6000, dtype=torch.float16, device=device, seed=cr, slack=1.0,
                           fill_cache=False)
         hanging = W.hanging_token_counts(st.context_lens, B).transpose(0, 1).contiguous()

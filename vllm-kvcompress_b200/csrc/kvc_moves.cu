@@ -245,6 +245,7 @@ extern "C" int kvc_execute_cache_moves(
               KVC_ERR_UNSUPPORTED, "Unsupported block size: %d", block_size);
   KVC_REQUIRE(dtype == KVC_F16 || dtype == KVC_BF16 || dtype == KVC_F32 || dtype == KVC_U8,
               KVC_ERR_UNSUPPORTED, "Unsupported data type: %d", dtype);
+  if (num_seqs == 0) return KVC_OK;
   KVC_REQUIRE(k_cache && v_cache && kv_metrics && kv_position && cache_moves_idx &&
                   cache_moves_count && evicted_kv_offsets,
               KVC_ERR_INVALID, "execute_cache_moves: null tensor");

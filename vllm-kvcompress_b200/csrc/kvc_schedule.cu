@@ -603,6 +603,7 @@ extern "C" int kvc_truncate_cache_evictions(
     int null_eviction_index, kvc_stream_t stream) {
   KVC_REQUIRE(supported_sched_block_size(block_size), KVC_ERR_UNSUPPORTED,
               "Unsupported block size: %d", block_size);
+  if (num_seqs == 0) return KVC_OK;  // empty batch: nothing to do (tensors may be empty / null)
   KVC_REQUIRE(evicted_kv_indices && evicted_logical_indices && evicted_kv_count &&
                   evicted_kv_offsets && hanging_token_count,
               KVC_ERR_INVALID, "truncate_cache_evictions: null tensor");
@@ -620,6 +621,7 @@ extern "C" int kvc_count_block_evictions(
     int total_kvs, int block_size, int null_value, kvc_stream_t stream) {
   KVC_REQUIRE(supported_sched_block_size(block_size), KVC_ERR_UNSUPPORTED,
               "Unsupported block size: %d", block_size);
+  if (num_seqs == 0) return KVC_OK;
   KVC_REQUIRE(evicted_block_count && evicted_logical_indices && evicted_kv_offsets &&
                   hanging_token_count,
               KVC_ERR_INVALID, "count_block_evictions: null tensor");
@@ -639,6 +641,7 @@ extern "C" int kvc_schedule_t1_cache_moves(
     int max_num_blocks_per_seq, int block_size, kvc_stream_t stream) {
   KVC_REQUIRE(supported_sched_block_size(block_size), KVC_ERR_UNSUPPORTED,
               "Unsupported block size: %d", block_size);
+  if (num_seqs == 0) return KVC_OK;
   KVC_REQUIRE(cache_moves_idx && cache_moves_count && evicted_logical_indices &&
                   evicted_kv_count && evicted_kv_offsets && block_tables && context_lens,
               KVC_ERR_INVALID, "schedule_t1_cache_moves: null tensor");
@@ -694,6 +697,7 @@ extern "C" int kvc_schedule_cache_evictions(
     kvc_stream_t stream) {
   KVC_REQUIRE(supported_sched_block_size(block_size), KVC_ERR_UNSUPPORTED,
               "Unsupported block size: %d", block_size);
+  if (num_seqs == 0) return KVC_OK;
   KVC_REQUIRE(evicted_kv_indices && evicted_logical_indices && evicted_kv_count &&
                   remaining_kv_count && evicted_kv_offsets && sorted_indices && seq_block_offsets &&
                   layer_by_block && head_by_block && virtual_block_num_by_block &&
