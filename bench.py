@@ -176,11 +176,24 @@ def compaction_roofline(device, peak):
         logical = torch.empty(N, dtype=torch.int32, device=device)
         cnt = torch.empty((S, L, H), dtype=torch.int32, device=device)
         blk = torch.empty_like(cnt)
-        ops.select_evictions(logical, cnt, blk, st.kv_metrics, st.kv_position, st.block_tables, st.context_lens,
-                             hanging, offs, budgets, last, prot, B, W.MAX_INT)
+        def timed(fn, reps=5):
+            ts = []
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            return sorted(ts[1:])[len(ts[1:]) // 2]
+
+        sel_ms = timed(lambda: ops.select_evictions(logical, cnt, blk, st.kv_metrics, st.kv_position,
+                                                    st.block_tables, st.context_lens, hanging, offs, budgets,
+                                                    last, prot, B, W.MAX_INT))
         moves = torch.empty((N, 2), dtype=torch.int32, device=device)
         mcnt = torch.empty((S, L, H), dtype=torch.int32, device=device)
-        ops.schedule_cache_moves(moves, mcnt, logical, cnt, offs, st.block_tables, st.context_lens, B)
+        k4_ms = timed(lambda: torch.ops._C_kvc_ops.schedule_t1_cache_moves(moves, mcnt, logical, cnt, offs,
+                                                                           st.block_tables, st.context_lens, B))
         nmoves = int(mcnt.sum())
         times = []
         for it in range(6):  # moves are idempotent on the same state (src never overwritten): re-run is valid
@@ -193,10 +206,40 @@ def compaction_roofline(device, peak):
         t = sorted(times[1:])[len(times[1:]) // 2]
         gbs = nmoves * 1048 / (t * 1e-3) / 1e9
         res[f"cr{cr}"] = {"moves": nmoves, "ms": t, "achieved_gbs": gbs, "frac": gbs / peak,
-                          "cache_gb": st.NB * 8192 / 1e9}
+                          "cache_gb": st.NB * 8192 / 1e9,
+                          # the schedule builders in front of it (12 B per candidate slot, 20 B per move)
+                          "select_evictions_ms": sel_ms, "select_gbs": N * 12 / (sel_ms * 1e-3) / 1e9,
+                          "schedule_moves_ms": k4_ms}
         del st, moves
         torch.cuda.empty_cache()
     return res
+
+
+def prefill_metrics_bench(device):
+    """Prefill metric initialisation (tcgen05 kernels) on 4 prompts of 6000 tokens, Llama-3-8B heads:
+    2 passes x 2*rows*keys*D FLOPs on the tensor cores (rows = 32 observed queries x 32 query heads)."""
+    from vllm_kvcompress_b200 import _custom_ops as ops
+    lens, Hq, H, D = [6000] * 4, 32, 8, 128
+    T = sum(lens)
+    g = torch.Generator(device=device).manual_seed(3)
+    q = torch.randn((T, Hq, D), generator=g, device=device, dtype=torch.float32).to(torch.float16)
+    k = torch.randn((T, H, D), generator=g, device=device, dtype=torch.float32).to(torch.float16)
+    buf = torch.zeros(len(lens), dtype=torch.int32, device=device)
+    metrics = torch.zeros((T * H // 16 + 1, 16), dtype=torch.float32, device=device)
+    slots = torch.randperm(T * H, device=device).view(T, H)
+    ts = []
+    for _ in range(6):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ops.prefill_kv_metrics(q, k, lens, D ** -0.5, buf, n_observed=32, kv_metrics=metrics, slot_mapping=slots,
+                               return_metrics=False)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = sorted(ts[1:])[len(ts[1:]) // 2]
+    flops = 2 * sum(2.0 * 32 * Hq * n * D for n in lens)
+    return {"prompts": lens, "ms": ms, "tflops": flops / (ms * 1e-3) / 1e12,
+            "note": "3 launches: row stats, squared-probability column sums, max-pool + aggregate_prefill"}
 
 
 def main():
@@ -311,6 +354,11 @@ def main():
             line["execute_cache_moves"] = compaction_roofline(device, peak)
         except Exception as ex:  # pragma: no cover
             line["execute_cache_moves"] = {"error": repr(ex)}
+    if not args.no_compaction:
+        try:
+            line["prefill_kv_metrics"] = prefill_metrics_bench(device)
+        except Exception as ex:  # pragma: no cover
+            line["prefill_kv_metrics"] = {"error": repr(ex)}
     if not args.no_cpu_baseline:
         import numpy as np
         from oracle import kvc_oracle as O

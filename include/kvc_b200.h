@@ -305,8 +305,7 @@ KVC_API int kvc_paged_attention_fused_step(
  * evicted_kv_offsets [S,L,H]; evicted_blocks_per_seq, last_position,
  * protected_window_size [S].  Candidate rule and completion logic = K1
  * (csrc/kvcompress_eviction_kernels.cu:136-153); ties by (metric, logical index).
- * No head-bias / use_average / attention-sink terms (reference defaults: zero bias,
- * use_average False, num_sinks 0).
+ * Head-bias / use_average / attention-sink terms: kvc_select_evictions_ex below.
  * ------------------------------------------------------------------------- */
 KVC_API size_t kvc_select_evictions_workspace_bytes(int64_t max_evicted_kv, int block_size);
 
@@ -319,6 +318,24 @@ KVC_API int kvc_select_evictions(
     int num_layers, int num_kv_heads, int max_num_blocks_per_seq, int block_size,
     int64_t max_evicted_kv, int null_eviction_index, void* workspace,
     size_t workspace_bytes, kvc_stream_t stream);
+
+/* kvc_select_evictions with the optional terms of the live selection
+ * (vllm/kvcompress/metrics.py:495-506, 539-544; KVHeadBias :45-81):
+ *   use_average: metric / (last_position[s] - kv_position)            (:495-501)
+ *   head_bias [L, H, num_bins] f32 + position_bins [num_bins] i32 (ascending bin starts):
+ *       metric += head_bias[l, h, bin(kv_position)] * bias_weight      (:503-506)
+ *   num_sinks: slots with kv_position < num_sinks are never evicted   (:542)
+ * head_bias NULL / use_average 0 / num_sinks 0 = kvc_select_evictions. */
+KVC_API int kvc_select_evictions_ex(
+    int* evicted_logical_indices, int* evicted_kv_count, int* evicted_block_count,
+    const float* kv_metrics, const int* kv_position, const int* block_tables,
+    const int* context_lens, const int* hanging_token_count,
+    const int* evicted_kv_offsets, const int* evicted_blocks_per_seq,
+    const int* last_position, const int* protected_window_size, int num_seqs,
+    int num_layers, int num_kv_heads, int max_num_blocks_per_seq, int block_size,
+    int64_t max_evicted_kv, int null_eviction_index, const float* head_bias,
+    const int* position_bins, int num_bins, float bias_weight, int use_average,
+    int num_sinks, void* workspace, size_t workspace_bytes, kvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Additive: block-state device ops around a compression cycle (the reference does these
@@ -344,6 +361,45 @@ KVC_API int kvc_free_and_append_slots(
     const int* hanging_token_count, const int* seq_len, int64_t* slot_mapping,
     int* kv_position, int num_seqs, int num_layers, int num_kv_heads,
     int max_num_blocks_per_seq, int block_size, int append, kvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Additive: prefill KV-metric initialisation on the tensor cores (tcgen05 / TMEM).
+ * replaces _naive_kvc_attention + _naive_kvc_masked_attention
+ *   vllm/attention/backends/flash_attn.py:1122-1211 (call site :993-1007: a second dense
+ *   pass over repeat_kv(key) in torch) and, when kv_metrics/slot_mapping are given,
+ *   CompressionMetrics.aggregate_prefill (vllm/kvcompress/metrics.py:395-427) as well.
+ * For each prompt i (tokens [seq_start_loc[i], seq_start_loc[i+1])): the last
+ * n_obs = min(prompt_len, n_observed) queries attend causally to the prompt's keys;
+ *   metric[k, hq] = sum_q [k <= pos(q) - kv_metric_buffer_len[i]] * softmax_k(scale * q.k)^2
+ * (^2 iff use_l2), * (k+1)/n_obs iff use_average, max-pool(7, pad 3) along k iff use_maxpool.
+ *   kv_metric_out [T, Hq] f32 or NULL
+ *   kv_metrics [NB, B] f32 + slot_mapping [T, H] int64, both or neither:
+ *       kv_metrics[slot_mapping[t,h]] += sum over the kv head's query heads (aggregate_prefill)
+ *   query [T, Hq, D], key [T, H, D] (NOT repeated per query head), token strides in elements
+ *   seq_start_loc [num_seqs+1], kv_metric_buffer_len [num_seqs]; max_prompt_len (host int)
+ * The QK product is rounded to the input type before the fp32 scale exactly as the reference's
+ * fp16/bf16 einsum is (flash_attn.py:1178).  head_size 128, F16/BF16, n_observed <= 128
+ * (single observation chunk: the reference default max_observed_block_size is 4096).
+ * ------------------------------------------------------------------------- */
+KVC_API size_t kvc_prefill_kv_metrics_workspace_bytes(
+    int num_tokens, int num_seqs, int num_heads, int num_kv_heads,
+    int n_observed, int max_prompt_len);
+
+KVC_API int kvc_prefill_kv_metrics(
+    float* kv_metric_out, float* kv_metrics, const int64_t* slot_mapping,
+    const void* query, const void* key, const int* seq_start_loc,
+    const int* kv_metric_buffer_len, int num_tokens, int num_seqs,
+    int num_heads, int num_kv_heads, int head_size, int64_t q_stride,
+    int64_t k_stride, int max_prompt_len, float scale, int n_observed,
+    int use_l2, int use_average, int use_maxpool, int dtype /* kvc_dtype */,
+    void* workspace, size_t workspace_bytes, kvc_stream_t stream);
+
+/* aggregate_prefill alone (vllm/kvcompress/metrics.py:395-427):
+ * kv_metrics[slot_mapping[t,h]] += sum_q prefill_metrics[t, h*Q + q]. */
+KVC_API int kvc_aggregate_prefill(
+    float* kv_metrics, const float* prefill_metrics,
+    const int64_t* slot_mapping, int num_tokens, int num_heads,
+    int num_kv_heads, kvc_stream_t stream);
 
 #ifdef __cplusplus
 } /* extern "C" */

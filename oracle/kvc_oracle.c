@@ -522,3 +522,116 @@ KVC_EXPORT void kvc_oracle_aggregate_decode(float* metrics, const float* temp_me
     metrics[i] += s;
   }
 }
+
+/* ------------------------------------------------------------------------
+ * Prefill KV-metric initialisation
+ * reference: vllm/attention/backends/flash_attn.py:1122-1211
+ *   _naive_kvc_attention (:1122-1164): per prompt, queries = the last
+ *   min(prompt_len, n_observed) tokens, processed in chunks of
+ *   max_observed_block_size; output[start:end] = sum over chunks of the
+ *   chunk's metrics.
+ *   _naive_kvc_masked_attention (:1167-1211): logits = scale *
+ *   float(einsum in the INPUT dtype) (so the dot product is rounded to
+ *   fp16/bf16 first, :1178); causal mask triu(diagonal=q_offset+1) (:1176-1179);
+ *   fp32 softmax over the keys (:1180); squared iff use_l2 (:1181-1182);
+ *   metric mask tril(diagonal=q_offset-kv_metric_buffer_len) (:1184);
+ *   sum over the chunk's queries (:1186); use_average: * (k+1)/n_queries
+ *   (:1187-1195); use_maxpool: max_pool1d(kernel 7, padding 3) (:1196-1202).
+ * and CompressionMetrics.aggregate_prefill, vllm/kvcompress/metrics.py:395-427.
+ * Here the key tensor is [T, H, D] (the reference repeats it to Hq heads
+ * first, flash_attn.py:988-991: query head hq reads kv head hq / Q).
+ * ---------------------------------------------------------------------- */
+static float round_half(float x) { return (float)(_Float16)x; }
+static float round_bf16(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) != 0x7f800000u) u += 0x7fffu + ((u >> 16) & 1u); /* RNE */
+  u &= 0xffff0000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+KVC_EXPORT void kvc_oracle_prefill_kv_metrics(
+    float* kv_metric_out,      /* [T, Hq] */
+    const uint16_t* query,     /* [T, Hq, D] */
+    const uint16_t* key,       /* [T, H, D] */
+    const int* seq_start_loc,  /* [num_seqs + 1] */
+    const int* kv_metric_buffer_len, /* [num_seqs] */
+    int T, int num_seqs, int Hq, int H, int D, float scale, int n_observed,
+    int max_observed_block_size, int use_l2, int use_average, int use_maxpool,
+    int is_bf16) {
+  const int Q = Hq / H;
+  (void)T;
+#pragma omp parallel for collapse(2) schedule(dynamic)
+  for (int i = 0; i < num_seqs; ++i) {
+    for (int hq = 0; hq < Hq; ++hq) {
+      const int start = seq_start_loc[i], end = seq_start_loc[i + 1];
+      const int P = end - start;
+      if (P <= 0) continue;
+      const int h = hq / Q;
+      const int nobs_total = P < n_observed ? P : n_observed;
+      const int start_trunc = end - nobs_total;
+      float* logits = (float*)malloc(sizeof(float) * (size_t)P);
+      float* chunk = (float*)malloc(sizeof(float) * (size_t)P);
+      float* pooled = (float*)malloc(sizeof(float) * (size_t)P);
+      for (int k = 0; k < P; ++k) kv_metric_out[(size_t)(start + k) * Hq + hq] = 0.f;
+      for (int l = start_trunc; l < end; l += max_observed_block_size) {
+        const int lend = l + max_observed_block_size < end ? l + max_observed_block_size : end;
+        const int nq = lend - l;
+        const int q_offset = l - start;
+        for (int k = 0; k < P; ++k) chunk[k] = 0.f;
+        for (int qi = 0; qi < nq; ++qi) {
+          const uint16_t* qv = query + ((size_t)(l + qi) * Hq + hq) * D;
+          float mx = -INFINITY;
+          for (int k = 0; k < P; ++k) {
+            const uint16_t* kv = key + ((size_t)(start + k) * H + h) * D;
+            float acc = 0.f;
+            for (int d = 0; d < D; ++d) acc += to_f32(qv[d], is_bf16) * to_f32(kv[d], is_bf16);
+            float s = scale * (is_bf16 ? round_bf16(acc) : round_half(acc));
+            /* additive mask of finfo(dtype).min: the softmax weight underflows to exactly 0 */
+            if (k - qi >= q_offset + 1) s = -INFINITY;
+            logits[k] = s;
+            if (s > mx) mx = s;
+          }
+          float sum = 0.f;
+          for (int k = 0; k < P; ++k) {
+            logits[k] = expf(logits[k] - mx);
+            sum += logits[k];
+          }
+          for (int k = 0; k < P; ++k) {
+            float pr = logits[k] / sum;
+            if (use_l2) pr = pr * pr;
+            if (k - qi <= q_offset - kv_metric_buffer_len[i]) chunk[k] += pr;
+          }
+        }
+        if (use_average)
+          for (int k = 0; k < P; ++k) chunk[k] *= (float)(k + 1) / (float)nq;
+        for (int k = 0; k < P; ++k) {
+          float v = chunk[k];
+          if (use_maxpool) {
+            const int j0 = k - 3 < 0 ? 0 : k - 3, j1 = k + 3 > P - 1 ? P - 1 : k + 3;
+            for (int j = j0; j <= j1; ++j) v = chunk[j] > v ? chunk[j] : v;
+          }
+          pooled[k] = v;
+        }
+        for (int k = 0; k < P; ++k) kv_metric_out[(size_t)(start + k) * Hq + hq] += pooled[k];
+      }
+      free(logits);
+      free(chunk);
+      free(pooled);
+    }
+  }
+}
+
+/* CompressionMetrics.aggregate_prefill, vllm/kvcompress/metrics.py:395-427 */
+KVC_EXPORT void kvc_oracle_aggregate_prefill(float* metrics, const float* prefill_metrics,
+                                             const int64_t* slot_mapping, int T, int Hq, int H) {
+  const int Q = Hq / H;
+  for (int t = 0; t < T; ++t)
+    for (int h = 0; h < H; ++h) {
+      float s = 0.f;
+      for (int q = 0; q < Q; ++q) s += prefill_metrics[(size_t)t * Hq + h * Q + q];
+      const int64_t slot = slot_mapping[(size_t)t * H + h];
+      if (slot >= 0) metrics[slot] += s;
+    }
+}

@@ -209,3 +209,91 @@ def sort_evictions_by_head(evicted_kv_indices, evicted_logical_indices):
     order2 = np.argsort(evicted_kv_indices[order], kind="stable")
     perm = order[order2]
     return evicted_logical_indices[perm].copy()
+
+
+def prefill_kv_metrics(query, key, seq_lens, scale, kv_metric_buffer_len, n_observed=32,
+                       max_observed_block_size=4096, use_l2=True, use_average=False, use_maxpool=True,
+                       is_bf16=False):
+    """_naive_kvc_attention (vllm/attention/backends/flash_attn.py:1122-1211) with an un-repeated
+    key [T, H, D]; query/key are uint16 bit patterns.  Returns kv_metric_out [T, Hq] f32."""
+    T, Hq, D = query.shape
+    H = key.shape[1]
+    assert query.dtype == np.uint16 and key.dtype == np.uint16
+    starts = np.concatenate([[0], np.cumsum(np.asarray(seq_lens, dtype=np.int64))]).astype(np.int32)
+    assert starts[-1] == T
+    out = np.zeros((T, Hq), np.float32)
+    lib().kvc_oracle_prefill_kv_metrics(
+        _p(out), _p(np.ascontiguousarray(query)), _p(np.ascontiguousarray(key)), _p(starts),
+        _p(_i32(kv_metric_buffer_len)), ctypes.c_int(T), ctypes.c_int(len(seq_lens)), ctypes.c_int(Hq),
+        ctypes.c_int(H), ctypes.c_int(D), ctypes.c_float(scale), ctypes.c_int(n_observed),
+        ctypes.c_int(max_observed_block_size), ctypes.c_int(int(use_l2)), ctypes.c_int(int(use_average)),
+        ctypes.c_int(int(use_maxpool)), ctypes.c_int(int(is_bf16)))
+    return out
+
+
+def aggregate_prefill(metrics, prefill_metrics, slot_mapping):
+    """CompressionMetrics.aggregate_prefill (vllm/kvcompress/metrics.py:395-427), in place on
+    `metrics` (any shape, indexed flat by slot)."""
+    T, Hq = prefill_metrics.shape
+    H = slot_mapping.shape[1]
+    assert metrics.dtype == np.float32 and prefill_metrics.dtype == np.float32
+    sm = np.ascontiguousarray(slot_mapping, dtype=np.int64)
+    lib().kvc_oracle_aggregate_prefill(_p(metrics), _p(np.ascontiguousarray(prefill_metrics)), _p(sm),
+                                       ctypes.c_int(T), ctypes.c_int(Hq), ctypes.c_int(H))
+
+
+def select_evictions(kv_metrics, kv_position, block_tables, context_lens, hanging_token_count,
+                     evicted_kv_offsets, evicted_blocks_per_seq, last_position, protected_window_size,
+                     block_size, null_eviction_index, head_bias=None, position_bins=None, bias_weight=0.0,
+                     use_average=False, num_sinks=0):
+    """CompressionMetrics.schedule_evictions (vllm/kvcompress/metrics.py:441-847) restated per head in
+    numpy (small cases): key = metric [/ (last_position - position), :495-501] [+ bias[l, h,
+    bin(position)] * weight, :503-506]; candidates = logical index < ctx, position <= last_position -
+    protected and position >= num_sinks (:539-544); a head's block k completes at its sorted rank
+    hanging-1 + k*B (:583-596); per sequence the `budget` smallest completion keys are granted
+    (:671-729, ties by (key, head, block)); a head with k granted blocks evicts its (k-1)*B + hanging
+    lowest keys (:774-792), listed ascending by logical index with `null` after them (:822-834).
+    Returns (evicted_logical_indices [N], evicted_kv_count [S,L,H], evicted_block_count [S,L,H])."""
+    B = block_size
+    L, S, H = context_lens.shape
+    nblk = (context_lens + B - 1) // B
+    N = int(nblk.sum()) * B
+    logical = np.full(N, null_eviction_index, np.int32)
+    kv_count = np.zeros((S, L, H), np.int32)
+    blk_count = np.zeros((S, L, H), np.int32)
+    m_flat, p_flat = kv_metrics.reshape(-1).astype(np.float32), kv_position.reshape(-1)
+    for s in range(S):
+        heads, events = [], []
+        for l in range(L):
+            for h in range(H):
+                n = int(context_lens[l, s, h])
+                idx = np.arange(n)
+                slots = block_tables[l, s, h, idx // B].astype(np.int64) * B + idx % B
+                pos = p_flat[slots]
+                key = m_flat[slots].copy()
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    if use_average:
+                        key = key / (int(last_position[s]) - pos).astype(np.float32)
+                    if head_bias is not None:
+                        bins = (pos[:, None] >= np.asarray(position_bins)[None]).sum(-1) - 1
+                        b = np.where(pos >= 0, head_bias[l, h, bins], 0).astype(np.float32)
+                        key = key + b * np.float32(bias_weight)
+                cand = (pos <= int(last_position[s]) - int(protected_window_size[s])) & (pos >= num_sinks)
+                ci = idx[cand]
+                order = ci[np.lexsort((ci, key[cand]))]          # by (key, logical index)
+                r0 = int(hanging_token_count[s, l, h])
+                nev = (len(order) - r0) // B + 1 if len(order) >= r0 >= 1 else 0
+                for k in range(nev):
+                    events.append((key[order[r0 - 1 + k * B]], len(heads), k))
+                heads.append((l, h, order, r0))
+        events.sort()
+        granted = np.zeros(len(heads), np.int64)
+        for _, hd, _k in events[: int(evicted_blocks_per_seq[s])]:
+            granted[hd] += 1
+        for hd, (l, h, order, r0) in enumerate(heads):
+            k = int(granted[hd])
+            cnt = (k - 1) * B + r0 if k > 0 else 0
+            kv_count[s, l, h], blk_count[s, l, h] = cnt, k
+            off = int(evicted_kv_offsets[s, l, h])
+            logical[off: off + cnt] = np.sort(order[:cnt])
+    return logical, kv_count, blk_count

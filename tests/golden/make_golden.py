@@ -402,6 +402,173 @@ def gen_cache_write():
     return cases
 
 
+def _load_reference_functions(path: str, names, class_name: Optional[str] = None, extra_ns=None):
+    """Compile some functions (or methods of one class) of a reference file by AST, decorators
+    stripped, without importing the file."""
+    tree = ast.parse(open(path).read())
+    body = tree.body
+    if class_name is not None:
+        body = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name][0].body
+    fns = [n for n in body if isinstance(n, ast.FunctionDef) and n.name in names]
+    for fn in fns:
+        fn.decorator_list = []
+    from typing import List, Tuple, Dict
+    ns = {"torch": torch, "F": torch.nn.functional, "Optional": Optional, "List": List, "Tuple": Tuple,
+          "Dict": Dict}
+    ns.update(extra_ns or {})
+    exec(compile(ast.Module(body=fns, type_ignores=[]), path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def gen_prefill_metrics():
+    """Prefill metric initialisation golden: the reference's _naive_kvc_attention
+    (vllm/attention/backends/flash_attn.py:1122-1211) executed on CPU tensors exactly as the
+    backend calls it (:988-1007: key repeated to the query heads first), then
+    CompressionMetrics.aggregate_prefill (vllm/kvcompress/metrics.py:395-427) on a stub object."""
+    naive, _masked = _load_reference_functions(
+        os.path.join(REF, "vllm", "attention", "backends", "flash_attn.py"),
+        ["_naive_kvc_attention", "_naive_kvc_masked_attention"])
+    (aggregate_prefill,) = _load_reference_functions(
+        os.path.join(REF, "vllm", "kvcompress", "metrics.py"), ["aggregate_prefill"],
+        class_name="CompressionMetrics")
+    cases = {}
+    g = torch.Generator().manual_seed(11)
+    rng = np.random.RandomState(11)
+    cfgs = [
+        # prompt lens, Hq, H, dtype, n_observed, buffer lens, use_l2, use_average, use_maxpool
+        ([70, 300], 4, 1, torch.float16, 32, [0, 10], True, False, True),
+        ([20, 1, 129, 33], 16, 2, torch.float16, 32, [0, 0, 5, 40], True, False, True),   # Q=8: two row tiles
+        ([150, 64], 8, 2, torch.bfloat16, 32, [3, 0], True, True, False),
+        ([200, 50], 2, 2, torch.float16, 64, [0, 7], True, False, True),                  # MHA, 64 observed
+        ([260], 4, 2, torch.float16, 100, [16], False, False, True),                      # 100 observed, no l2
+        ([600, 140], 4, 1, torch.float16, 32, [0, 0], True, False, True),                 # several key splits
+    ]
+    for k, (lens, Hq, H, dtype, n_obs, buf, use_l2, use_avg, use_pool) in enumerate(cfgs):
+        T, D, Q = sum(lens), 128, Hq // H
+        scale = float(D ** -0.5)
+        q = torch.randn((T, Hq, D), generator=g)
+        key = torch.randn((T, H, D), generator=g)
+        if k != len(cfgs) - 1:
+            # values on a 1/8 grid: every dot product is exact in fp32 whatever the summation order, so
+            # the fp16/bf16 rounding of the logits is reproducible bit for bit (and the file compresses)
+            q, key = (q * 8).round() / 8, (key * 8).round() / 8
+        q, key = q.to(dtype), key.to(dtype)
+        key_rep = key[:, :, None, :].expand(T, H, Q, D).reshape(T, Hq, D)   # repeat_kv, flash_attn.py:988-991
+        buf_t = torch.tensor(buf, dtype=torch.int32)
+        _, out = naive(q, key_rep, key_rep, lens, scale, buf_t, n_observed=n_obs,
+                       max_observed_block_size=4096, use_l2=use_l2, use_average=use_avg, use_maxpool=use_pool)
+        B = 16
+        NB = (T * H + B - 1) // B + 3
+        slots = torch.tensor(rng.choice(NB * B, T * H, replace=False).astype(np.int64).reshape(T, H))
+        metrics0 = torch.rand((NB, B), generator=g)
+        stub = types.SimpleNamespace(random=False, num_kv_heads=H, metrics=metrics0.clone())
+        aggregate_prefill(stub, out, slots)
+        view16 = lambda t: t.view(torch.int16).numpy().view(np.uint16)
+        cases[f"prefill{k}"] = dict(seq_lens=np.array(lens, np.int32), Hq=Hq, H=H, D=D,
+                                    is_bf16=int(dtype == torch.bfloat16), scale=np.float32(scale),
+                                    n_observed=n_obs, kv_metric_buffer_len=np.array(buf, np.int32),
+                                    use_l2=int(use_l2), use_average=int(use_avg), use_maxpool=int(use_pool),
+                                    query=view16(q), key=view16(key), slot_mapping=slots.numpy(),
+                                    kv_metrics_in=metrics0.numpy(), out_kv_metric=out.numpy(),
+                                    out_kv_metrics=stub.metrics.numpy())
+    return cases
+
+
+def gen_selection_v2():
+    """Live selection golden: CompressionMetrics.schedule_evictions (vllm/kvcompress/metrics.py:441-847,
+    the "V2" path the engine runs, scheduler.py:488-500) executed on CPU tensors with a stub `self`,
+    incl. KVHeadBias (:45-81), use_average (:495-501) and attention sinks (:542).
+    count_block_evictions (a CUDA op in the reference, :774) is supplied by the C oracle, itself pinned
+    against ref_count_block_evictions in count_blocks.npz.
+    Single-sequence calls only: for batches the reference counts +inf block metrics from offset 0
+    instead of the sequence's own offset (`[:unevicted_offset]`, :718), which silently shrinks the
+    budget of every sequence but the first; we follow K1 (the author's acceptance oracle, :690-697)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle import kvc_oracle as O
+    from vllm_kvcompress_b200 import workload as W
+
+    def count_block_evictions(evicted_block_count, evicted_logical_indices, evicted_kv_offsets,
+                              hanging_token_count, block_size, null_value, evicted_blocks_per_seq=None):
+        cnt = np.zeros(tuple(evicted_block_count.shape), np.int32)
+        logical = evicted_logical_indices.numpy()          # shares memory: in-place like the CUDA op
+        assert logical.dtype == np.int32 and logical.flags["C_CONTIGUOUS"]
+        O.count_block_evictions(cnt, logical, evicted_kv_offsets.numpy(), hanging_token_count.numpy(),
+                                block_size, null_value)
+        evicted_block_count.copy_(torch.from_numpy(cnt))
+
+    class _Ckpt:
+        def checkpoint(self, *a, **k):
+            pass
+
+    class _Bench:
+        def start_range(self, *a, **k):
+            pass
+        end_range = start_range
+
+    (KVHeadBias,) = [None]
+    tree = ast.parse(open(os.path.join(REF, "vllm", "kvcompress", "metrics.py")).read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "KVHeadBias"][0]
+    from dataclasses import dataclass
+    ns = {"torch": torch, "dataclass": dataclass}
+    exec(compile(ast.Module(body=[cls], type_ignores=[]), "metrics.py", "exec"), ns)
+    KVHeadBias = ns["KVHeadBias"]
+    (schedule_evictions,) = _load_reference_functions(
+        os.path.join(REF, "vllm", "kvcompress", "metrics.py"), ["schedule_evictions"],
+        class_name="CompressionMetrics",
+        extra_ns={"count_block_evictions": count_block_evictions, "MAX_INT": MAX_INT,
+                  "CHECKPOINTER": _Ckpt(), "BENCHMARKER": _Bench(), "np": np})
+
+    cases = {}
+    cfgs = [
+        # seed, L, H, B, max_blocks, protected, budget fraction, bins, bias weight, use_average, sinks
+        (201, 2, 4, 16, 12, 32, 0.5, None, 0.0, False, 0),
+        (202, 4, 8, 16, 20, 16, 0.7, [0, 40, 150], 0.5, False, 0),
+        (203, 2, 2, 16, 30, 32, 0.6, None, 0.0, True, 0),
+        (204, 3, 4, 16, 9, 8, 0.8, [0, 64], 2.0, True, 4),
+        (205, 2, 2, 16, 45, 32, 0.9, None, 0.0, False, 7),      # > 512 slots per head
+        (206, 2, 4, 4, 10, 3, 0.5, [0, 5, 9, 30], 1.0, False, 2),
+    ]
+    for seed, L, H, B, max_blocks, prot, frac, bins, weight, use_avg, sinks in cfgs:
+        g = torch.Generator().manual_seed(seed)
+        S = 1
+        ctx = torch.randint(1, max_blocks * B + 1, (L, S, H), generator=g, dtype=torch.int32)
+        st = W.make_state(S, L, H, B, 16, ctx, dtype=torch.float16, device="cpu", seed=seed, fill_cache=False)
+        pos = torch.full((st.NB * B,), -1, dtype=torch.int32)
+        for l in range(L):
+            for h in range(H):
+                n = int(ctx[l, 0, h])
+                slots = st.block_tables[l, 0, h, torch.arange(n) // B].long() * B + torch.arange(n) % B
+                pos[slots] = torch.randperm(2 * n, generator=g)[:n].to(torch.int32)
+        st.kv_position = pos.view(st.NB, B)
+        last = int(2 * ctx.max())
+        nblk = (ctx + B - 1) // B
+        budget = int(float(nblk.sum()) * frac)
+        hanging = W.hanging_token_counts(ctx, B).transpose(0, 1).contiguous()
+        offs = W.evicted_kv_offsets(ctx, B)
+        nbins = 1 if bins is None else len(bins)
+        bias = torch.rand((L, H, nbins), generator=g) if bins is not None else torch.zeros((L, H, 1))
+        hb = KVHeadBias(bias.clone(), torch.tensor(bins if bins is not None else [0], dtype=torch.int32))
+        # blocks of a head beyond ceil(ctx/B) do not exist here (exact allocation), like the engine
+        stub = types.SimpleNamespace(
+            seq_index_by_block=st.seq_by_block, layer_index_by_block=st.layer_by_block,
+            head_index_by_block=st.head_by_block, logical_block_num_by_block=st.logical_by_block,
+            token_positions=st.kv_position, metrics=st.kv_metrics.clone(), block_size=B, num_layers=L,
+            num_kv_heads=H, device="cpu", use_average=use_avg, kv_metric_head_bias=hb,
+            kv_metric_bias_weight=weight, num_sinks=sinks)
+        logical, kv_count, blk_count = quiet(schedule_evictions, stub, [0], [last], [budget], ctx, hanging, offs,
+                                             [prot])
+        cases[f"sel{seed}"] = dict(
+            L=L, H=H, B=B, last_position=last, protected=prot, budget=budget, use_average=int(use_avg),
+            num_sinks=sinks, bias_weight=np.float32(weight), has_bias=int(bins is not None),
+            head_bias=bias.numpy(), position_bins=hb.position_bins.numpy(),
+            context_lens=ctx.numpy(), block_tables=st.block_tables.numpy(), kv_metrics=st.kv_metrics.numpy(),
+            kv_position=st.kv_position.numpy(), hanging_token_count=hanging.numpy(),
+            evicted_kv_offsets=offs.numpy(), out_evicted_logical_indices=logical.numpy().astype(np.int32),
+            out_evicted_kv_count=kv_count.numpy().astype(np.int32),
+            out_evicted_block_count=blk_count.numpy().astype(np.int32))
+    return cases
+
+
 def save(name, cases):
     flat = {}
     for cname, d in cases.items():
@@ -413,12 +580,25 @@ def save(name, cases):
 
 
 def main():
-    ops = _load_reference_custom_ops()
-    save("evictions.npz", gen_evictions(ops))
-    save("count_blocks.npz", gen_count_blocks(ops))
-    save("moves.npz", gen_moves(ops))
-    save("attention.npz", gen_attention())
-    save("cache_write.npz", gen_cache_write())
+    """python tests/golden/make_golden.py [name ...] -- regenerate all, or only the named files
+    (evictions count_blocks moves attention cache_write selection_v2 prefill_metrics)."""
+    want = set(sys.argv[1:])
+    on = lambda n: not want or n in want
+    ops = _load_reference_custom_ops() if (not want or want & {"evictions", "count_blocks", "moves"}) else None
+    if on("evictions"):
+        save("evictions.npz", gen_evictions(ops))
+    if on("count_blocks"):
+        save("count_blocks.npz", gen_count_blocks(ops))
+    if on("moves"):
+        save("moves.npz", gen_moves(ops))
+    if on("attention"):
+        save("attention.npz", gen_attention())
+    if on("cache_write"):
+        save("cache_write.npz", gen_cache_write())
+    if on("selection_v2"):
+        save("selection_v2.npz", gen_selection_v2())
+    if on("prefill_metrics"):
+        save("prefill_metrics.npz", gen_prefill_metrics())
 
 
 if __name__ == "__main__":

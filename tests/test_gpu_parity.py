@@ -552,7 +552,8 @@ def selection_case(seed, S, L, H, B, max_blocks, prot, frac):
     (71, 3, 2, 2, 4, 5, 3, 0.5),
     (72, 4, 4, 8, 16, 10, 16, 0.4),      # <= 256 slots per head: warp-per-head path
     (77, 3, 4, 8, 16, 28, 32, 0.6),      # 257..512 slots per head: warp path with 16 keys per lane
-    (73, 2, 4, 8, 16, 40, 32, 0.7),      # > 512 slots per head: CTA-per-head path
+    (73, 2, 4, 8, 16, 40, 32, 0.7),      # > 512 slots per head: CTA-per-head sort path
+    (78, 2, 1, 3, 16, 380, 32, 0.95),    # post-prefill-like: ~6000 slots per head, CR ~ 20
     (74, 3, 3, 4, 16, 9, 0, 2.0),        # budget larger than what exists
     (75, 2, 2, 2, 1, 100, 7, 0.5),
     (76, 2, 32, 8, 16, 9, 32, 0.12),     # Llama-3-8B head count, steady-state-like budget
@@ -586,6 +587,64 @@ def test_select_evictions_equals_reference_chain(capi, O, cfg):
                           last.cuda(), protected.cuda(), B, MAX_INT)
     np.testing.assert_array_equal(out_cnt.cpu().numpy(), cnt)
     np.testing.assert_array_equal(out_blk.cpu().numpy(), want_blocks)
+    np.testing.assert_array_equal(out_logical.cpu().numpy(), want_logical)
+
+
+SELV2 = load_cases("selection_v2.npz")
+
+
+@pytest.mark.parametrize("name", sorted(SELV2))
+def test_select_evictions_v2_golden(capi, name):
+    """bit-exact against CompressionMetrics.schedule_evictions (metrics.py:441-847) run on CPU,
+    incl. head bias, use_average and attention sinks."""
+    c = SELV2[name]
+    one = lambda v: torch.tensor([int(v)], dtype=torch.int32, device="cuda")
+    N = c["out_evicted_logical_indices"].shape[0]
+    out_logical = torch.full((N,), -5, dtype=torch.int32, device="cuda")
+    out_cnt = torch.full(c["out_evicted_kv_count"].shape, -5, dtype=torch.int32, device="cuda")
+    out_blk = torch.full_like(out_cnt, -5)
+    has_bias = bool(int(c["has_bias"]))
+    capi.select_evictions(out_logical, out_cnt, out_blk, cu(c["kv_metrics"]), cu(c["kv_position"]),
+                          cu(c["block_tables"]), cu(c["context_lens"]), cu(c["hanging_token_count"]),
+                          cu(c["evicted_kv_offsets"]), one(c["budget"]), one(c["last_position"]), one(c["protected"]),
+                          int(c["B"]), MAX_INT, cu(c["head_bias"]) if has_bias else None,
+                          cu(c["position_bins"]) if has_bias else None, float(c["bias_weight"]),
+                          bool(c["use_average"]), int(c["num_sinks"]))
+    np.testing.assert_array_equal(out_cnt.cpu().numpy(), c["out_evicted_kv_count"])
+    np.testing.assert_array_equal(out_blk.cpu().numpy(), c["out_evicted_block_count"])
+    np.testing.assert_array_equal(out_logical.cpu().numpy(), c["out_evicted_logical_indices"])
+
+
+@pytest.mark.parametrize("cfg", [
+    # seed, S, L, H, B, max_blocks, prot, frac, bins, weight, use_average, sinks
+    (91, 3, 4, 8, 16, 10, 16, 0.5, [0, 50, 120], 0.7, False, 3),     # warp path, 8 keys per lane
+    (92, 2, 4, 8, 16, 28, 32, 0.6, None, 0.0, True, 0),             # warp path, 16 keys per lane
+    (93, 2, 2, 4, 16, 70, 32, 0.7, [0, 300], 1.5, True, 5),         # CTA sort path
+    (94, 2, 1, 2, 16, 400, 32, 0.9, None, 0.0, False, 0),           # CTA sort path, 6400 slots per head
+])
+def test_select_evictions_options_vs_oracle(capi, O, cfg):
+    from vllm_kvcompress_b200 import workload as W
+    seed, S, L, H, B, max_blocks, prot, frac, bins, weight, use_avg, sinks = cfg
+    st, ctx, last, protected, budgets = selection_case(seed, S, L, H, B, max_blocks, prot, frac)
+    hanging = W.hanging_token_counts(ctx, B).transpose(0, 1).contiguous()
+    offs = W.evicted_kv_offsets(ctx, B)
+    g = torch.Generator().manual_seed(seed)
+    bias = torch.rand((L, H, len(bins)), generator=g) if bins is not None else None
+    pbins = torch.tensor(bins, dtype=torch.int32) if bins is not None else None
+    n = lambda t: None if t is None else t.numpy()
+    want_logical, want_cnt, want_blk = O.select_evictions(
+        n(st.kv_metrics), n(st.kv_position), n(st.block_tables), n(ctx), n(hanging), n(offs), n(budgets), n(last),
+        n(protected), B, MAX_INT, n(bias), n(pbins), weight, use_avg, sinks)
+    N = want_logical.shape[0]
+    out_logical = torch.full((N,), -5, dtype=torch.int32, device="cuda")
+    out_cnt = torch.full((S, L, H), -5, dtype=torch.int32, device="cuda")
+    out_blk = torch.full((S, L, H), -5, dtype=torch.int32, device="cuda")
+    dev = lambda t: None if t is None else t.cuda()
+    capi.select_evictions(out_logical, out_cnt, out_blk, st.kv_metrics.cuda(), st.kv_position.cuda(),
+                          st.block_tables.cuda(), ctx.cuda(), hanging.cuda(), offs.cuda(), budgets.cuda(),
+                          last.cuda(), protected.cuda(), B, MAX_INT, dev(bias), dev(pbins), weight, use_avg, sinks)
+    np.testing.assert_array_equal(out_cnt.cpu().numpy(), want_cnt)
+    np.testing.assert_array_equal(out_blk.cpu().numpy(), want_blk)
     np.testing.assert_array_equal(out_logical.cpu().numpy(), want_logical)
 
 

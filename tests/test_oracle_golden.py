@@ -193,3 +193,63 @@ def test_aggregate_decode():
     want = metrics + (temp ** 2).sum(-1)
     O.aggregate_decode(metrics, temp)
     np.testing.assert_allclose(metrics, want, rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------
+# prefill metric initialisation (_naive_kvc_attention + aggregate_prefill)
+# ---------------------------------------------------------------------------
+PREFILL = load_cases("prefill_metrics.npz")
+
+
+def oracle_prefill(c):
+    return O.prefill_kv_metrics(c["query"], c["key"], c["seq_lens"].tolist(), float(c["scale"]),
+                                c["kv_metric_buffer_len"], int(c["n_observed"]), 4096, bool(c["use_l2"]),
+                                bool(c["use_average"]), bool(c["use_maxpool"]), bool(c["is_bf16"]))
+
+
+@pytest.mark.parametrize("name", sorted(PREFILL))
+def test_prefill_kv_metrics_matches_reference_python(name):
+    """fp32 softmax of fp16/bf16-rounded logits: tolerance rtol 1e-5 / atol 1e-6 against
+    _naive_kvc_attention run on CPU tensors (summation order is the only difference)."""
+    c = PREFILL[name]
+    out = oracle_prefill(c)
+    np.testing.assert_allclose(out, c["out_kv_metric"], rtol=1e-5, atol=1e-6)
+    m = c["kv_metrics_in"].copy()
+    O.aggregate_prefill(m, c["out_kv_metric"], c["slot_mapping"])
+    np.testing.assert_allclose(m, c["out_kv_metrics"], rtol=1e-6, atol=1e-7)
+
+
+def test_prefill_observation_chunks_sum():
+    """max_observed_block_size splits the observed queries into chunks whose (separately pooled)
+    metrics add up (flash_attn.py:1146-1160): without max-pool the split is invisible."""
+    c = PREFILL["prefill0"]
+    args = (c["query"], c["key"], c["seq_lens"].tolist(), float(c["scale"]), c["kv_metric_buffer_len"], 32)
+    one = O.prefill_kv_metrics(*args, 4096, True, False, False, False)
+    two = O.prefill_kv_metrics(*args, 8, True, False, False, False)
+    np.testing.assert_allclose(one, two, rtol=1e-5, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------
+# live ("V2") selection incl. head bias / use_average / attention sinks
+# ---------------------------------------------------------------------------
+SELV2 = load_cases("selection_v2.npz")
+
+
+def oracle_select_v2(c):
+    one = lambda v: np.array([int(v)], np.int32)
+    return O.select_evictions(
+        c["kv_metrics"], c["kv_position"], c["block_tables"], c["context_lens"], c["hanging_token_count"],
+        c["evicted_kv_offsets"], one(c["budget"]), one(c["last_position"]), one(c["protected"]), int(c["B"]),
+        MAX_INT, c["head_bias"] if int(c["has_bias"]) else None, c["position_bins"], float(c["bias_weight"]),
+        bool(c["use_average"]), int(c["num_sinks"]))
+
+
+@pytest.mark.parametrize("name", sorted(SELV2))
+def test_select_evictions_matches_reference_schedule_evictions(name):
+    """bit-exact against CompressionMetrics.schedule_evictions run on CPU tensors."""
+    c = SELV2[name]
+    logical, kv_count, blk_count = oracle_select_v2(c)
+    np.testing.assert_array_equal(kv_count, c["out_evicted_kv_count"])
+    np.testing.assert_array_equal(blk_count, c["out_evicted_block_count"])
+    np.testing.assert_array_equal(logical, c["out_evicted_logical_indices"])
+    assert int(blk_count.sum()) == min(int(c["budget"]), int(blk_count.sum()))

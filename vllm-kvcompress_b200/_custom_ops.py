@@ -148,17 +148,23 @@ SELECT_EVICTIONS_LAUNCHES = 3  # rank, threshold, emit
 def select_evictions(out_evicted_logical_indices, out_evicted_kv_count, out_evicted_block_count,
                      kv_metrics, kv_position, block_tables, context_lens, hanging_token_count,
                      evicted_kv_offsets, evicted_blocks_per_seq, last_position, protected_window_size,
-                     block_size: int, null_eviction_index: int) -> None:
+                     block_size: int, null_eviction_index: int,
+                     head_bias: Optional[torch.Tensor] = None, position_bins: Optional[torch.Tensor] = None,
+                     bias_weight: float = 0.0, use_average: bool = False, num_sinks: int = 0) -> None:
     """ADDITIVE op: fused replacement of CompressionMetrics.schedule_evictions
     (vllm/kvcompress/metrics.py:441-847) / the sort_seq_metrics -> schedule_cache_evictions ->
     re-sort chain (metrics.py:849-966, scheduler.py:285-486).  Same outputs as
-    schedule_evictions returns: (evicted_logical_indices, evicted_kv_count, evicted_block_count)."""
+    schedule_evictions returns: (evicted_logical_indices, evicted_kv_count, evicted_block_count).
+    head_bias [L, H, bins] / position_bins [bins] / bias_weight = KVHeadBias and
+    kv_metric_bias_weight (metrics.py:45-81, 503-506); use_average (:495-501); num_sinks (:542)."""
     torch.ops._C_kvc_ops.select_evictions(
         out_evicted_logical_indices, out_evicted_kv_count, out_evicted_block_count, kv_metrics,
         kv_position.contiguous(), block_tables.contiguous(), context_lens.contiguous(),
         hanging_token_count.contiguous(), evicted_kv_offsets.contiguous(),
         evicted_blocks_per_seq.contiguous(), last_position.type(torch.int), protected_window_size,
-        block_size, null_eviction_index)
+        block_size, null_eviction_index, head_bias,
+        None if position_bins is None else position_bins.type(torch.int).contiguous(), bias_weight,
+        use_average, num_sinks)
 
 
 def prepare_compression(context_lens, out_hanging_token_count, out_evicted_kv_offsets,
@@ -190,3 +196,33 @@ def paged_attention_kvc_fused_step(out, kv_metrics, query, key, value, key_cache
         out, kv_metrics, query, key, value, key_cache, value_cache, slot_mapping, kv_metric_head_bias,
         num_kv_heads, scale, block_tables, context_lens, kv_position, last_position, kv_metric_buffer_len,
         block_size, max_context_len, alibi_slopes, kv_cache_dtype)
+
+
+def prefill_kv_metrics(query, key, seq_lens, scale: float, kv_metric_buffer_len, n_observed: int = 32,
+                       use_l2: bool = True, use_average: bool = False, use_maxpool: bool = True,
+                       kv_metrics: Optional[torch.Tensor] = None,
+                       slot_mapping: Optional[torch.Tensor] = None,
+                       return_metrics: bool = True) -> Optional[torch.Tensor]:
+    """ADDITIVE op: tensor-core (tcgen05) replacement of _naive_kvc_attention
+    (vllm/attention/backends/flash_attn.py:1122-1211; same argument meaning, `seq_lens` is the
+    Python list prefill_meta.seq_lens, `key` is the un-repeated [T, num_kv_heads, D] tensor).
+    Returns kv_metric_out [T, num_heads] f32 like the reference; when kv_metrics / slot_mapping
+    are given, CompressionMetrics.aggregate_prefill (metrics.py:395-427) is fused in."""
+    starts = [0]
+    for n in seq_lens:
+        starts.append(starts[-1] + int(n))
+    assert starts[-1] == query.shape[0], "seq_lens must cover the prefill tokens"
+    seq_start_loc = torch.tensor(starts, dtype=torch.int32, device=query.device)
+    out = (torch.empty((query.shape[0], query.shape[1]), dtype=torch.float32, device=query.device)
+           if return_metrics else None)
+    torch.ops._C_kvc_ops.prefill_kv_metrics(
+        out, kv_metrics, None if slot_mapping is None else slot_mapping.contiguous(), query, key,
+        seq_start_loc, kv_metric_buffer_len.type(torch.int).contiguous(), max(seq_lens) if seq_lens else 0,
+        scale, n_observed, use_l2, use_average, use_maxpool)
+    return out
+
+
+def aggregate_prefill(kv_metrics, prefill_metrics, slot_mapping) -> None:
+    """ADDITIVE op: CompressionMetrics.aggregate_prefill (vllm/kvcompress/metrics.py:395-427) as one
+    launch: kv_metrics[slot_mapping[t, h]] += prefill_metrics[t, h*Q:(h+1)*Q].sum()."""
+    torch.ops._C_kvc_ops.aggregate_prefill(kv_metrics, prefill_metrics.contiguous(), slot_mapping.contiguous())

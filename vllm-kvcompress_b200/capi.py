@@ -183,7 +183,8 @@ def paged_attention_fused_metrics(out, kv_metrics, query, key_cache, value_cache
 def select_evictions(evicted_logical_indices, evicted_kv_count, evicted_block_count, kv_metrics,
                      kv_position, block_tables, context_lens, hanging_token_count, evicted_kv_offsets,
                      evicted_blocks_per_seq, last_position, protected_window_size, block_size,
-                     null_eviction_index):
+                     null_eviction_index, head_bias=None, position_bins=None, bias_weight=0.0,
+                     use_average=False, num_sinks=0):
     lib = native.load_lib()
     lib.kvc_select_evictions_workspace_bytes.restype = ctypes.c_size_t
     S, L, H = evicted_kv_count.shape
@@ -195,8 +196,46 @@ def select_evictions(evicted_logical_indices, evicted_kv_count, evicted_block_co
             evicted_blocks_per_seq, last_position, protected_window_size]
     for i, t in enumerate(ints):
         _i32(t, f"arg{i}")
-    _check(lib.kvc_select_evictions(
+    if head_bias is not None:
+        assert head_bias.dtype == torch.float32 and head_bias.is_contiguous() and head_bias.shape[:2] == (L, H)
+        _i32(position_bins, "position_bins")
+    _check(lib.kvc_select_evictions_ex(
         _ptr(_i32(evicted_logical_indices, "evicted_logical_indices")),
         _ptr(_i32(evicted_kv_count, "evicted_kv_count")), _ptr(_i32(evicted_block_count, "evicted_block_count")),
         _ptr(kv_metrics), *[_ptr(t) for t in ints], S, L, H, block_tables.shape[3], block_size,
-        ctypes.c_int64(max_kv), null_eviction_index, _ptr(ws), ctypes.c_size_t(ws.numel()), _stream()))
+        ctypes.c_int64(max_kv), null_eviction_index, _ptr(head_bias), _ptr(position_bins),
+        0 if head_bias is None else head_bias.shape[2], ctypes.c_float(bias_weight), int(use_average),
+        int(num_sinks), _ptr(ws), ctypes.c_size_t(ws.numel()), _stream()))
+
+
+def prefill_kv_metrics(kv_metric_out, kv_metrics, slot_mapping, query, key, seq_start_loc,
+                       kv_metric_buffer_len, max_prompt_len, scale, n_observed=32, use_l2=True,
+                       use_average=False, use_maxpool=True):
+    lib = native.load_lib()
+    lib.kvc_prefill_kv_metrics_workspace_bytes.restype = ctypes.c_size_t
+    T, Hq, D = query.shape
+    H = key.shape[1]
+    num_seqs = seq_start_loc.numel() - 1
+    nbytes = lib.kvc_prefill_kv_metrics_workspace_bytes(T, num_seqs, Hq, H, n_observed, max_prompt_len)
+    ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=query.device)
+    assert query.stride(-1) == 1 and query.stride(1) == D and key.stride(-1) == 1 and key.stride(1) == D
+    for t in (kv_metric_out, kv_metrics):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    assert slot_mapping is None or (slot_mapping.dtype == torch.int64 and slot_mapping.is_contiguous())
+    _check(lib.kvc_prefill_kv_metrics(
+        _ptr(kv_metric_out), _ptr(kv_metrics), _ptr(slot_mapping), _ptr(query), _ptr(key),
+        _ptr(_i32(seq_start_loc, "seq_start_loc")), _ptr(_i32(kv_metric_buffer_len, "kv_metric_buffer_len")),
+        T, num_seqs, Hq, H, D, ctypes.c_int64(query.stride(0)), ctypes.c_int64(key.stride(0)),
+        int(max_prompt_len), ctypes.c_float(scale), int(n_observed), int(use_l2), int(use_average),
+        int(use_maxpool), _DT[query.dtype], _ptr(ws), ctypes.c_size_t(ws.numel()), _stream()))
+
+
+def aggregate_prefill(kv_metrics, prefill_metrics, slot_mapping):
+    lib = native.load_lib()
+    T, Hq = prefill_metrics.shape
+    H = slot_mapping.shape[1]
+    assert kv_metrics.dtype == torch.float32 and kv_metrics.is_contiguous()
+    assert prefill_metrics.dtype == torch.float32 and prefill_metrics.is_contiguous()
+    assert slot_mapping.dtype == torch.int64 and slot_mapping.is_contiguous()
+    _check(lib.kvc_aggregate_prefill(_ptr(kv_metrics), _ptr(prefill_metrics), _ptr(slot_mapping), T, Hq, H,
+                                     _stream()))

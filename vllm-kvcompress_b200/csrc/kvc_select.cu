@@ -58,13 +58,39 @@ struct SelectParams {
   const int* protected_window;  // [S]
   int S, L, H, MB, B, null_index;
   unsigned* events;  // [total slots / B] workspace
+  // optional terms of the live selection (metrics.py:495-506, 539-544); all off by default
+  const float* head_bias;     // [L, H, num_bins] or null (KVHeadBias.bias, metrics.py:45-81)
+  const int* position_bins;   // [num_bins] ascending bin starts
+  int num_bins;
+  float bias_weight;          // kv_metric_bias_weight
+  int use_average;            // metric / (last_position - token_position)
+  int num_sinks;              // positions < num_sinks are never evicted
 };
+
+// eviction key of one slot: kInfKey = not a candidate.  The float arithmetic is the reference's
+// elementwise torch ops, one rounding each (no FMA contraction): metric / count, + bias * weight.
+__device__ __forceinline__ unsigned slot_key(const SelectParams& p, float m, int pos, int max_pos, int last_pos,
+                                             int l, int h) {
+  if (pos > max_pos || pos < p.num_sinks) return kInfKey;
+  if (p.use_average) m = __fdiv_rn(m, (float)(last_pos - pos));
+  if (p.head_bias != nullptr) {
+    float b = 0.f;
+    if (pos >= 0) {
+      int bin = -1;  // (#bins with start <= pos) - 1; -1 wraps to the last bin like the reference's index
+      for (int i = 0; i < p.num_bins; ++i) bin += (pos >= p.position_bins[i]);
+      if (bin < 0) bin = p.num_bins - 1;
+      b = p.head_bias[((int64_t)l * p.H + h) * p.num_bins + bin];
+    }
+    m = __fadd_rn(m, __fmul_rn(b, p.bias_weight));
+  }
+  return orderable(m);
+}
 
 // load the (up to) 8 consecutive logical slots i0..i0+7 of a head as orderable keys
 // (kInfKey for non-candidates and for i >= n); i0 is a multiple of 8 so the slots are half a block
 template <int B>
 __device__ __forceinline__ void load_keys8(const SelectParams& p, const int* __restrict__ bt, int i0, int n,
-                                           int max_pos, unsigned (&k)[8]) {
+                                           int max_pos, int last_pos, int l, int h, unsigned (&k)[8]) {
   if (B == 16) {
     if (i0 < n) {
       const int64_t slot = (int64_t)bt[i0 >> 4] * 16 + (i0 & 15);
@@ -75,7 +101,7 @@ __device__ __forceinline__ void load_keys8(const SelectParams& p, const int* __r
       const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
       const int q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-      for (int r = 0; r < 8; ++r) k[r] = (i0 + r < n && q[r] <= max_pos) ? orderable(m[r]) : kInfKey;
+      for (int r = 0; r < 8; ++r) k[r] = (i0 + r < n) ? slot_key(p, m[r], q[r], max_pos, last_pos, l, h) : kInfKey;
     } else {
 #pragma unroll
       for (int r = 0; r < 8; ++r) k[r] = kInfKey;
@@ -87,7 +113,7 @@ __device__ __forceinline__ void load_keys8(const SelectParams& p, const int* __r
       unsigned key = kInfKey;
       if (i < n) {
         const int64_t slot = (int64_t)bt[i / B] * B + i % B;
-        if (p.kv_position[slot] <= max_pos) key = orderable(p.kv_metrics[slot]);
+        key = slot_key(p, p.kv_metrics[slot], p.kv_position[slot], max_pos, last_pos, l, h);
       }
       k[r] = key;
     }
@@ -107,13 +133,14 @@ __global__ void __launch_bounds__(128) select_sort_kernel(SelectParams p) {
   const int nblk = (n + B - 1) / B;
   const int off = p.offsets[g];
   const int r0 = p.hanging[g];
-  const int max_pos = p.last_position[s] - p.protected_window[s];
+  const int last_pos = p.last_position[s];
+  const int max_pos = last_pos - p.protected_window[s];
   constexpr int N = 32 * KPL;  // keys sorted by the warp (256 or 512)
   unsigned k[KPL];
 #pragma unroll
   for (int q = 0; q < KPL / 8; ++q) {
     unsigned t8[8];
-    load_keys8<B>(p, p.block_tables + (int64_t)lsh * p.MB, lane * KPL + 8 * q, n, max_pos, t8);
+    load_keys8<B>(p, p.block_tables + (int64_t)lsh * p.MB, lane * KPL + 8 * q, n, max_pos, last_pos, l, h, t8);
 #pragma unroll
     for (int r = 0; r < 8; ++r) k[8 * q + r] = t8[r];
   }
@@ -179,12 +206,13 @@ __global__ void __launch_bounds__(128) select_emit_warp_kernel(SelectParams p) {
   const int kblk = p.evicted_block_count[g];
   int* __restrict__ out = p.evicted_logical_indices + off;
   if (cnt > 0) {
-    const int max_pos = p.last_position[s] - p.protected_window[s];
+    const int last_pos = p.last_position[s];
+    const int max_pos = last_pos - p.protected_window[s];
     unsigned k[KPL];
 #pragma unroll
     for (int q = 0; q < KPL / 8; ++q) {
       unsigned t8[8];
-      load_keys8<B>(p, p.block_tables + (int64_t)lsh * p.MB, lane * KPL + 8 * q, n, max_pos, t8);
+      load_keys8<B>(p, p.block_tables + (int64_t)lsh * p.MB, lane * KPL + 8 * q, n, max_pos, last_pos, l, h, t8);
 #pragma unroll
       for (int r = 0; r < 8; ++r) k[8 * q + r] = t8[r];
     }
@@ -240,15 +268,15 @@ __global__ void __launch_bounds__(128) select_rank_kernel(SelectParams p, int ma
   const int nblk = (n + p.B - 1) / p.B;
   const int off = p.offsets[g];
   const int r0 = p.hanging[g];
-  const int max_pos = p.last_position[s] - p.protected_window[s];
+  const int last_pos = p.last_position[s];
+  const int max_pos = last_pos - p.protected_window[s];
   const int* __restrict__ bt = p.block_tables + (int64_t)lsh * p.MB;
   if (t == 0) s_ncand = 0;
   __syncthreads();
   int local = 0;
   for (int i = t; i < n; i += 128) {
     const int64_t slot = (int64_t)bt[i / p.B] * p.B + i % p.B;
-    unsigned k = kInfKey;
-    if (p.kv_position[slot] <= max_pos) k = orderable(p.kv_metrics[slot]);
+    const unsigned k = slot_key(p, p.kv_metrics[slot], p.kv_position[slot], max_pos, last_pos, l, h);
     local += (k != kInfKey);
     keys[i] = k;
   }
@@ -271,6 +299,60 @@ __global__ void __launch_bounds__(128) select_rank_kernel(SelectParams p, int ma
   for (int k = nev + t; k < nblk; k += 128) ev[k] = kInfKey;
 }
 
+// ---- CTA-per-head path, contexts up to 32768 slots: bitonic sort of the keys in shared memory ----
+// Only key VALUES at ranks r0-1+kB are needed (equal keys are interchangeable), so the sort carries
+// no payload.  Each head sorts the next power of two >= its own context length.
+constexpr int kSortThreads = 512;
+__global__ void __launch_bounds__(kSortThreads) select_sort_cta_kernel(SelectParams p) {
+  extern __shared__ unsigned keys[];
+  __shared__ int s_ncand;
+  const int t = threadIdx.x;
+  const int g = blockIdx.x;
+  const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
+  const int lsh = (l * p.S + s) * p.H + h;
+  const int n = p.context_lens[lsh];
+  const int nblk = (n + p.B - 1) / p.B;
+  const int off = p.offsets[g];
+  const int r0 = p.hanging[g];
+  const int last_pos = p.last_position[s];
+  const int max_pos = last_pos - p.protected_window[s];
+  const int* __restrict__ bt = p.block_tables + (int64_t)lsh * p.MB;
+  int m = 64;
+  while (m < n) m <<= 1;
+  if (t == 0) s_ncand = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = t; i < m; i += kSortThreads) {
+    unsigned k = kInfKey;
+    if (i < n) {
+      const int64_t slot = (int64_t)bt[i / p.B] * p.B + i % p.B;
+      k = slot_key(p, p.kv_metrics[slot], p.kv_position[slot], max_pos, last_pos, l, h);
+    }
+    local += (k != kInfKey);
+    keys[i] = k;
+  }
+  if (local) atomicAdd(&s_ncand, local);
+  __syncthreads();
+  for (int kk = 2; kk <= m; kk <<= 1) {
+    for (int j = kk >> 1; j >= 1; j >>= 1) {
+      for (int idx = t; idx < (m >> 1); idx += kSortThreads) {
+        const int i = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));  // idx with a 0 inserted at bit log2(j)
+        const unsigned a = keys[i], b = keys[i | j];
+        const bool up = (i & kk) == 0;
+        if ((a > b) == up) {
+          keys[i] = b;
+          keys[i | j] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int ncand = s_ncand;
+  const int nev = (r0 >= 1 && ncand >= r0) ? (ncand - r0) / p.B + 1 : 0;
+  unsigned* ev = p.events + off / p.B;
+  for (int k = t; k < nblk; k += kSortThreads) ev[k] = (k < nev) ? keys[r0 - 1 + k * p.B] : kInfKey;
+}
+
 __global__ void __launch_bounds__(128) select_emit_cta_kernel(SelectParams p) {
   __shared__ int s_less, s_w[4], s_w2[4];
   const int t = threadIdx.x, lane = t % kWarp, w = t / kWarp;
@@ -282,14 +364,15 @@ __global__ void __launch_bounds__(128) select_emit_cta_kernel(SelectParams p) {
   const int off = p.offsets[g];
   const int cnt = p.evicted_kv_count[g];
   const int kblk = p.evicted_block_count[g];
-  const int max_pos = p.last_position[s] - p.protected_window[s];
+  const int last_pos = p.last_position[s];
+  const int max_pos = last_pos - p.protected_window[s];
   const int* __restrict__ bt = p.block_tables + (int64_t)lsh * p.MB;
   int* __restrict__ out = p.evicted_logical_indices + off;
   if (cnt > 0) {  // CTA-uniform
     const unsigned T = p.events[off / p.B + kblk - 1];
     auto key_of = [&](int i) -> unsigned {
       const int64_t slot = (int64_t)bt[i / p.B] * p.B + i % p.B;
-      return (p.kv_position[slot] <= max_pos) ? orderable(p.kv_metrics[slot]) : kInfKey;
+      return slot_key(p, p.kv_metrics[slot], p.kv_position[slot], max_pos, last_pos, l, h);
     };
     if (t == 0) s_less = 0;
     __syncthreads();
@@ -449,6 +532,23 @@ extern "C" int kvc_select_evictions(
     const int* last_position, const int* protected_window_size, int num_seqs, int num_layers,
     int num_kv_heads, int max_num_blocks_per_seq, int block_size, int64_t max_evicted_kv,
     int null_eviction_index, void* workspace, size_t workspace_bytes, kvc_stream_t stream) {
+  return kvc_select_evictions_ex(evicted_logical_indices, evicted_kv_count, evicted_block_count, kv_metrics,
+                                 kv_position, block_tables, context_lens, hanging_token_count,
+                                 evicted_kv_offsets, evicted_blocks_per_seq, last_position,
+                                 protected_window_size, num_seqs, num_layers, num_kv_heads,
+                                 max_num_blocks_per_seq, block_size, max_evicted_kv, null_eviction_index,
+                                 nullptr, nullptr, 0, 0.f, 0, 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int kvc_select_evictions_ex(
+    int* evicted_logical_indices, int* evicted_kv_count, int* evicted_block_count,
+    const float* kv_metrics, const int* kv_position, const int* block_tables, const int* context_lens,
+    const int* hanging_token_count, const int* evicted_kv_offsets, const int* evicted_blocks_per_seq,
+    const int* last_position, const int* protected_window_size, int num_seqs, int num_layers,
+    int num_kv_heads, int max_num_blocks_per_seq, int block_size, int64_t max_evicted_kv,
+    int null_eviction_index, const float* head_bias, const int* position_bins, int num_bins,
+    float bias_weight, int use_average, int num_sinks, void* workspace, size_t workspace_bytes,
+    kvc_stream_t stream) {
   KVC_REQUIRE(block_size == 1 || block_size == 2 || block_size == 4 || block_size == 16,
               KVC_ERR_UNSUPPORTED, "Unsupported block size: %d", block_size);
   KVC_REQUIRE(evicted_logical_indices && evicted_kv_count && evicted_block_count && kv_metrics &&
@@ -471,6 +571,10 @@ extern "C" int kvc_select_evictions(
   p.protected_window = protected_window_size;
   p.S = num_seqs; p.L = num_layers; p.H = num_kv_heads; p.MB = max_num_blocks_per_seq;
   p.B = block_size; p.null_index = null_eviction_index;
+  KVC_REQUIRE(head_bias == nullptr || (position_bins != nullptr && num_bins > 0), KVC_ERR_INVALID,
+              "select_evictions: head_bias needs position_bins");
+  p.head_bias = head_bias; p.position_bins = position_bins; p.num_bins = num_bins;
+  p.bias_weight = bias_weight; p.use_average = use_average; p.num_sinks = num_sinks;
   uintptr_t w = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
   p.events = reinterpret_cast<unsigned*>(w);
   cudaStream_t st = as_stream(stream);
@@ -495,6 +599,16 @@ extern "C" int kvc_select_evictions(
   if (warp_path) {
     KVC_SEL_WARP(select_sort_kernel);
     KVC_CHECK_LAUNCH("select_sort_kernel");
+  } else if (max_slots <= 32768) {
+    int m = 64;
+    while (m < max_slots) m <<= 1;
+    const size_t smem = (size_t)m * sizeof(unsigned);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(select_sort_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "select_sort_cta smem attr: %s", cudaGetErrorString(e));
+    }
+    select_sort_cta_kernel<<<total, kSortThreads, smem, st>>>(p);
+    KVC_CHECK_LAUNCH("select_sort_cta_kernel");
   } else {
     const size_t smem = (size_t)max_slots * sizeof(unsigned);
     KVC_REQUIRE(smem <= 220 * 1024, KVC_ERR_UNSUPPORTED,

@@ -162,7 +162,24 @@ void select_evictions(torch::Tensor& evicted_logical_indices, torch::Tensor& evi
                       torch::Tensor& kv_position, torch::Tensor& block_tables, torch::Tensor& context_lens,
                       torch::Tensor& hanging_token_count, torch::Tensor& evicted_kv_offsets,
                       torch::Tensor& evicted_blocks_per_seq, torch::Tensor& last_position,
-                      torch::Tensor& protected_window_size, int64_t block_size, int64_t null_eviction_index) {
+                      torch::Tensor& protected_window_size, int64_t block_size, int64_t null_eviction_index,
+                      const c10::optional<torch::Tensor>& head_bias, const c10::optional<torch::Tensor>& position_bins,
+                      double bias_weight, bool use_average, int64_t num_sinks) {
+  const float* bias_ptr = nullptr;
+  const int* bins_ptr = nullptr;
+  int num_bins = 0;
+  if (head_bias) {
+    const auto& b = head_bias.value();
+    TORCH_CHECK(position_bins.has_value(), "head_bias needs position_bins");
+    TORCH_CHECK(b.is_cuda() && b.scalar_type() == at::kFloat && b.is_contiguous() && b.dim() == 3,
+                "head_bias must be a contiguous float32 [num_layers, num_kv_heads, num_bins] CUDA tensor");
+    TORCH_CHECK(b.size(0) == evicted_kv_count.size(1) && b.size(1) == evicted_kv_count.size(2) &&
+                    b.size(2) == position_bins.value().numel(),
+                "head_bias shape does not match [num_layers, num_kv_heads, len(position_bins)]");
+    bias_ptr = b.data_ptr<float>();
+    bins_ptr = i32(position_bins.value(), "position_bins");
+    num_bins = b.size(2);
+  }
   TORCH_CHECK(evicted_kv_count.dim() == 3, "evicted_kv_count must be [num_seqs, num_layers, num_kv_heads]");
   TORCH_CHECK(block_tables.dim() == 4, "block_tables must be [num_layers, num_seqs, num_kv_heads, max_blocks]");
   TORCH_CHECK(kv_metrics.scalar_type() == at::kFloat && kv_metrics.is_contiguous() && kv_metrics.is_cuda(),
@@ -171,7 +188,7 @@ void select_evictions(torch::Tensor& evicted_logical_indices, torch::Tensor& evi
   const int64_t max_kv = evicted_logical_indices.numel();
   const size_t ws_bytes = kvc_select_evictions_workspace_bytes(max_kv, (int)block_size);
   auto ws = torch::empty({(int64_t)ws_bytes}, evicted_logical_indices.options().dtype(at::kByte));
-  check_status(kvc_select_evictions(
+  check_status(kvc_select_evictions_ex(
                    i32_mut(evicted_logical_indices, "evicted_logical_indices"),
                    i32_mut(evicted_kv_count, "evicted_kv_count"), i32_mut(evicted_block_count, "evicted_block_count"),
                    kv_metrics.data_ptr<float>(), i32(kv_position, "kv_position"), i32(block_tables, "block_tables"),
@@ -179,9 +196,73 @@ void select_evictions(torch::Tensor& evicted_logical_indices, torch::Tensor& evi
                    i32(evicted_kv_offsets, "evicted_kv_offsets"), i32(evicted_blocks_per_seq, "evicted_blocks_per_seq"),
                    i32(last_position, "last_position"), i32(protected_window_size, "protected_window_size"),
                    evicted_kv_count.size(0), evicted_kv_count.size(1), evicted_kv_count.size(2),
-                   block_tables.size(3), (int)block_size, max_kv, (int)null_eviction_index, ws.data_ptr(),
-                   ws_bytes, cur_stream()),
+                   block_tables.size(3), (int)block_size, max_kv, (int)null_eviction_index, bias_ptr, bins_ptr,
+                   num_bins, (float)bias_weight, use_average ? 1 : 0, (int)num_sinks, ws.data_ptr(), ws_bytes,
+                   cur_stream()),
                "select_evictions");
+}
+
+// additive ops: see include/kvc_b200.h kvc_prefill_kv_metrics / kvc_aggregate_prefill
+void prefill_kv_metrics(const c10::optional<torch::Tensor>& kv_metric_out,
+                        const c10::optional<torch::Tensor>& kv_metrics,
+                        const c10::optional<torch::Tensor>& slot_mapping, torch::Tensor& query, torch::Tensor& key,
+                        torch::Tensor& seq_start_loc, torch::Tensor& kv_metric_buffer_len, int64_t max_prompt_len,
+                        double scale, int64_t n_observed, bool use_l2, bool use_average, bool use_maxpool) {
+  TORCH_CHECK(query.dim() == 3 && key.dim() == 3, "query [T, Hq, D] and key [T, H, D] expected");
+  TORCH_CHECK(query.is_cuda() && key.is_cuda() && query.scalar_type() == key.scalar_type(),
+              "query and key must be CUDA tensors of one dtype");
+  TORCH_CHECK(query.stride(2) == 1 && key.stride(2) == 1 && query.stride(1) == query.size(2) &&
+                  key.stride(1) == key.size(2),
+              "query/key must be contiguous within a token");
+  TORCH_CHECK(query.size(0) == key.size(0), "query and key must hold the same tokens");
+  TORCH_CHECK(kv_metrics.has_value() == slot_mapping.has_value(), "kv_metrics and slot_mapping go together");
+  TORCH_CHECK(kv_metric_out.has_value() || kv_metrics.has_value(), "nothing to write");
+  const int T = query.size(0), Hq = query.size(1), H = key.size(1), D = query.size(2);
+  const int num_seqs = seq_start_loc.numel() - 1;
+  float* out_ptr = nullptr;
+  float* metrics_ptr = nullptr;
+  const int64_t* slots_ptr = nullptr;
+  if (kv_metric_out) {
+    const auto& t = kv_metric_out.value();
+    TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kFloat && t.is_contiguous() && t.numel() == (int64_t)T * Hq,
+                "kv_metric_out must be a contiguous float32 [T, Hq] CUDA tensor");
+    out_ptr = t.data_ptr<float>();
+  }
+  if (kv_metrics) {
+    const auto& m = kv_metrics.value();
+    const auto& sm = slot_mapping.value();
+    TORCH_CHECK(m.is_cuda() && m.scalar_type() == at::kFloat && m.is_contiguous(), "kv_metrics must be contiguous float32");
+    TORCH_CHECK(sm.is_cuda() && sm.scalar_type() == at::kLong && sm.is_contiguous() && sm.numel() == (int64_t)T * H,
+                "slot_mapping must be a contiguous int64 [T, H] CUDA tensor");
+    metrics_ptr = m.data_ptr<float>();
+    slots_ptr = sm.data_ptr<int64_t>();
+  }
+  const at::cuda::OptionalCUDAGuard guard(device_of(query));
+  const size_t ws_bytes = kvc_prefill_kv_metrics_workspace_bytes(T, num_seqs, Hq, H, (int)n_observed, (int)max_prompt_len);
+  auto ws = torch::empty({(int64_t)ws_bytes + 1}, query.options().dtype(at::kByte));
+  check_status(kvc_prefill_kv_metrics(out_ptr, metrics_ptr, slots_ptr, query.data_ptr(), key.data_ptr(),
+                                      i32(seq_start_loc, "seq_start_loc"),
+                                      i32(kv_metric_buffer_len, "kv_metric_buffer_len"), T, num_seqs, Hq, H, D,
+                                      query.stride(0), key.stride(0), (int)max_prompt_len, (float)scale,
+                                      (int)n_observed, use_l2, use_average, use_maxpool, cache_dtype(query),
+                                      ws.data_ptr(), ws_bytes, cur_stream()),
+               "prefill_kv_metrics");
+}
+
+void aggregate_prefill(torch::Tensor& kv_metrics, torch::Tensor& prefill_metrics, torch::Tensor& slot_mapping) {
+  TORCH_CHECK(prefill_metrics.dim() == 2 && slot_mapping.dim() == 2 && prefill_metrics.size(0) == slot_mapping.size(0),
+              "prefill_metrics [T, Hq] and slot_mapping [T, H] expected");
+  TORCH_CHECK(kv_metrics.is_cuda() && kv_metrics.scalar_type() == at::kFloat && kv_metrics.is_contiguous(),
+              "kv_metrics must be a contiguous float32 CUDA tensor");
+  TORCH_CHECK(prefill_metrics.is_cuda() && prefill_metrics.scalar_type() == at::kFloat && prefill_metrics.is_contiguous(),
+              "prefill_metrics must be a contiguous float32 CUDA tensor");
+  TORCH_CHECK(slot_mapping.is_cuda() && slot_mapping.scalar_type() == at::kLong && slot_mapping.is_contiguous(),
+              "slot_mapping must be a contiguous int64 CUDA tensor");
+  const at::cuda::OptionalCUDAGuard guard(device_of(kv_metrics));
+  check_status(kvc_aggregate_prefill(kv_metrics.data_ptr<float>(), prefill_metrics.data_ptr<float>(),
+                                     slot_mapping.data_ptr<int64_t>(), prefill_metrics.size(0), prefill_metrics.size(1),
+                                     slot_mapping.size(1), cur_stream()),
+               "aggregate_prefill");
 }
 
 // additive ops: see include/kvc_b200.h kvc_prepare_compression / kvc_free_and_append_slots
@@ -510,7 +591,9 @@ TORCH_LIBRARY_FRAGMENT(_C_kvc_ops, kvc_ops) {
       "                  Tensor block_tables, Tensor context_lens, Tensor hanging_token_count,"
       "                  Tensor evicted_kv_offsets, Tensor evicted_blocks_per_seq,"
       "                  Tensor last_position, Tensor protected_window_size,"
-      "                  int block_size, int null_eviction_index) -> ()");
+      "                  int block_size, int null_eviction_index, Tensor? head_bias=None,"
+      "                  Tensor? position_bins=None, float bias_weight=0.0, bool use_average=False,"
+      "                  int num_sinks=0) -> ()");
   kvc_ops.impl("select_evictions", torch::kCUDA, &select_evictions);
   kvc_ops.def(
       "prepare_compression(Tensor context_lens, Tensor! hanging_token_count, Tensor! evicted_kv_offsets,"
@@ -521,6 +604,13 @@ TORCH_LIBRARY_FRAGMENT(_C_kvc_ops, kvc_ops) {
       "                       Tensor? hanging_token_count, Tensor seq_len, Tensor! slot_mapping,"
       "                       Tensor! kv_position, int block_size, bool append) -> ()");
   kvc_ops.impl("free_and_append_slots", torch::kCUDA, &free_and_append_slots);
+  kvc_ops.def(
+      "prefill_kv_metrics(Tensor(a!)? kv_metric_out, Tensor(b!)? kv_metrics, Tensor? slot_mapping, Tensor query,"
+      "                    Tensor key, Tensor seq_start_loc, Tensor kv_metric_buffer_len, int max_prompt_len,"
+      "                    float scale, int n_observed, bool use_l2, bool use_average, bool use_maxpool) -> ()");
+  kvc_ops.impl("prefill_kv_metrics", torch::kCUDA, &prefill_kv_metrics);
+  kvc_ops.def("aggregate_prefill(Tensor! kv_metrics, Tensor prefill_metrics, Tensor slot_mapping) -> ()");
+  kvc_ops.impl("aggregate_prefill", torch::kCUDA, &aggregate_prefill);
 }
 
 // importable as a Python module named _C, like the reference's REGISTER_EXTENSION
