@@ -66,7 +66,10 @@ def test_prefill_metrics_fused_aggregate_golden(capi, name):
     np.testing.assert_allclose(metrics.cpu().numpy(), c["out_kv_metrics"], rtol=RTOL, atol=ATOL)
     # aggregate-only mode (no [T, Hq] output) gives the same cache metrics
     _, metrics2 = run_capi(capi, c, fused=True, want_out=False)
-    assert torch.equal(metrics, metrics2)
+    if int(c["n_observed"]) <= 32:
+        assert torch.equal(metrics, metrics2)
+    else:  # several warps add into one query head's column sums with atomics: order-dependent last bits
+        torch.testing.assert_close(metrics, metrics2, rtol=1e-5, atol=1e-7)
 
 
 @pytest.mark.parametrize("name", sorted(PREFILL))
