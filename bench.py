@@ -338,7 +338,9 @@ def main():
         "value": total_tokens / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": workload_config(args, total_tokens),
+        "config": dict(workload_config(args, total_tokens),
+                       attention_launch="programmatic dependent launch, kvc_set_attention_pdl mode %d"
+                                        % eng.attention_pdl),
         "e2e": {"value": total_tokens / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": qkv_host.numel() * qkv_host.element_size(),
                 "d2h_bytes_per_step": out_host.numel() * out_host.element_size()},

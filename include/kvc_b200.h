@@ -290,6 +290,21 @@ KVC_API int kvc_paged_attention_fused_step(
     size_t workspace_bytes, kvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Launch mode of the streaming decode-attention kernel (process-wide; initial value from the
+ * environment variable KVC_ATTN_PDL, default 1):
+ *   0  plain stream-ordered launches.
+ *   1  programmatic dependent launch (PDL): the kernel may start occupying SMs while the previous
+ *      kernel of the stream drains; its TMA producers prefetch cache blocks (written by EARLIER
+ *      steps) immediately, its consumers execute griddepcontrol.wait before they read the step's
+ *      query / new key / new value, which may be the previous kernel's output.  Always safe.
+ *   2  as 1, but the caller guarantees that query / key / value are NOT produced by the previous
+ *      kernel in the stream (e.g. every layer's q/k/v already resident, as in bench.py's step);
+ *      the wait moves to the kernel's end (it only keeps grid completion ordered).
+ * ------------------------------------------------------------------------- */
+KVC_API int kvc_set_attention_pdl(int mode);
+KVC_API int kvc_get_attention_pdl(void);
+
+/* ---------------------------------------------------------------------------
  * Additive: fused eviction selection straight from the paged metrics.
  * replaces CompressionMetrics.schedule_evictions (vllm/kvcompress/metrics.py:441-847:
  * mask gathers + 6 torch.sort + per-sequence host loop + count_block_evictions + final

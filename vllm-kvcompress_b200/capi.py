@@ -239,3 +239,13 @@ def aggregate_prefill(kv_metrics, prefill_metrics, slot_mapping):
     assert slot_mapping.dtype == torch.int64 and slot_mapping.is_contiguous()
     _check(lib.kvc_aggregate_prefill(_ptr(kv_metrics), _ptr(prefill_metrics), _ptr(slot_mapping), T, Hq, H,
                                      _stream()))
+
+
+def set_attention_pdl(mode: int) -> None:
+    """kvc_set_attention_pdl: 0 plain launches, 1 PDL with the wait before q/k/v (default), 2 PDL for
+    callers whose q/k/v do not come from the previous kernel in the stream."""
+    _check(native.load_lib().kvc_set_attention_pdl(int(mode)))
+
+
+def get_attention_pdl() -> int:
+    return int(native.load_lib().kvc_get_attention_pdl())

@@ -431,8 +431,12 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 template <bool BF16, int NT, int MODE, bool ALIBI>
 __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kernel(AttnParams p, float* scratch,
                                                                                    int scratch_tokens,
-                                                                                   int smem_logit_tokens) {
+                                                                                   int smem_logit_tokens, int pdl_late) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  // Programmatic dependent launch: the next kernel in the stream may start occupying SMs as this grid's
+  // CTAs retire (its producers then stream cache blocks under this grid's tail).  No-ops without the
+  // launch attribute.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
   constexpr int kPsBytes = NT * 8 * 16 * 2;
   const int H = p.num_kv_heads, Q = p.Q;
@@ -540,6 +544,9 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   // fused cache write (kvcompress_reshape_and_cache folded in, csrc/kvcompress_cache_kernels.cu:44-88):
   // the step's new token of this head is stored to the cache for later steps, and patched into the
   // staged copy of the last block below (the TMA read of that block may race with the store).
+  // Everything read so far (tables, context lengths, cache blocks of earlier steps) predates the stream's
+  // previous kernel; the step's q / new k / new v may be its output: wait for it here.
+  if (!pdl_late) asm volatile("griddepcontrol.wait;" ::: "memory");
   uint4 newk = make_uint4(0, 0, 0, 0);   // lane j < 16: chunk j of the new K
   uint16_t newv[4] = {0, 0, 0, 0};       // rows d = lane + 32 r of the new V
   int new_o = -1;                        // block offset of the new token, -1 = none
@@ -900,6 +907,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
       }
     }
   }
+  // inputs declared independent of the previous kernel: still order this grid's completion after it
+  if (pdl_late) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // -----------------------------------------------------------------------------
@@ -959,6 +968,16 @@ __global__ void __launch_bounds__(kAttnThreads) paged_attention_reduce_kernel(At
   }
 }
 
+static int g_pdl_mode = -1;  // -1 = not set yet: KVC_ATTN_PDL from the environment, else 1
+static int attention_pdl_mode() {
+  if (g_pdl_mode < 0) {
+    const char* v = getenv("KVC_ATTN_PDL");
+    g_pdl_mode = v ? atoi(v) : 1;
+    if (g_pdl_mode < 0 || g_pdl_mode > 2) g_pdl_mode = 1;
+  }
+  return g_pdl_mode;
+}
+
 template <bool BF16, int NT, int MODE>
 static size_t attn_smem_bytes(int fused_tokens, int Q) {
   constexpr int NQ = NT * 8;
@@ -1013,16 +1032,29 @@ static int launch_stream(const AttnParams& p, int num_seqs, float* scratch, int 
   const int items = num_seqs * p.num_kv_heads;
   const dim3 grid((items + kConsumers - 1) / kConsumers);
   cudaError_t e;
+  // launch mode: see kvc_set_attention_pdl (include/kvc_b200.h)
+  const int pdl_mode = attention_pdl_mode();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kStreamThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_mode > 0 ? 1 : 0;
+  const int pdl_late = pdl_mode == 2 ? 1 : 0;
   if (p.alibi_slopes) {
     auto kern = paged_attention_stream_kernel<BF16, NT, MODE, true>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) kern<<<grid, kStreamThreads, smem, st>>>(p, scratch, scratch_tokens, smem_logit_tokens);
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, p, scratch, scratch_tokens, smem_logit_tokens, pdl_late);
   } else {
     auto kern = paged_attention_stream_kernel<BF16, NT, MODE, false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) kern<<<grid, kStreamThreads, smem, st>>>(p, scratch, scratch_tokens, smem_logit_tokens);
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, p, scratch, scratch_tokens, smem_logit_tokens, pdl_late);
   }
-  if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "paged attention (stream) smem attr: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "paged attention (stream) launch: %s", cudaGetErrorString(e));
   KVC_CHECK_LAUNCH("paged_attention_stream_kernel");
   return KVC_OK;
 }
@@ -1201,3 +1233,10 @@ extern "C" int kvc_paged_attention_fused_step(
   return dispatch_stream<kModeFusedWrite>(p, num_seqs, reinterpret_cast<float*>(workspace), padded, dtype,
                                           as_stream(stream));
 }
+
+extern "C" int kvc_set_attention_pdl(int mode) {
+  KVC_REQUIRE(mode >= 0 && mode <= 2, KVC_ERR_INVALID, "attention PDL mode must be 0, 1 or 2, got %d", mode);
+  g_pdl_mode = mode;
+  return KVC_OK;
+}
+extern "C" int kvc_get_attention_pdl(void) { return attention_pdl_mode(); }

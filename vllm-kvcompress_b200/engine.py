@@ -26,12 +26,14 @@ shrinking; the reference frees the trailing blocks and never rewrites table entr
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional
 
 import torch
 
 from . import _custom_ops as ops
+from . import capi
 from . import workload as W
 
 MAX_INT = W.MAX_INT
@@ -53,6 +55,10 @@ class HotPathConfig:
     selection: str = "fused"           # "fused" (kvc_select kernels) | "chain" (torch.sort + K1 + K2)
     fused_metrics: bool = True         # attention accumulates sum_q p^2 itself
     fused_cache_write: bool = True     # ... and writes the step's new K/V (one launch per layer)
+    # the step's q/k/v of every layer are resident before the step starts (synthetic projections), i.e.
+    # never the output of the previous kernel in the stream: lets consecutive attention launches overlap
+    # (kvc_set_attention_pdl mode 2).  A model whose QKV GEMM feeds the attention kernel uses mode 1.
+    inputs_independent: bool = True
     seed: int = 0
 
 
@@ -63,6 +69,9 @@ class DecodeHotPath:
     def __init__(self, cfg: HotPathConfig, device: torch.device):
         self.cfg = cfg
         self.dev = device
+        if "KVC_ATTN_PDL" not in os.environ:   # an explicit environment setting wins (A/B runs)
+            capi.set_attention_pdl(2 if cfg.inputs_independent else 1)
+        self.attention_pdl = capi.get_attention_pdl()
         S, L, H, B, D = cfg.num_seqs, cfg.num_layers, cfg.num_kv_heads, cfg.block_size, cfg.head_size
         self.launches = 0
         st = W.make_state(S, L, H, B, D, cfg.max_cache_tokens, dtype=cfg.dtype, device=device,
