@@ -416,6 +416,73 @@ KVC_API int kvc_aggregate_prefill(
     const int64_t* slot_mapping, int num_tokens, int num_heads,
     int num_kv_heads, kvc_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * Additive: device-side block allocator and block-state updates.
+ * replaces ParallelBlockAllocator (vllm/kvcompress/block_manager.py:75-140: every allocate()
+ * compacts the whole free mask, `block_numbers[free_mask][:n]`) and the BlockSpaceManagerKVC
+ * paths on top of it, which materialise [L,S,H,MB] boolean masks and advanced-index copies of
+ * the block tables (block.py:337-412): _add_sequence (:196-222), _append_to_sequence_batch
+ * (:269-294), free_compressed_blocks (:466-530 + block.py:184-210), _remove_sequence_batch
+ * (:243-262), plus CompressionMetrics.insert_metadata / remove_metadata (metrics.py:344-370).
+ * State = the reference's own tensors, updated IN PLACE (no batch-view copies):
+ *   free_mask [num_blocks] bool bytes (1 = free), free_count [1] i32, status [1] i32
+ *   block_tables [L, max_seqs, H, MB] i32, context_lens [L, max_seqs, H] i32
+ *   kv_position (= token_positions) [num_blocks, B] i32
+ *   optional metadata [num_blocks] i32 each (NULL to skip): seq_index_by_block,
+ *   layer_index_by_block, head_index_by_block, logical_block_num_by_block
+ * Allocation order is the reference's: the lowest-numbered free blocks, ascending, handed out
+ * in row-major order of (layer, batch position, head[, block]); block tables come out identical.
+ * If fewer blocks are free than requested NOTHING is allocated and *status is set to 1
+ * (reference: ValueError("Out of memory!") on the host, :108-110); the caller polls status.
+ * seq_slots [n] = batch slot index of each sequence of the call (NULL = 0..n-1 for append/free).
+ * ------------------------------------------------------------------------- */
+KVC_API size_t kvc_alloc_workspace_bytes(int64_t num_blocks, int num_batch,
+                                         int num_layers, int num_kv_heads);
+
+/* free_all (:127-129): every block free, free_count = num_blocks, status = 0 */
+KVC_API int kvc_alloc_init(uint8_t* free_mask, int* free_count, int* status,
+                           int64_t num_blocks, kvc_stream_t stream);
+
+/* _append_to_sequence_batch + decode slot mapping (block.py:303-321): every head of the batch
+ * grows by one token at position seq_len[i]; heads on a block boundary get a new block.
+ * slot_mapping [L, num_batch, H] int64 out. */
+KVC_API int kvc_alloc_append_slots(
+    uint8_t* free_mask, int* free_count, int* status, int64_t num_blocks,
+    int* block_tables, int* context_lens, const int* seq_slots,
+    const int* seq_len, int64_t* slot_mapping, int* kv_position,
+    int* seq_index_by_block, int* layer_index_by_block,
+    int* head_index_by_block, int* logical_block_num_by_block, int num_batch,
+    int max_seqs, int num_layers, int num_kv_heads, int max_num_blocks_per_seq,
+    int block_size, void* workspace, size_t workspace_bytes, kvc_stream_t stream);
+
+/* _add_sequence for num_new prompts: seq_lens [num_new] tokens each, ceil(len/B) blocks per
+ * head in (sequence, layer, head, block) order; context_lens = len; positions = logical index.
+ * max_seq_len (host) = max of seq_lens. */
+KVC_API int kvc_alloc_add_sequences(
+    uint8_t* free_mask, int* free_count, int* status, int64_t num_blocks,
+    int* block_tables, int* context_lens, const int* seq_slots,
+    const int* seq_lens, int* kv_position, int* seq_index_by_block,
+    int* layer_index_by_block, int* head_index_by_block,
+    int* logical_block_num_by_block, int num_new, int max_seq_len, int max_seqs,
+    int num_layers, int num_kv_heads, int max_num_blocks_per_seq, int block_size,
+    void* workspace, size_t workspace_bytes, kvc_stream_t stream);
+
+/* free_compressed_blocks: evicted_block_count [num_batch, L, H] trailing blocks of each head are
+ * freed, context_lens -= max(k*B - (B - hanging), 0), seq_index_by_block[freed] = -1. */
+KVC_API int kvc_alloc_free_compressed(
+    uint8_t* free_mask, int* free_count, const int* block_tables,
+    int* context_lens, const int* evicted_block_count, const int* seq_slots,
+    int* seq_index_by_block, int num_batch, int max_seqs, int num_layers,
+    int num_kv_heads, int max_num_blocks_per_seq, int block_size,
+    kvc_stream_t stream);
+
+/* _remove_sequence_batch: free every allocated block of the sequences, context_lens = 0. */
+KVC_API int kvc_alloc_remove_sequences(
+    uint8_t* free_mask, int* free_count, const int* block_tables,
+    int* context_lens, const int* seq_slots, int* seq_index_by_block,
+    int num_removed, int max_seqs, int num_layers, int num_kv_heads,
+    int max_num_blocks_per_seq, int block_size, kvc_stream_t stream);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -297,3 +297,95 @@ def select_evictions(kv_metrics, kv_position, block_tables, context_lens, hangin
             off = int(evicted_kv_offsets[s, l, h])
             logical[off: off + cnt] = np.sort(order[:cnt])
     return logical, kv_count, blk_count
+
+
+class BlockManagerOracle:
+    """numpy restatement of ParallelBlockAllocator (vllm/kvcompress/block_manager.py:75-140) and the
+    block-state updates of BlockSpaceManagerKVC: _add_sequence (:196-222), _append_to_sequence_batch
+    (:269-294, metadata block.py:505-560 + metrics.py:344-362), free_compressed_blocks (:466-530 +
+    block.py:184-210, metrics.py:364-370) and _remove_sequence_batch (:243-262)."""
+
+    def __init__(self, L, H, B, max_seqs, MB, NB):
+        self.L, self.H, self.B, self.MS, self.MB, self.NB = L, H, B, max_seqs, MB, NB
+        self.block_tables = np.full((L, max_seqs, H, MB), -1, np.int32)
+        self.context_lens = np.zeros((L, max_seqs, H), np.int32)
+        self.free_mask = np.ones(NB, bool)
+        self.seq_index_by_block = np.full(NB, -1, np.int32)
+        self.layer_index_by_block = np.zeros(NB, np.int32)
+        self.head_index_by_block = np.zeros(NB, np.int32)
+        self.logical_block_num_by_block = np.zeros(NB, np.int32)
+        self.token_positions = np.full((NB, B), -1, np.int32)
+
+    @property
+    def free_count(self):
+        return int(self.free_mask.sum())
+
+    def _allocate(self, n):  # :106-114: the n lowest-numbered free blocks, ascending
+        if n > self.free_count:
+            raise ValueError("Out of memory!")
+        ids = np.nonzero(self.free_mask)[0][:n]
+        self.free_mask[ids] = False
+        return ids.astype(np.int32)
+
+    def add_sequences(self, slots, lens):
+        for slot, n in zip(slots, lens):
+            nblk = (n + self.B - 1) // self.B
+            ids = self._allocate(self.L * self.H * nblk).reshape(self.L, self.H, nblk)
+            self.context_lens[:, slot] = n
+            self.block_tables[:, slot, :, :nblk] = ids
+            for l in range(self.L):
+                for h in range(self.H):
+                    for b in range(nblk):
+                        self._meta(ids[l, h, b], slot, l, h, b, b * self.B)
+
+    def _meta(self, blk, slot, l, h, b, pos0):
+        self.seq_index_by_block[blk] = slot
+        self.layer_index_by_block[blk] = l
+        self.head_index_by_block[blk] = h
+        self.logical_block_num_by_block[blk] = b
+        self.token_positions[blk] = pos0 + np.arange(self.B)
+
+    def append_slots(self, slots, positions):
+        """+1 token per head of the batch; returns slot_mapping [L, batch, H] (block.py:303-321)."""
+        ctx = self.context_lens[:, slots]                                   # [L, batch, H] copy
+        need = (ctx % self.B) == 0
+        ids = self._allocate(int(need.sum()))
+        out = np.zeros(ctx.shape, np.int64)
+        k = 0
+        for l in range(self.L):
+            for sb, slot in enumerate(slots):
+                for h in range(self.H):
+                    c = int(ctx[l, sb, h])
+                    if need[l, sb, h]:
+                        blk = ids[k]
+                        k += 1
+                        self.block_tables[l, slot, h, c // self.B] = blk
+                        self._meta(blk, slot, l, h, c // self.B, positions[sb])
+                    blk = self.block_tables[l, slot, h, c // self.B]
+                    self.token_positions[blk, c % self.B] = positions[sb]
+                    out[l, sb, h] = int(blk) * self.B + c % self.B
+                    self.context_lens[l, slot, h] = c + 1
+        return out
+
+    def free_compressed(self, slots, counts):
+        """counts [batch, L, H] = freed blocks per head."""
+        for sb, slot in enumerate(slots):
+            for l in range(self.L):
+                for h in range(self.H):
+                    k, c = int(counts[sb, l, h]), int(self.context_lens[l, slot, h])
+                    nblk = (c + self.B - 1) // self.B
+                    ids = self.block_tables[l, slot, h, max(nblk - k, 0):nblk]
+                    self.free_mask[ids] = True
+                    self.seq_index_by_block[ids] = -1
+                    hanging = c % self.B or self.B
+                    self.context_lens[l, slot, h] = c - max(k * self.B - (self.B - hanging), 0)
+
+    def remove_sequences(self, slots):
+        for slot in slots:
+            for l in range(self.L):
+                for h in range(self.H):
+                    nblk = (int(self.context_lens[l, slot, h]) + self.B - 1) // self.B
+                    ids = self.block_tables[l, slot, h, :nblk]
+                    self.free_mask[ids] = True
+                    self.seq_index_by_block[ids] = -1
+            self.context_lens[:, slot] = 0

@@ -569,6 +569,134 @@ def gen_selection_v2():
     return cases
 
 
+def gen_block_manager():
+    """Block-manager golden: the reference's ParallelBlockAllocator (vllm/kvcompress/block_manager.py:75-140),
+    BlockState / BlockStateView (vllm/kvcompress/block.py:69-594) and the BlockSpaceManagerKVC methods
+    _add_sequence (:196-222), _append_to_sequence_batch (:269-294), free_compressed_blocks (:466-530),
+    _remove_sequence_batch (:243-262) plus CompressionMetrics.insert_metadata / remove_metadata
+    (metrics.py:344-370), executed on CPU tensors (the hard-coded "cuda:0" of BlockState._initialize and
+    the allocator default are redirected to "cpu" at load time; nothing else is altered).  A scripted
+    sequence of operations is replayed and the state after every operation recorded."""
+    class _Bench:
+        def wrap(self, *a, **k):
+            return lambda f: f
+        def start_range(self, *a, **k):
+            pass
+        end_range = start_range
+
+    class _Ckpt:
+        def checkpoint(self, *a, **k):
+            pass
+
+    src = open(os.path.join(REF, "vllm", "kvcompress", "block.py")).read().replace('"cuda:0"', '"cpu"')
+    tree = ast.parse(src)
+    body = [n for n in tree.body if not isinstance(n, (ast.Import, ast.ImportFrom))]
+    from typing import Any, List, Tuple, Dict, NamedTuple, Union
+    import math
+    ns = {"torch": torch, "np": np, "math": math, "Any": Any, "List": List, "Tuple": Tuple, "Dict": Dict,
+          "Optional": Optional, "NamedTuple": NamedTuple, "Union": Union, "Device": object,
+          "CHECKPOINTER": _Ckpt(), "BENCHMARKER": _Bench()}
+    saved = torch.cuda.memory_allocated
+    torch.cuda.memory_allocated = lambda *a, **k: 0          # debug prints in _initialize
+    exec(compile(ast.Module(body=body, type_ignores=[]), "block.py", "exec"), ns)
+    BlockState = ns["BlockState"]
+
+    msrc = open(os.path.join(REF, "vllm", "kvcompress", "block_manager.py")).read().replace('"cuda:0"', '"cpu"')
+    mtree = ast.parse(msrc)
+    classes = {n.name: n for n in mtree.body if isinstance(n, ast.ClassDef)}
+    mns = dict(ns, BlockAllocatorBase=object, ABC=object, abstractmethod=lambda f: f, tqdm=lambda it, **k: it)
+    exec(compile(ast.Module(body=[classes["BlockTableView"], classes["ParallelBlockAllocator"]], type_ignores=[]),
+                 "block_manager.py", "exec"), mns)
+    Allocator = mns["ParallelBlockAllocator"]
+    methods = [n for n in classes["BlockSpaceManagerKVC"].body if isinstance(n, ast.FunctionDef)
+               and n.name in ("_add_sequence", "_append_to_sequence_batch", "free_compressed_blocks",
+                              "_remove_sequence_batch")]
+    for m in methods:
+        m.decorator_list = []
+    mns.update(Sequence=object, FreedBlockCounts=dict)
+    exec(compile(ast.Module(body=methods, type_ignores=[]), "block_manager.py", "exec"), mns)
+    insert_metadata, remove_metadata = _load_reference_functions(
+        os.path.join(REF, "vllm", "kvcompress", "metrics.py"), ["insert_metadata", "remove_metadata"],
+        class_name="CompressionMetrics", extra_ns={"BlockMetadata": ns["BlockMetadata"]})
+
+    cases = {}
+    for name, (L, H, B, MS, MB, NB, script) in {
+        "bm_b4": (2, 3, 4, 4, 12, 150, [
+            ("add", 0, 9), ("add", 1, 16), ("append", [0, 1], 3), ("free", [1, 0], 7), ("append", [1, 0], 6),
+            ("remove", [0]), ("add", 2, 5), ("append", [1, 2], 9), ("free", [2], 8), ("add", 3, 1),
+            ("append", [3, 2, 1], 4)]),
+        "bm_b16": (3, 2, 16, 3, 8, 120, [
+            ("add", 0, 33), ("add", 1, 64), ("append", [0, 1], 20), ("free", [0, 1], 5), ("append", [1], 17),
+            ("remove", [1]), ("add", 2, 47), ("append", [0, 2], 18)]),
+    }.items():
+        rng = np.random.RandomState(len(name))
+        bs = BlockState(B, L, H, MS, MB, 0, False)
+        bs.block_tables.fill_(-1)                       # torch.empty in the reference: unallocated entries are don't-care
+        km = types.SimpleNamespace(
+            seq_index_by_block=torch.full((NB,), -1, dtype=torch.int), logical_block_num_by_block=torch.zeros(NB, dtype=torch.int),
+            layer_index_by_block=torch.zeros(NB, dtype=torch.int), head_index_by_block=torch.zeros(NB, dtype=torch.int),
+            token_positions=torch.full((NB, B), -1, dtype=torch.int))
+        km.insert_metadata = lambda md, km=km: insert_metadata(km, md)
+        mgr = types.SimpleNamespace(block_size=B, num_layers=L, num_kv_heads=H, device="cpu", gpu_allocator=Allocator(NB, "cpu"),
+                                    block_state=bs, kv_metrics=km, free_batch_slots=set(range(MS)), batch_slot_mapping={})
+        seq_len = {}
+        steps = []
+
+        def snap(op, **kw):
+            steps.append(dict(op=op, **kw, block_tables=bs.block_tables.numpy().copy(),
+                              context_lens=bs.context_lens.numpy().copy(),
+                              free_mask=mgr.gpu_allocator.free_mask.numpy().copy(),
+                              free_count=int(mgr.gpu_allocator.free_count),
+                              seq_index_by_block=km.seq_index_by_block.numpy().copy(),
+                              layer_index_by_block=km.layer_index_by_block.numpy().copy(),
+                              head_index_by_block=km.head_index_by_block.numpy().copy(),
+                              logical_block_num_by_block=km.logical_block_num_by_block.numpy().copy(),
+                              token_positions=km.token_positions.numpy().copy()))
+
+        for item in script:
+            if item[0] == "add":
+                _, sid, n = item
+                quiet(mns["_add_sequence"], mgr, sid, n)
+                seq_len[sid] = n
+                snap("add", slots=[mgr.batch_slot_mapping[sid]], lens=[n])
+            elif item[0] == "append":
+                _, sids, times = item
+                for _ in range(times):
+                    for sid in sids:
+                        seq_len[sid] += 1
+                    seqs = [types.SimpleNamespace(seq_id=sid, data=types.SimpleNamespace(get_len=lambda sid=sid: seq_len[sid]))
+                            for sid in sids]
+                    quiet(mns["_append_to_sequence_batch"], mgr, seqs)
+                    snap("append", slots=[mgr.batch_slot_mapping[sid] for sid in sids],
+                         positions=[seq_len[sid] - 1 for sid in sids])
+            elif item[0] == "free":
+                _, sids, seed = item
+                r = np.random.RandomState(seed)
+                counts = {}
+                for sid in sids:
+                    slot = mgr.batch_slot_mapping[sid]
+                    nblk = (bs.context_lens[:, slot].numpy() + B - 1) // B
+                    counts[sid] = torch.tensor(r.randint(0, nblk + 1).astype(np.int32))   # [L, H], 0..all blocks
+                freed = quiet(mns["free_compressed_blocks"], mgr, counts)
+                remove_metadata(km, freed)                                              # scheduler.py:555
+                snap("free", slots=[mgr.batch_slot_mapping[sid] for sid in sids],
+                     counts=np.stack([counts[sid].numpy() for sid in sids]))            # [batch, L, H]
+            elif item[0] == "remove":
+                _, sids = item
+                slots = [mgr.batch_slot_mapping[sid] for sid in sids]
+                seqs = [types.SimpleNamespace(seq_id=sid) for sid in sids]
+                freed = quiet(mns["_remove_sequence_batch"], mgr, seqs)
+                remove_metadata(km, freed)                                              # core/scheduler.py:1519
+                snap("remove", slots=slots)
+        flat = dict(L=L, H=H, B=B, MS=MS, MB=MB, NB=NB, num_steps=len(steps))
+        for i, st in enumerate(steps):
+            for k, v in st.items():
+                flat[f"s{i:03d}_{k}"] = np.asarray(v)
+        cases[name] = flat
+    torch.cuda.memory_allocated = saved
+    return cases
+
+
 def save(name, cases):
     flat = {}
     for cname, d in cases.items():
@@ -581,7 +709,7 @@ def save(name, cases):
 
 def main():
     """python tests/golden/make_golden.py [name ...] -- regenerate all, or only the named files
-    (evictions count_blocks moves attention cache_write selection_v2 prefill_metrics)."""
+    (evictions count_blocks moves attention cache_write selection_v2 block_manager prefill_metrics)."""
     want = set(sys.argv[1:])
     on = lambda n: not want or n in want
     ops = _load_reference_custom_ops() if (not want or want & {"evictions", "count_blocks", "moves"}) else None
@@ -597,6 +725,8 @@ def main():
         save("cache_write.npz", gen_cache_write())
     if on("selection_v2"):
         save("selection_v2.npz", gen_selection_v2())
+    if on("block_manager"):
+        save("block_manager.npz", gen_block_manager())
     if on("prefill_metrics"):
         save("prefill_metrics.npz", gen_prefill_metrics())
 

@@ -253,3 +253,56 @@ def test_select_evictions_matches_reference_schedule_evictions(name):
     np.testing.assert_array_equal(blk_count, c["out_evicted_block_count"])
     np.testing.assert_array_equal(logical, c["out_evicted_logical_indices"])
     assert int(blk_count.sum()) == min(int(c["budget"]), int(blk_count.sum()))
+
+
+# ---------------------------------------------------------------------------
+# block manager / allocator
+# ---------------------------------------------------------------------------
+BLOCKMGR = load_cases("block_manager.npz")
+
+
+def replay_block_manager(c, mgr, check):
+    """Replays the golden script on `mgr` (oracle or CUDA adapter), calling check(step_index, prefix)."""
+    for i in range(int(c["num_steps"])):
+        pre = f"s{i:03d}_"
+        op = str(c[pre + "op"])
+        slots = c[pre + "slots"].tolist()
+        if op == "add":
+            mgr.add_sequences(slots, c[pre + "lens"].tolist())
+        elif op == "append":
+            mgr.append_slots(slots, c[pre + "positions"].tolist())
+        elif op == "free":
+            mgr.free_compressed(slots, c[pre + "counts"])
+        elif op == "remove":
+            mgr.remove_sequences(slots)
+        check(i, pre)
+
+
+def assert_block_state_equal(c, pre, B, block_tables, context_lens, free_mask, seq_idx, layer_idx, head_idx,
+                             logical_idx, token_positions):
+    np.testing.assert_array_equal(context_lens, c[pre + "context_lens"])
+    np.testing.assert_array_equal(free_mask.astype(bool), c[pre + "free_mask"])
+    MB = block_tables.shape[-1]
+    alloc = np.arange(MB)[None, None, None] < ((context_lens + B - 1) // B)[..., None]
+    np.testing.assert_array_equal(block_tables[alloc], c[pre + "block_tables"][alloc])
+    np.testing.assert_array_equal(seq_idx, c[pre + "seq_index_by_block"])
+    used = seq_idx >= 0   # metadata of live blocks (freed blocks keep stale values in the reference too)
+    np.testing.assert_array_equal(layer_idx[used], c[pre + "layer_index_by_block"][used])
+    np.testing.assert_array_equal(head_idx[used], c[pre + "head_index_by_block"][used])
+    np.testing.assert_array_equal(logical_idx[used], c[pre + "logical_block_num_by_block"][used])
+    np.testing.assert_array_equal(token_positions[used], c[pre + "token_positions"][used])
+
+
+@pytest.mark.parametrize("name", sorted(BLOCKMGR))
+def test_block_manager_oracle_matches_reference_python(name):
+    c = BLOCKMGR[name]
+    L, H, B, MS, MB, NB = (int(c[k]) for k in ("L", "H", "B", "MS", "MB", "NB"))
+    mgr = O.BlockManagerOracle(L, H, B, MS, MB, NB)
+
+    def check(i, pre):
+        assert mgr.free_count == int(c[pre + "free_count"])
+        assert_block_state_equal(c, pre, B, mgr.block_tables, mgr.context_lens, mgr.free_mask,
+                                 mgr.seq_index_by_block, mgr.layer_index_by_block, mgr.head_index_by_block,
+                                 mgr.logical_block_num_by_block, mgr.token_positions)
+
+    replay_block_manager(c, mgr, check)

@@ -249,3 +249,64 @@ def set_attention_pdl(mode: int) -> None:
 
 def get_attention_pdl() -> int:
     return int(native.load_lib().kvc_get_attention_pdl())
+
+
+class DeviceBlockAllocator:
+    """The allocator / block-state ops of include/kvc_b200.h (kvc_alloc_*) bound to one set of state
+    tensors -- the same tensors the reference keeps in ParallelBlockAllocator, BlockState and
+    CompressionMetrics (block_manager.py:75-140, block.py:94-126, metrics.py:220-275)."""
+
+    def __init__(self, num_blocks, block_tables, context_lens, kv_position, block_size, metadata=None):
+        dev = block_tables.device
+        self.NB, self.B = int(num_blocks), int(block_size)
+        self.block_tables, self.context_lens, self.kv_position = block_tables, context_lens, kv_position
+        self.L, self.MS, self.H, self.MB = block_tables.shape
+        self.free_mask = torch.empty(self.NB, dtype=torch.bool, device=dev)
+        self.free_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        # (seq, layer, head, logical block) index by block, or None
+        self.metadata = metadata if metadata is not None else (None, None, None, None)
+        lib = native.load_lib()
+        lib.kvc_alloc_workspace_bytes.restype = ctypes.c_size_t
+        nbytes = lib.kvc_alloc_workspace_bytes(ctypes.c_int64(self.NB), self.MS, self.L, self.H)
+        self.ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        _check(lib.kvc_alloc_init(_ptr(self.free_mask), _ptr(self.free_count), _ptr(self.status),
+                                  ctypes.c_int64(self.NB), _stream()))
+
+    def _state(self):
+        return (_ptr(self.free_mask), _ptr(self.free_count), _ptr(self.status), ctypes.c_int64(self.NB),
+                _ptr(_i32(self.block_tables, "block_tables")), _ptr(_i32(self.context_lens, "context_lens")))
+
+    def _meta(self):
+        return [_ptr(t) for t in self.metadata]
+
+    def _ws(self):
+        return _ptr(self.ws), ctypes.c_size_t(self.ws.numel())
+
+    def append_slots(self, seq_slots, seq_len, slot_mapping):
+        n = seq_len.numel()
+        assert slot_mapping.dtype == torch.int64 and slot_mapping.is_contiguous()
+        _check(native.load_lib().kvc_alloc_append_slots(
+            *self._state(), _ptr(None if seq_slots is None else _i32(seq_slots, "seq_slots")),
+            _ptr(_i32(seq_len, "seq_len")), _ptr(slot_mapping), _ptr(_i32(self.kv_position, "kv_position")),
+            *self._meta(), n, self.MS, self.L, self.H, self.MB, self.B, *self._ws(), _stream()))
+
+    def add_sequences(self, seq_slots, seq_lens, max_seq_len):
+        _check(native.load_lib().kvc_alloc_add_sequences(
+            *self._state(), _ptr(_i32(seq_slots, "seq_slots")), _ptr(_i32(seq_lens, "seq_lens")),
+            _ptr(_i32(self.kv_position, "kv_position")), *self._meta(), seq_lens.numel(), int(max_seq_len),
+            self.MS, self.L, self.H, self.MB, self.B, *self._ws(), _stream()))
+
+    def free_compressed(self, seq_slots, evicted_block_count):
+        n = evicted_block_count.shape[0]
+        _check(native.load_lib().kvc_alloc_free_compressed(
+            _ptr(self.free_mask), _ptr(self.free_count), _ptr(self.block_tables), _ptr(self.context_lens),
+            _ptr(_i32(evicted_block_count, "evicted_block_count")),
+            _ptr(None if seq_slots is None else _i32(seq_slots, "seq_slots")), self._meta()[0], n, self.MS,
+            self.L, self.H, self.MB, self.B, _stream()))
+
+    def remove_sequences(self, seq_slots):
+        _check(native.load_lib().kvc_alloc_remove_sequences(
+            _ptr(self.free_mask), _ptr(self.free_count), _ptr(self.block_tables), _ptr(self.context_lens),
+            _ptr(_i32(seq_slots, "seq_slots")), self._meta()[0], seq_slots.numel(), self.MS, self.L, self.H,
+            self.MB, self.B, _stream()))
