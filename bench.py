@@ -48,12 +48,24 @@ def parse():
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama3-70b"],
                     help="shape preset: 8b = L32 H8 Q4 CR64 (max_cache_tokens 128); 70b = L80 H8 Q8 CR16 (368)")
     ap.add_argument("--selection", default="fused", choices=["fused", "chain"])
+    ap.add_argument("--allocator", default="device", choices=["device", "static"],
+                    help="device = blocks freed/allocated every step by the device-side allocator")
     ap.add_argument("--unfused-metrics", action="store_true")
     ap.add_argument("--separate-cache-write", action="store_true", help="K6 as its own launch per layer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-compaction", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=16)
     return ap.parse_args()
+
+
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json),
+    or None when no capture of this configuration exists."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p)).get(kernel)
+    return None if d is None else d["dram_bytes_read_per_launch"] + d["dram_bytes_write_per_launch"]
 
 
 def peaks():
@@ -151,7 +163,8 @@ def workload_config(args, batch):
     return {"workload": wl,
             "global_batch": batch, "seq_len": 6000, "parallelism": "request-sharded replicas",
             "l2": "inputs larger than L2 (per-step KV read ~4.6 GB vs 126 MB L2)",
-            "selection": args.selection, "fused_metrics": not args.unfused_metrics,
+            "selection": args.selection, "allocator": getattr(args, "allocator", "device"),
+            "fused_metrics": not args.unfused_metrics,
             "fused_cache_write": not getattr(args, "separate_cache_write", False),
             "launch": "one CUDA graph per step" if args.selection == "fused" else "eager"}
 
@@ -264,7 +277,7 @@ def main():
         args.layers = 80
         preset = dict(queries_per_kv=8, max_cache_tokens=368, blocks_per_head=28)
     cfg = HotPathConfig(num_seqs=args.batch, num_layers=args.layers, selection=args.selection,
-                        fused_metrics=not args.unfused_metrics, **preset,
+                        fused_metrics=not args.unfused_metrics, allocator=args.allocator, **preset,
                         fused_cache_write=not args.separate_cache_write, seed=rank)
     from vllm_kvcompress_b200 import sharding
     # the only collective on this path: one start-up broadcast (stands in for the weight broadcast
@@ -349,7 +362,9 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "paged_attention_stream_kernel (cache write + attention + metric aggregation), %d launches/step" % L,
                      "achieved": attn_b / (attn_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": attn_b / (attn_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-                     "bytes_per_launch": attn_b, "ms_per_launch": attn_ms, "traffic": None},
+                     "bytes_per_launch": attn_b, "ms_per_launch": attn_ms,
+                     "traffic": ncu_traffic("paged_attention_stream_kernel")
+                     if (args.model == "llama3-8b" and args.batch == 256) else None},
     }
     if not args.no_compaction:
         try:

@@ -686,14 +686,19 @@ def test_block_state_ops_match_reference_formulas(capi):
     assert torch.equal(slot.cpu(), want_slot) and torch.equal(pos.cpu(), want_pos)
 
 
-@pytest.mark.parametrize("cfg", [(81, 6, 32, 8, 160, False), (82, 3, 64, 8, 300, True), (83, 4, 8, 8, 33, False)])
+@pytest.mark.parametrize("cfg", [(81, 6, 32, 8, 160, False), (82, 3, 64, 8, 300, True), (83, 4, 8, 8, 33, False),
+                                 # every head's new token opens a fresh block (ctx = 16k + 1): the kernel does
+                                 # not fetch that block at all and serves it from the step's k/v registers
+                                 (84, 6, 32, 8, 160, False, True), (85, 2, 64, 8, 49, True, True)])
 def test_fused_step_equals_cache_write_then_attention(capi, cfg):
     """kvcompress_paged_attention_fused_step == reshape_and_cache_kvc followed by the fused-metrics
     attention (bit-exact caches, identical recording rule, outputs within the attention tolerance)."""
     from vllm_kvcompress_b200 import _custom_ops as ops
-    seed, S, Hq, H, max_ctx, bf = cfg
+    seed, S, Hq, H, max_ctx, bf = cfg[:6]
     c = attn_case(seed, S, Hq, H, max_ctx, bf, False, 0, min_ctx=1)
     D, B = 128, 16
+    if len(cfg) > 6:
+        c["context_lens"] = ((c["context_lens"] - 1) // B * B + 1).astype(np.int32)
     q, kc, vc = cu16(c["query"], bf), cu16(c["key_cache"], bf), cu16(c["value_cache"], bf)
     NB = kc.shape[0]
     bt, cl = cu(c["block_tables"], torch.int32), cu(c["context_lens"], torch.int32)

@@ -25,7 +25,7 @@ namespace kvc {
 
 constexpr int kChunk = 256;        // blocks per chunk (= bytes of the bool mask)
 constexpr int kSuper = 256;        // chunks per super-chunk
-constexpr int kNeedCta = 1024;     // heads per CTA in the rank scan
+constexpr int kNeedCta = 256;      // heads per CTA in the rank scan
 
 struct AllocIndex {
   const uint8_t* free_mask;
@@ -102,18 +102,15 @@ __global__ void __launch_bounds__(256) alloc_count_kernel(AppendParams p, int co
     chunk_count_warp(p.ix, blockIdx.x * 8 + warp, lane);
     return;
   }
-  // need partials: this CTA covers kNeedCta heads
+  // need partials: this CTA covers kNeedCta heads, one per thread
   __shared__ int s_tot;
   if (threadIdx.x == 0) s_tot = 0;
   __syncthreads();
   const int cta = blockIdx.x - count_ctas;
   const int total = p.L * p.num_batch * p.H;
-  int local = 0;
-  for (int i = threadIdx.x; i < kNeedCta; i += 256) {
-    const int g = cta * kNeedCta + i;
-    int lsh, ctx;
-    if (g < total) local += append_need(p, g, lsh, ctx);
-  }
+  const int g = cta * kNeedCta + threadIdx.x;
+  int lsh, ctx;
+  int local = (g < total) ? append_need(p, g, lsh, ctx) : 0;
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
   if (lane == 0 && local) atomicAdd(&s_tot, local);
@@ -199,14 +196,24 @@ __global__ void __launch_bounds__(kNeedCta) alloc_append_kernel(AppendParams p) 
   __shared__ int s_base, s_total_need;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const int total_free = load_super_prefix(p.ix, s_super);
-  if (t == 0) {
-    int acc = 0, base = 0;
-    for (int i = 0; i < p.n_need_ctas; ++i) {
-      if (i == (int)blockIdx.x) base = acc;
-      acc += p.need_partials[i];
+  if (t == 0) s_base = s_total_need = 0;
+  __syncthreads();
+  {
+    int before = 0, all = 0;  // needs of the CTAs before this one / of all CTAs
+    for (int i = t; i < p.n_need_ctas; i += kNeedCta) {
+      const int v = p.need_partials[i];
+      all += v;
+      if (i < (int)blockIdx.x) before += v;
     }
-    s_base = base;
-    s_total_need = acc;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      before += __shfl_xor_sync(0xffffffffu, before, d);
+      all += __shfl_xor_sync(0xffffffffu, all, d);
+    }
+    if (lane == 0 && all) {
+      atomicAdd(&s_total_need, all);
+      if (before) atomicAdd(&s_base, before);
+    }
   }
   __syncthreads();
   const int total_need = s_total_need;
@@ -313,34 +320,40 @@ __global__ void __launch_bounds__(256) alloc_add_kernel(AddParams p, int max_nbl
 }
 
 // ---- free the trailing blocks of compressed heads + shrink the context lengths ----
-// one warp per (batch position, l, h) of evicted_block_count [num_batch, L, H]
+// one thread per (batch position, l, h) of evicted_block_count [num_batch, L, H]; one atomic per CTA
 __global__ void __launch_bounds__(256) alloc_free_compressed_kernel(
     uint8_t* free_mask, int* free_count, const int* block_tables, int* context_lens,
     const int* evicted_block_count, const int* seq_slots, int* seq_index_by_block, int num_batch, int max_seqs,
     int L, int H, int MB, int B) {
-  const int lane = threadIdx.x & 31;
-  const int g = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (g >= num_batch * L * H) return;
-  const int k = evicted_block_count[g];
-  if (k <= 0) return;
-  const int h = g % H, l = (g / H) % L, sb = g / (L * H);
-  const int slot = seq_slots ? seq_slots[sb] : sb;
-  const int lsh = (l * max_seqs + slot) * H + h;
-  const int ctx = context_lens[lsh];
-  const int nblk = (ctx + B - 1) / B;   // block.py:337-355, 367-379: the last k allocated blocks
-  const int* bt = block_tables + (int64_t)lsh * MB;
-  for (int j = nblk - k + lane; j < nblk; j += 32) {
-    if (j < 0) continue;
-    const int blk = bt[j];
-    free_mask[blk] = 1;
-    if (seq_index_by_block) seq_index_by_block[blk] = -1;   // metrics.py:364-370
+  __shared__ int s_freed;
+  if (threadIdx.x == 0) s_freed = 0;
+  __syncthreads();
+  const int g = blockIdx.x * 256 + threadIdx.x;
+  int freed = 0;
+  if (g < num_batch * L * H) {
+    const int k = evicted_block_count[g];
+    if (k > 0) {
+      const int h = g % H, l = (g / H) % L, sb = g / (L * H);
+      const int slot = seq_slots ? seq_slots[sb] : sb;
+      const int lsh = (l * max_seqs + slot) * H + h;
+      const int ctx = context_lens[lsh];
+      const int nblk = (ctx + B - 1) / B;   // block.py:337-355, 367-379: the last k allocated blocks
+      const int* bt = block_tables + (int64_t)lsh * MB;
+      for (int j = max(nblk - k, 0); j < nblk; ++j) {
+        const int blk = bt[j];
+        free_mask[blk] = 1;
+        if (seq_index_by_block) seq_index_by_block[blk] = -1;   // metrics.py:364-370
+      }
+      freed = min(k, nblk);
+      const int hanging = (ctx % B) ? (ctx % B) : B;            // block.py:330-335
+      context_lens[lsh] = ctx - max(k * B - (B - hanging), 0);  // block.py:184-210
+    }
   }
-  if (lane == 0) {
-    const int freed = min(k, nblk);
-    atomicAdd(free_count, freed);
-    const int hanging = (ctx % B) ? (ctx % B) : B;          // block.py:330-335
-    context_lens[lsh] = ctx - max(k * B - (B - hanging), 0);  // block.py:184-210
-  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) freed += __shfl_xor_sync(0xffffffffu, freed, d);
+  if ((threadIdx.x & 31) == 0 && freed) atomicAdd(&s_freed, freed);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_freed) atomicAdd(free_count, s_freed);
 }
 
 // ---- remove sequences: free every allocated block, context length 0 ----
@@ -506,7 +519,7 @@ extern "C" int kvc_alloc_free_compressed(uint8_t* free_mask, int* free_count, co
               KVC_ERR_INVALID, "alloc_free_compressed: bad sizes");
   if (num_batch == 0) return KVC_OK;
   const int heads = num_batch * num_layers * num_kv_heads;
-  alloc_free_compressed_kernel<<<(heads + 7) / 8, 256, 0, as_stream(stream)>>>(
+  alloc_free_compressed_kernel<<<(heads + 255) / 256, 256, 0, as_stream(stream)>>>(
       free_mask, free_count, block_tables, context_lens, evicted_block_count, seq_slots, seq_index_by_block,
       num_batch, max_seqs, num_layers, num_kv_heads, max_num_blocks_per_seq, block_size);
   KVC_CHECK_LAUNCH("alloc_free_compressed_kernel");

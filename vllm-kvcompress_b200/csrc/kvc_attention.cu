@@ -474,6 +474,16 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     const uint32_t ring = smem_u32(ring_of(w)), full = full_of(w), empty = empty_of(w);
     const unsigned lanes = __activemask();
     const int nunits = 4 * nblk;
+    // Fused cache write, new token opens a fresh block (the steady state of continual compression: every
+    // head sits on a block boundary after each compression): that block's only valid token is the one this
+    // step writes, and the consumer patches it into the staged copy from registers -- nothing to fetch.
+    // Its 4 units are released with a plain arrive; whatever the ring slot still holds is masked like any
+    // other slot beyond the context length.
+    bool skip_last = false;
+    if (MODE == kModeFusedWrite) {
+      const int64_t nslot = p.slot_mapping[item];
+      skip_last = nslot >= 0 && (nslot & (kB - 1)) == 0 && ctx == (nblk - 1) * kB + 1;
+    }
     // Unit order = the consumer's software pipeline: K(0) lo/hi; then per block b: K(b+1) lo/hi (if any), V(b) lo/hi.
     auto decode = [&](int u, int& isv, int& hf, int& blk) {
       if (u < 2) { isv = 0; hf = u; blk = 0; return; }
@@ -495,9 +505,13 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
           ready = ok != 0;
         }
         if (ready) {
-          const uint16_t* src = (isv ? vc : kc) + (int64_t)phys * p.kv_block_stride + hf * (kUnitBytes / 2);
-          mbar_expect_tx(full + 8 * slot, kUnitBytes);
-          bulk_g2s(ring + slot * kUnitBytes, src, kUnitBytes, full + 8 * slot);
+          if (skip_last && blk == nblk - 1) {
+            mbar_arrive(full + 8 * slot);
+          } else {
+            const uint16_t* src = (isv ? vc : kc) + (int64_t)phys * p.kv_block_stride + hf * (kUnitBytes / 2);
+            mbar_expect_tx(full + 8 * slot, kUnitBytes);
+            bulk_g2s(ring + slot * kUnitBytes, src, kUnitBytes, full + 8 * slot);
+          }
           u += 4;
           if (u < nunits) { decode(u, isv, hf, blk); phys = bt[blk]; }  // table entry of the lane's next unit
         }

@@ -59,6 +59,10 @@ class HotPathConfig:
     # never the output of the previous kernel in the stream: lets consecutive attention launches overlap
     # (kvc_set_attention_pdl mode 2).  A model whose QKV GEMM feeds the attention kernel uses mode 1.
     inputs_independent: bool = True
+    # "device": blocks come from / return to the device-side allocator every step (kvc_alloc_*: free the
+    # compressed trailing blocks, allocate for heads crossing a block boundary, tables rewritten in place);
+    # "static": every head owns a fixed slab and only context_lens moves (round-1 harness)
+    allocator: str = "device"
     seed: int = 0
 
 
@@ -74,9 +78,15 @@ class DecodeHotPath:
         self.attention_pdl = capi.get_attention_pdl()
         S, L, H, B, D = cfg.num_seqs, cfg.num_layers, cfg.num_kv_heads, cfg.block_size, cfg.head_size
         self.launches = 0
-        st = W.make_state(S, L, H, B, D, cfg.max_cache_tokens, dtype=cfg.dtype, device=device,
-                          seed=cfg.seed, slack=1.0, max_blocks=cfg.blocks_per_head, fill_cache=True,
-                          blocks_per_head_alloc=cfg.blocks_per_head)
+        if cfg.allocator == "device":
+            # heads start with exactly ceil(ctx/B) scattered blocks; the rest of the cache is the free pool
+            st = W.make_state(S, L, H, B, D, cfg.max_cache_tokens, dtype=cfg.dtype, device=device,
+                              seed=cfg.seed, slack=float(cfg.blocks_per_head) / (cfg.max_cache_tokens // B),
+                              max_blocks=cfg.blocks_per_head, fill_cache=True)
+        else:
+            st = W.make_state(S, L, H, B, D, cfg.max_cache_tokens, dtype=cfg.dtype, device=device,
+                              seed=cfg.seed, slack=1.0, max_blocks=cfg.blocks_per_head, fill_cache=True,
+                              blocks_per_head_alloc=cfg.blocks_per_head)
         self.st = st
         # token positions of the surviving KVs: a random subset of the prompt (what a CR=64 eviction
         # leaves), newest `protected_window` tokens always present
@@ -115,6 +125,12 @@ class DecodeHotPath:
         self.arangeB = torch.arange(B, dtype=torch.int32, device=device)
         if not cfg.fused_metrics:
             self.temp_metrics = torch.zeros((st.NB, B, cfg.queries_per_kv), dtype=torch.float32, device=device)
+        self.alloc = None
+        if cfg.allocator == "device":
+            self.alloc = capi.DeviceBlockAllocator(st.NB, st.block_tables, st.context_lens, st.kv_position, B)
+            used = st.block_tables.view(heads, -1)[:, : n // B].reshape(-1).long()
+            self.alloc.free_mask[used] = False
+            self.alloc.free_count.fill_(st.NB - used.numel())
 
     # ------------------------------------------------------------------ compression
     def _budgets(self) -> torch.Tensor:
@@ -171,10 +187,17 @@ class DecodeHotPath:
         """free_compressed_blocks (block.py:184-210) + batch_append_slots (block_manager.py:269-294):
         one launch; then the sequence length advances."""
         cfg, st = self.cfg, self.st
-        ops.free_and_append_slots(st.context_lens, st.block_tables, self.evicted_block_count, self.hanging,
-                                  self.seq_len, self.slot_mapping, st.kv_position, cfg.block_size, True)
+        if self.alloc is not None:
+            # free_compressed_blocks (block_manager.py:466-530) then _append_to_sequence_batch (:269-294) against
+            # the device allocator: 1 + 3 launches, block tables rewritten in place
+            self.alloc.free_compressed(None, self.evicted_block_count)
+            self.alloc.append_slots(None, self.seq_len, self.slot_mapping)
+            self.launches += 4
+        else:
+            ops.free_and_append_slots(st.context_lens, st.block_tables, self.evicted_block_count, self.hanging,
+                                      self.seq_len, self.slot_mapping, st.kv_position, cfg.block_size, True)
+            self.launches += 1
         self.seq_len.add_(1)
-        self.launches += 1
 
     def forward_layer(self, l: int, x: torch.Tensor, o: torch.Tensor, last_pos: torch.Tensor,
                       timing=None) -> None:
