@@ -17,8 +17,9 @@ BLOCKMGR = load_cases("block_manager.npz")
 class CudaBlockManager:
     """Adapter with the oracle's method names over capi.DeviceBlockAllocator."""
 
-    def __init__(self, L, H, B, MS, MB, NB):
+    def __init__(self, L, H, B, MS, MB, NB, via="capi"):
         from vllm_kvcompress_b200 import capi
+        self.via = via
         dev = "cuda"
         self.L, self.H, self.B = L, H, B
         self.block_tables = torch.full((L, MS, H, MB), -1, dtype=torch.int32, device=dev)
@@ -33,17 +34,40 @@ class CudaBlockManager:
         return torch.tensor(x, dtype=torch.int32, device="cuda")
 
     def add_sequences(self, slots, lens):
+        if self.via == "torch":
+            from vllm_kvcompress_b200 import _custom_ops as ops
+            a = self.alloc
+            return ops.alloc_add_sequences(a.free_mask, a.free_count, a.status, self.block_tables, self.context_lens,
+                                           self._i(slots), self._i(lens), max(lens), self.token_positions, self.B,
+                                           *self.meta)
         self.alloc.add_sequences(self._i(slots), self._i(lens), max(lens))
 
     def append_slots(self, slots, positions):
         out = torch.full((self.L, len(slots), self.H), -1, dtype=torch.int64, device="cuda")
-        self.alloc.append_slots(self._i(slots), self._i(positions), out)
+        if self.via == "torch":
+            from vllm_kvcompress_b200 import _custom_ops as ops
+            a = self.alloc
+            ops.alloc_append_slots(a.free_mask, a.free_count, a.status, self.block_tables, self.context_lens,
+                                   self._i(slots), self._i(positions), out, self.token_positions, self.B, *self.meta)
+        else:
+            self.alloc.append_slots(self._i(slots), self._i(positions), out)
         return out.cpu().numpy()
 
     def free_compressed(self, slots, counts):
-        self.alloc.free_compressed(self._i(slots), torch.as_tensor(np.ascontiguousarray(counts, dtype=np.int32)).cuda())
+        counts = torch.as_tensor(np.ascontiguousarray(counts, dtype=np.int32)).cuda()
+        if self.via == "torch":
+            from vllm_kvcompress_b200 import _custom_ops as ops
+            a = self.alloc
+            return ops.alloc_free_compressed(a.free_mask, a.free_count, self.block_tables, self.context_lens, counts,
+                                             self._i(slots), self.B, self.meta[0])
+        self.alloc.free_compressed(self._i(slots), counts)
 
     def remove_sequences(self, slots):
+        if self.via == "torch":
+            from vllm_kvcompress_b200 import _custom_ops as ops
+            a = self.alloc
+            return ops.alloc_remove_sequences(a.free_mask, a.free_count, self.block_tables, self.context_lens,
+                                              self._i(slots), self.B, self.meta[0])
         self.alloc.remove_sequences(self._i(slots))
 
     def state(self):
@@ -52,11 +76,12 @@ class CudaBlockManager:
                 n(self.token_positions))
 
 
+@pytest.mark.parametrize("via", ["capi", "torch"])
 @pytest.mark.parametrize("name", sorted(BLOCKMGR))
-def test_block_manager_golden(name):
+def test_block_manager_golden(name, via):
     c = BLOCKMGR[name]
     L, H, B, MS, MB, NB = (int(c[k]) for k in ("L", "H", "B", "MS", "MB", "NB"))
-    mgr = CudaBlockManager(L, H, B, MS, MB, NB)
+    mgr = CudaBlockManager(L, H, B, MS, MB, NB, via=via)
 
     def check(i, pre):
         assert int(mgr.alloc.free_count.item()) == int(c[pre + "free_count"]), f"step {i}"

@@ -226,3 +226,51 @@ def aggregate_prefill(kv_metrics, prefill_metrics, slot_mapping) -> None:
     """ADDITIVE op: CompressionMetrics.aggregate_prefill (vllm/kvcompress/metrics.py:395-427) as one
     launch: kv_metrics[slot_mapping[t, h]] += prefill_metrics[t, h*Q:(h+1)*Q].sum()."""
     torch.ops._C_kvc_ops.aggregate_prefill(kv_metrics, prefill_metrics.contiguous(), slot_mapping.contiguous())
+
+
+# ---- ADDITIVE ops: device-side block allocator / block-state updates (include/kvc_b200.h kvc_alloc_*) ----
+# They operate IN PLACE on the reference's own state tensors: ParallelBlockAllocator.free_mask
+# (block_manager.py:101-103), BlockState.block_tables / context_lens (block.py:94-126) and the
+# CompressionMetrics metadata arrays (metrics.py:220-275); free_count / status are int32 [1] tensors.
+def alloc_init(free_mask, free_count, status) -> None:
+    """ParallelBlockAllocator.free_all (block_manager.py:127-129)."""
+    torch.ops._C_kvc_ops.alloc_init(free_mask, free_count, status)
+
+
+def alloc_append_slots(free_mask, free_count, status, block_tables, context_lens, seq_slots, seq_len,
+                       out_slot_mapping, token_positions, block_size: int, seq_index_by_block=None,
+                       layer_index_by_block=None, head_index_by_block=None,
+                       logical_block_num_by_block=None) -> None:
+    """BlockSpaceManagerKVC._append_to_sequence_batch (block_manager.py:269-294) + insert_metadata
+    (metrics.py:344-362) + BlockStateView.get_decode_slot_mapping (block.py:303-321) in 3 launches."""
+    torch.ops._C_kvc_ops.alloc_append_slots(free_mask, free_count, status, block_tables, context_lens, seq_slots,
+                                            seq_len, out_slot_mapping, token_positions, seq_index_by_block,
+                                            layer_index_by_block, head_index_by_block,
+                                            logical_block_num_by_block, block_size)
+
+
+def alloc_add_sequences(free_mask, free_count, status, block_tables, context_lens, seq_slots, seq_lens,
+                        max_seq_len: int, token_positions, block_size: int, seq_index_by_block=None,
+                        layer_index_by_block=None, head_index_by_block=None,
+                        logical_block_num_by_block=None) -> None:
+    """BlockSpaceManagerKVC._add_sequence (block_manager.py:196-222) for a batch of prompts."""
+    torch.ops._C_kvc_ops.alloc_add_sequences(free_mask, free_count, status, block_tables, context_lens, seq_slots,
+                                             seq_lens, max_seq_len, token_positions, seq_index_by_block,
+                                             layer_index_by_block, head_index_by_block,
+                                             logical_block_num_by_block, block_size)
+
+
+def alloc_free_compressed(free_mask, free_count, block_tables, context_lens, evicted_block_count, seq_slots,
+                          block_size: int, seq_index_by_block=None) -> None:
+    """BlockSpaceManagerKVC.free_compressed_blocks (block_manager.py:466-530) + remove_trailing_blocks
+    (block.py:184-210) + remove_metadata (metrics.py:364-370)."""
+    torch.ops._C_kvc_ops.alloc_free_compressed(free_mask, free_count, block_tables, context_lens,
+                                               evicted_block_count.contiguous(), seq_slots, seq_index_by_block,
+                                               block_size)
+
+
+def alloc_remove_sequences(free_mask, free_count, block_tables, context_lens, seq_slots, block_size: int,
+                           seq_index_by_block=None) -> None:
+    """BlockSpaceManagerKVC._remove_sequence_batch (block_manager.py:243-262)."""
+    torch.ops._C_kvc_ops.alloc_remove_sequences(free_mask, free_count, block_tables, context_lens, seq_slots,
+                                                seq_index_by_block, block_size)

@@ -120,37 +120,11 @@ __device__ __forceinline__ void load_keys8(const SelectParams& p, const int* __r
   }
 }
 
-// ---- warp-per-head path (ctx <= 256): bitonic sort of 256 keys, 8 per lane ----
-// element e = lane * 8 + r  <->  logical slot e.
-template <int B, int KPL>
-__global__ void __launch_bounds__(128) select_sort_kernel(SelectParams p) {
-  const int lane = threadIdx.x % kWarp;
-  const int g = blockIdx.x * 4 + threadIdx.x / kWarp;
-  if (g >= p.S * p.L * p.H) return;
-  const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
-  const int lsh = (l * p.S + s) * p.H + h;
-  const int n = p.context_lens[lsh];
-  const int nblk = (n + B - 1) / B;
-  const int off = p.offsets[g];
-  const int r0 = p.hanging[g];
-  const int last_pos = p.last_position[s];
-  const int max_pos = last_pos - p.protected_window[s];
-  constexpr int N = 32 * KPL;  // keys sorted by the warp (256 or 512)
-  unsigned k[KPL];
-#pragma unroll
-  for (int q = 0; q < KPL / 8; ++q) {
-    unsigned t8[8];
-    load_keys8<B>(p, p.block_tables + (int64_t)lsh * p.MB, lane * KPL + 8 * q, n, max_pos, last_pos, l, h, t8);
-#pragma unroll
-    for (int r = 0; r < 8; ++r) k[8 * q + r] = t8[r];
-  }
-  int local = 0;
-#pragma unroll
-  for (int r = 0; r < KPL; ++r) local += (k[r] != kInfKey);
-  int ncand = local;
-#pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) ncand += __shfl_xor_sync(0xffffffffu, ncand, d);
-  // bitonic sort, ascending over e = lane*KPL + r
+// ---- warp-per-head path (ctx <= 512): bitonic sort of the head's CANDIDATE keys in registers ----
+// ascending bitonic sort of 32*KPL keys, element e = lane * KPL + r
+template <int KPL>
+__device__ __forceinline__ void warp_bitonic_sort(unsigned (&k)[KPL], int lane) {
+  constexpr int N = 32 * KPL;
 #pragma unroll
   for (int kk = 2; kk <= N; kk <<= 1) {
 #pragma unroll
@@ -180,14 +154,85 @@ __global__ void __launch_bounds__(128) select_sort_kernel(SelectParams p) {
       }
     }
   }
-  // completion keys: sorted rank e = r0-1 + kB for k < nev
-  const int nev = (r0 >= 1 && ncand >= r0) ? (ncand - r0) / B + 1 : 0;
-  unsigned* ev = p.events + off / B;
+}
+
+// completion keys = sorted ranks r0-1 + kB (k < nev) of a warp-sorted key set
+template <int B, int KPL>
+__device__ __forceinline__ void write_completion_keys(const unsigned (&k)[KPL], int lane, int r0, int nev,
+                                                      unsigned* ev) {
 #pragma unroll
   for (int r = 0; r < KPL; ++r) {
     const int e = lane * KPL + r;
     const int d = e - (r0 - 1);
     if (d >= 0 && d % B == 0 && d / B < nev) ev[d / B] = k[r];
+  }
+}
+
+// Only candidates can carry a completion key, and the protected window / the slack of the last block
+// usually leave fewer than half of the loaded slots as candidates: the candidate keys are compacted
+// through the warp's shared-memory row first, and the sort runs on the smallest power of two that
+// holds them (a 128-key network costs ~45 % of the 256-key one).
+template <int B, int KPL>
+__global__ void __launch_bounds__(128) select_sort_kernel(SelectParams p) {
+  __shared__ unsigned s_keys[4][32 * KPL];
+  const int lane = threadIdx.x % kWarp, w = threadIdx.x / kWarp;
+  const int g = blockIdx.x * 4 + w;
+  if (g >= p.S * p.L * p.H) return;
+  const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
+  const int lsh = (l * p.S + s) * p.H + h;
+  const int n = p.context_lens[lsh];
+  const int nblk = (n + B - 1) / B;
+  const int off = p.offsets[g];
+  const int r0 = p.hanging[g];
+  const int last_pos = p.last_position[s];
+  const int max_pos = last_pos - p.protected_window[s];
+  unsigned k[KPL];
+#pragma unroll
+  for (int q = 0; q < KPL / 8; ++q) {
+    unsigned t8[8];
+    load_keys8<B>(p, p.block_tables + (int64_t)lsh * p.MB, lane * KPL + 8 * q, n, max_pos, last_pos, l, h, t8);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) k[8 * q + r] = t8[r];
+  }
+  int local = 0;
+#pragma unroll
+  for (int r = 0; r < KPL; ++r) local += (k[r] != kInfKey);
+  int incl = local;
+#pragma unroll
+  for (int d = 1; d < kWarp; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const int ncand = __shfl_sync(0xffffffffu, incl, 31);
+  const int nev = (r0 >= 1 && ncand >= r0) ? (ncand - r0) / B + 1 : 0;
+  unsigned* ev = p.events + off / B;
+  if (nev > 0) {  // warp-uniform
+    if (ncand <= 32 * (KPL / 2)) {
+      // compact the candidates, pad with inf, sort half (or a quarter) as many keys
+      unsigned* row = s_keys[w];
+      int pos = incl - local;
+#pragma unroll
+      for (int r = 0; r < KPL; ++r)
+        if (k[r] != kInfKey) row[pos++] = k[r];
+      for (int i = ncand + lane; i < 32 * (KPL / 2); i += kWarp) row[i] = kInfKey;
+      __syncwarp();
+      if (KPL >= 16 && ncand <= 32 * (KPL / 4)) {
+        unsigned kq[KPL / 4 > 0 ? KPL / 4 : 1];
+#pragma unroll
+        for (int r = 0; r < KPL / 4; ++r) kq[r] = row[lane * (KPL / 4) + r];
+        warp_bitonic_sort<(KPL / 4 > 0 ? KPL / 4 : 1)>(kq, lane);
+        write_completion_keys<B, (KPL / 4 > 0 ? KPL / 4 : 1)>(kq, lane, r0, nev, ev);
+      } else {
+        unsigned kh[KPL / 2];
+#pragma unroll
+        for (int r = 0; r < KPL / 2; ++r) kh[r] = row[lane * (KPL / 2) + r];
+        warp_bitonic_sort<KPL / 2>(kh, lane);
+        write_completion_keys<B, KPL / 2>(kh, lane, r0, nev, ev);
+      }
+    } else {
+      warp_bitonic_sort<KPL>(k, lane);
+      write_completion_keys<B, KPL>(k, lane, r0, nev, ev);
+    }
   }
   for (int q = nev + lane; q < nblk; q += kWarp) ev[q] = kInfKey;
 }

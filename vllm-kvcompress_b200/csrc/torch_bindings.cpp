@@ -265,6 +265,122 @@ void aggregate_prefill(torch::Tensor& kv_metrics, torch::Tensor& prefill_metrics
                "aggregate_prefill");
 }
 
+}  // namespace
+
+// additive ops: device-side block allocator (include/kvc_b200.h kvc_alloc_*).  `state` tensors are the
+// reference's own: free_mask [NB] bool, block_tables [L,MS,H,MB], context_lens [L,MS,H], token positions.
+namespace {
+struct AllocState {
+  uint8_t* free_mask;
+  int* free_count;
+  int* status;
+  int64_t num_blocks;
+  int L, MS, H, MB;
+};
+inline AllocState alloc_state(torch::Tensor& free_mask, torch::Tensor& free_count, torch::Tensor& status,
+                              torch::Tensor& block_tables, torch::Tensor& context_lens) {
+  TORCH_CHECK(free_mask.is_cuda() && free_mask.is_contiguous() &&
+                  (free_mask.scalar_type() == at::kBool || free_mask.scalar_type() == at::kByte),
+              "free_mask must be a contiguous bool CUDA tensor");
+  TORCH_CHECK(block_tables.dim() == 4 && context_lens.dim() == 3, "block_tables [L,S,H,MB], context_lens [L,S,H] expected");
+  AllocState a;
+  a.free_mask = reinterpret_cast<uint8_t*>(free_mask.data_ptr());
+  a.free_count = i32_mut(free_count, "free_count");
+  a.status = i32_mut(status, "status");
+  a.num_blocks = free_mask.numel();
+  a.L = block_tables.size(0); a.MS = block_tables.size(1); a.H = block_tables.size(2); a.MB = block_tables.size(3);
+  return a;
+}
+inline int* opt_i32(const c10::optional<torch::Tensor>& t, const char* name) {
+  return t ? const_cast<int*>(i32(t.value(), name)) : nullptr;
+}
+}  // namespace
+
+void alloc_init(torch::Tensor& free_mask, torch::Tensor& free_count, torch::Tensor& status) {
+  const at::cuda::OptionalCUDAGuard guard(device_of(free_mask));
+  check_status(kvc_alloc_init(reinterpret_cast<uint8_t*>(free_mask.data_ptr()), i32_mut(free_count, "free_count"),
+                              i32_mut(status, "status"), free_mask.numel(), cur_stream()),
+               "alloc_init");
+}
+
+void alloc_append_slots(torch::Tensor& free_mask, torch::Tensor& free_count, torch::Tensor& status,
+                        torch::Tensor& block_tables, torch::Tensor& context_lens,
+                        const c10::optional<torch::Tensor>& seq_slots, torch::Tensor& seq_len,
+                        torch::Tensor& slot_mapping, torch::Tensor& kv_position,
+                        const c10::optional<torch::Tensor>& seq_index_by_block,
+                        const c10::optional<torch::Tensor>& layer_index_by_block,
+                        const c10::optional<torch::Tensor>& head_index_by_block,
+                        const c10::optional<torch::Tensor>& logical_block_num_by_block, int64_t block_size) {
+  AllocState a = alloc_state(free_mask, free_count, status, block_tables, context_lens);
+  TORCH_CHECK(slot_mapping.scalar_type() == at::kLong && slot_mapping.is_contiguous(), "slot_mapping must be contiguous int64");
+  const int n = seq_len.numel();
+  const at::cuda::OptionalCUDAGuard guard(device_of(free_mask));
+  const size_t ws_bytes = kvc_alloc_workspace_bytes(a.num_blocks, n, a.L, a.H);
+  auto ws = torch::empty({(int64_t)ws_bytes + 1}, free_mask.options().dtype(at::kByte));
+  check_status(kvc_alloc_append_slots(a.free_mask, a.free_count, a.status, a.num_blocks, i32_mut(block_tables, "block_tables"),
+                                      i32_mut(context_lens, "context_lens"), opt_i32(seq_slots, "seq_slots"),
+                                      i32(seq_len, "seq_len"), slot_mapping.data_ptr<int64_t>(),
+                                      i32_mut(kv_position, "kv_position"), opt_i32(seq_index_by_block, "seq_index_by_block"),
+                                      opt_i32(layer_index_by_block, "layer_index_by_block"),
+                                      opt_i32(head_index_by_block, "head_index_by_block"),
+                                      opt_i32(logical_block_num_by_block, "logical_block_num_by_block"), n, a.MS, a.L, a.H,
+                                      a.MB, (int)block_size, ws.data_ptr(), ws_bytes, cur_stream()),
+               "alloc_append_slots");
+}
+
+void alloc_add_sequences(torch::Tensor& free_mask, torch::Tensor& free_count, torch::Tensor& status,
+                         torch::Tensor& block_tables, torch::Tensor& context_lens, torch::Tensor& seq_slots,
+                         torch::Tensor& seq_lens, int64_t max_seq_len, torch::Tensor& kv_position,
+                         const c10::optional<torch::Tensor>& seq_index_by_block,
+                         const c10::optional<torch::Tensor>& layer_index_by_block,
+                         const c10::optional<torch::Tensor>& head_index_by_block,
+                         const c10::optional<torch::Tensor>& logical_block_num_by_block, int64_t block_size) {
+  AllocState a = alloc_state(free_mask, free_count, status, block_tables, context_lens);
+  const at::cuda::OptionalCUDAGuard guard(device_of(free_mask));
+  const size_t ws_bytes = kvc_alloc_workspace_bytes(a.num_blocks, 0, a.L, a.H);
+  auto ws = torch::empty({(int64_t)ws_bytes + 1}, free_mask.options().dtype(at::kByte));
+  check_status(kvc_alloc_add_sequences(a.free_mask, a.free_count, a.status, a.num_blocks, i32_mut(block_tables, "block_tables"),
+                                       i32_mut(context_lens, "context_lens"), i32(seq_slots, "seq_slots"),
+                                       i32(seq_lens, "seq_lens"), i32_mut(kv_position, "kv_position"),
+                                       opt_i32(seq_index_by_block, "seq_index_by_block"),
+                                       opt_i32(layer_index_by_block, "layer_index_by_block"),
+                                       opt_i32(head_index_by_block, "head_index_by_block"),
+                                       opt_i32(logical_block_num_by_block, "logical_block_num_by_block"),
+                                       (int)seq_lens.numel(), (int)max_seq_len, a.MS, a.L, a.H, a.MB, (int)block_size,
+                                       ws.data_ptr(), ws_bytes, cur_stream()),
+               "alloc_add_sequences");
+}
+
+void alloc_free_compressed(torch::Tensor& free_mask, torch::Tensor& free_count, torch::Tensor& block_tables,
+                           torch::Tensor& context_lens, torch::Tensor& evicted_block_count,
+                           const c10::optional<torch::Tensor>& seq_slots,
+                           const c10::optional<torch::Tensor>& seq_index_by_block, int64_t block_size) {
+  TORCH_CHECK(evicted_block_count.dim() == 3, "evicted_block_count must be [num_batch, num_layers, num_kv_heads]");
+  TORCH_CHECK(block_tables.dim() == 4, "block_tables [L,S,H,MB] expected");
+  const at::cuda::OptionalCUDAGuard guard(device_of(free_mask));
+  check_status(kvc_alloc_free_compressed(reinterpret_cast<uint8_t*>(free_mask.data_ptr()), i32_mut(free_count, "free_count"),
+                                         i32(block_tables, "block_tables"), i32_mut(context_lens, "context_lens"),
+                                         i32(evicted_block_count, "evicted_block_count"), opt_i32(seq_slots, "seq_slots"),
+                                         opt_i32(seq_index_by_block, "seq_index_by_block"), evicted_block_count.size(0),
+                                         block_tables.size(1), block_tables.size(0), block_tables.size(2),
+                                         block_tables.size(3), (int)block_size, cur_stream()),
+               "alloc_free_compressed");
+}
+
+void alloc_remove_sequences(torch::Tensor& free_mask, torch::Tensor& free_count, torch::Tensor& block_tables,
+                            torch::Tensor& context_lens, torch::Tensor& seq_slots,
+                            const c10::optional<torch::Tensor>& seq_index_by_block, int64_t block_size) {
+  TORCH_CHECK(block_tables.dim() == 4, "block_tables [L,S,H,MB] expected");
+  const at::cuda::OptionalCUDAGuard guard(device_of(free_mask));
+  check_status(kvc_alloc_remove_sequences(reinterpret_cast<uint8_t*>(free_mask.data_ptr()), i32_mut(free_count, "free_count"),
+                                          i32(block_tables, "block_tables"), i32_mut(context_lens, "context_lens"),
+                                          i32(seq_slots, "seq_slots"), opt_i32(seq_index_by_block, "seq_index_by_block"),
+                                          (int)seq_slots.numel(), block_tables.size(1), block_tables.size(0),
+                                          block_tables.size(2), block_tables.size(3), (int)block_size, cur_stream()),
+               "alloc_remove_sequences");
+}
+
+namespace {
 // additive ops: see include/kvc_b200.h kvc_prepare_compression / kvc_free_and_append_slots
 void prepare_compression(torch::Tensor& context_lens, torch::Tensor& hanging_token_count,
                          torch::Tensor& evicted_kv_offsets, torch::Tensor& evicted_blocks_per_seq,
@@ -611,6 +727,29 @@ TORCH_LIBRARY_FRAGMENT(_C_kvc_ops, kvc_ops) {
   kvc_ops.impl("prefill_kv_metrics", torch::kCUDA, &prefill_kv_metrics);
   kvc_ops.def("aggregate_prefill(Tensor! kv_metrics, Tensor prefill_metrics, Tensor slot_mapping) -> ()");
   kvc_ops.impl("aggregate_prefill", torch::kCUDA, &aggregate_prefill);
+  kvc_ops.def("alloc_init(Tensor! free_mask, Tensor! free_count, Tensor! status) -> ()");
+  kvc_ops.impl("alloc_init", torch::kCUDA, &alloc_init);
+  kvc_ops.def(
+      "alloc_append_slots(Tensor! free_mask, Tensor! free_count, Tensor! status, Tensor! block_tables,"
+      "                    Tensor! context_lens, Tensor? seq_slots, Tensor seq_len, Tensor! slot_mapping,"
+      "                    Tensor! kv_position, Tensor(a!)? seq_index_by_block, Tensor(b!)? layer_index_by_block,"
+      "                    Tensor(c!)? head_index_by_block, Tensor(d!)? logical_block_num_by_block, int block_size) -> ()");
+  kvc_ops.impl("alloc_append_slots", torch::kCUDA, &alloc_append_slots);
+  kvc_ops.def(
+      "alloc_add_sequences(Tensor! free_mask, Tensor! free_count, Tensor! status, Tensor! block_tables,"
+      "                     Tensor! context_lens, Tensor seq_slots, Tensor seq_lens, int max_seq_len,"
+      "                     Tensor! kv_position, Tensor(a!)? seq_index_by_block, Tensor(b!)? layer_index_by_block,"
+      "                     Tensor(c!)? head_index_by_block, Tensor(d!)? logical_block_num_by_block, int block_size) -> ()");
+  kvc_ops.impl("alloc_add_sequences", torch::kCUDA, &alloc_add_sequences);
+  kvc_ops.def(
+      "alloc_free_compressed(Tensor! free_mask, Tensor! free_count, Tensor block_tables, Tensor! context_lens,"
+      "                       Tensor evicted_block_count, Tensor? seq_slots, Tensor(a!)? seq_index_by_block,"
+      "                       int block_size) -> ()");
+  kvc_ops.impl("alloc_free_compressed", torch::kCUDA, &alloc_free_compressed);
+  kvc_ops.def(
+      "alloc_remove_sequences(Tensor! free_mask, Tensor! free_count, Tensor block_tables, Tensor! context_lens,"
+      "                        Tensor seq_slots, Tensor(a!)? seq_index_by_block, int block_size) -> ()");
+  kvc_ops.impl("alloc_remove_sequences", torch::kCUDA, &alloc_remove_sequences);
 }
 
 // importable as a Python module named _C, like the reference's REGISTER_EXTENSION
