@@ -52,6 +52,7 @@ def parse():
                     help="device = blocks freed/allocated every step by the device-side allocator")
     ap.add_argument("--unfused-metrics", action="store_true")
     ap.add_argument("--separate-cache-write", action="store_true", help="K6 as its own launch per layer")
+    ap.add_argument("--host-copy-layers", type=int, default=4, help="e2e: layers per H2D / D2H copy")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-compaction", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=16)
@@ -277,7 +278,8 @@ def main():
         args.layers = 80
         preset = dict(queries_per_kv=8, max_cache_tokens=368, blocks_per_head=28)
     cfg = HotPathConfig(num_seqs=args.batch, num_layers=args.layers, selection=args.selection,
-                        fused_metrics=not args.unfused_metrics, allocator=args.allocator, **preset,
+                        fused_metrics=not args.unfused_metrics, allocator=args.allocator,
+                        host_copy_layers=args.host_copy_layers, **preset,
                         fused_cache_write=not args.separate_cache_write, seed=rank)
     from vllm_kvcompress_b200 import sharding
     # the only collective on this path: one start-up broadcast (stands in for the weight broadcast
