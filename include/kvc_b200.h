@@ -290,6 +290,46 @@ KVC_API int kvc_paged_attention_fused_step(
     size_t workspace_bytes, kvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------
+ * Additive: deferred append.  In the steady state of continual compression every head sits on a
+ * block boundary after each compression (block.py:184-210), so the step's new token opens a fresh
+ * block -- 128 + 16 partial-sector stores (a 4.6 KB fill + 4.6 KB write-back in DRAM) -- and the next
+ * compression moves exactly that token into an evicted slot and frees the block again
+ * (kvcompress_eviction_kernels.cu:252-288 emits the newest surviving token first), reading the 4 KB
+ * block back for 512 useful bytes.  With these two entry points such a token is parked instead in a
+ * compact side buffer and stored once, where it finally belongs:
+ *   kvc_paged_attention_fused_step_deferred: as kvc_paged_attention_fused_step; a new token whose
+ *     slot is the first of its block goes to pend_kv [S, H, 2*D] (K | V, cache dtype) with
+ *     pend_slot [S, H] = slot (int64); every other head gets pend_slot = -1 and the ordinary store.
+ *     Metric (head bias) and position of the slot are written as usual.
+ *   kvc_execute_cache_moves_deferred: as kvc_execute_cache_moves with pend_kv [L, S, H, 2*D] /
+ *     pend_slot [L, S, H]: a move whose source is the head's pending slot copies from pend_kv; a
+ *     pending token that no move consumes is stored to its own slot.  On completion the cache is
+ *     bit-identical to what reshape_and_cache + execute_cache_moves leave.  Must run before anything
+ *     else reads K/V of the pending slots (the fused step kernel itself patches the staged block from
+ *     registers).  Production layout only (2-byte cache, D=128, B=16, x=8).
+ * ------------------------------------------------------------------------- */
+KVC_API int kvc_paged_attention_fused_step_deferred(
+    void* out, float* kv_metrics, const void* query, const void* key,
+    const void* value, void* key_cache, void* value_cache,
+    const int64_t* slot_mapping, const float* kv_metric_head_bias,
+    void* pend_kv, int64_t* pend_slot, int num_seqs,
+    int num_heads, int num_kv_heads, int head_size, float scale,
+    const int* block_tables, const int* context_lens, const int* kv_position,
+    const int* last_position, const int* kv_metric_buffer_len, int block_size,
+    int max_context_len, int max_num_blocks_per_seq, int64_t q_stride,
+    int64_t key_stride, int64_t value_stride, int64_t kv_block_stride,
+    const float* alibi_slopes, int dtype /* kvc_dtype */, void* workspace,
+    size_t workspace_bytes, kvc_stream_t stream);
+
+KVC_API int kvc_execute_cache_moves_deferred(
+    void* k_cache, void* v_cache, float* kv_metrics, int* kv_position,
+    const int* cache_moves_idx, const int* cache_moves_count,
+    const int* evicted_kv_offsets, const void* pend_kv, const int64_t* pend_slot,
+    int num_seqs, int num_layers, int num_kv_heads, int64_t num_blocks,
+    int head_size, int vec_size, int block_size, int dtype /* kvc_dtype */,
+    kvc_stream_t stream);
+
+/* ---------------------------------------------------------------------------
  * Launch mode of the streaming decode-attention kernel (process-wide; initial value from the
  * environment variable KVC_ATTN_PDL, default 1):
  *   0  plain stream-ordered launches.

@@ -35,11 +35,10 @@ def test_device_allocator_is_invisible_to_results(graph):
     out_a = torch.zeros((L, S, H * Q * D), device=dev, dtype=cfg.dtype)
     out_b = torch.zeros_like(out_a)
     if graph:
-        state = lambda e: [t.clone() for t in (e.st.k_cache, e.st.v_cache, e.st.kv_metrics, e.st.kv_position,
-                                               e.st.context_lens, e.st.block_tables, e.seq_len)]
-        restore = lambda e, s: [t.copy_(v) for t, v in zip((e.st.k_cache, e.st.v_cache, e.st.kv_metrics,
-                                                            e.st.kv_position, e.st.context_lens,
-                                                            e.st.block_tables, e.seq_len), s)]
+        tensors = lambda e: (e.st.k_cache, e.st.v_cache, e.st.kv_metrics, e.st.kv_position, e.st.context_lens,
+                             e.st.block_tables, e.seq_len) + ((e.pend_kv, e.pend_slot) if e.deferred else ())
+        state = lambda e: [t.clone() for t in tensors(e)]
+        restore = lambda e, s: [t.copy_(v) for t, v in zip(tensors(e), s)]
         sa, sb = state(a), state(b)
         fm = b.alloc.free_mask.clone(), b.alloc.free_count.clone()
         assert a.capture(qkv, out_a) and b.capture(qkv, out_b)   # capture runs the step: rewind the state
@@ -72,3 +71,74 @@ def test_device_allocator_is_invisible_to_results(graph):
     assert live_blocks.unique().numel() == live_blocks.numel()
     assert not b.alloc.free_mask[live_blocks].any()
     assert int(b.alloc.free_count.item()) == int(b.alloc.free_mask.sum()) == b.st.NB - live_blocks.numel()
+
+
+@pytest.mark.parametrize("shape", [dict(num_seqs=2, num_layers=2), dict(num_seqs=5, num_layers=3),
+                                   dict(num_seqs=40, num_layers=32)])
+@pytest.mark.parametrize("graph", [False, True])
+def test_deferred_append_is_invisible_to_results(shape, graph):
+    """Deferred append (new tokens that open a fresh block are parked in a compact buffer and stored by the
+    next execute_cache_moves_deferred) against the plain fused step on the same allocator: identical
+    attention outputs, tables and context lengths every step, and after flush_pending() bit-identical
+    K / V / metrics / positions in every live slot.  Shapes cover gridDim.y > 1 (few heads: several warps
+    share a head's move list) and the one-warp-per-head launch of the benchmark."""
+    from vllm_kvcompress_b200.engine import DecodeHotPath, HotPathConfig
+    dev = torch.device("cuda", 0)
+    kw = dict(max_cache_tokens=64, blocks_per_head=8, protected_window=16, seed=11, **shape)
+    a = DecodeHotPath(HotPathConfig(deferred_append=False, **kw), dev)
+    b = DecodeHotPath(HotPathConfig(deferred_append=True, **kw), dev)
+    assert b.deferred and not a.deferred
+    for name in ("k_cache", "v_cache", "kv_metrics", "kv_position"):
+        assert torch.equal(getattr(a.st, name), getattr(b.st, name))
+    cfg = a.cfg
+    H, Q, D, L, S = cfg.num_kv_heads, cfg.queries_per_kv, cfg.head_size, cfg.num_layers, cfg.num_seqs
+    g = torch.Generator(device=dev).manual_seed(6)
+    steps = 36
+    nvar = 4
+    qkv_all = (torch.rand((nvar, L, S, (H * Q + 2 * H) * D), generator=g, device=dev) - 0.5).to(cfg.dtype)
+    qkv = qkv_all[0].clone()
+    out_a = torch.zeros((L, S, H * Q * D), device=dev, dtype=cfg.dtype)
+    out_b = torch.zeros_like(out_a)
+    if graph:
+        def tensors(e):
+            t = (e.st.k_cache, e.st.v_cache, e.st.kv_metrics, e.st.kv_position, e.st.context_lens,
+                 e.st.block_tables, e.seq_len, e.alloc.free_mask, e.alloc.free_count)
+            return t + ((e.pend_kv, e.pend_slot) if e.deferred else ())
+        sa, sb = [t.clone() for t in tensors(a)], [t.clone() for t in tensors(b)]
+        assert a.capture(qkv, out_a) and b.capture(qkv, out_b)
+        [t.copy_(v) for t, v in zip(tensors(a), sa)]
+        [t.copy_(v) for t, v in zip(tensors(b), sb)]
+
+    def live_equal(tag):
+        nblk = (a.st.context_lens.view(-1) + 15) // 16
+        bt = a.st.block_tables.view(-1, a.st.block_tables.shape[-1])
+        mask = torch.arange(bt.shape[1], device=dev)[None] < nblk[:, None]
+        blocks = bt[mask].long()
+        tok = (torch.arange(bt.shape[1] * 16, device=dev)[None] < a.st.context_lens.view(-1)[:, None])
+        tok = tok.view(-1, bt.shape[1], 16)[mask]                                    # [live blocks, 16]
+        assert torch.equal(a.st.kv_metrics[blocks][tok], b.st.kv_metrics[blocks][tok]), tag
+        assert torch.equal(a.st.kv_position[blocks][tok], b.st.kv_position[blocks][tok]), tag
+        ka = a.st.k_cache[blocks].permute(0, 2, 1, 3)[tok]                           # [tokens, D/x, x]
+        kb = b.st.k_cache[blocks].permute(0, 2, 1, 3)[tok]
+        assert torch.equal(ka, kb), tag
+        va = a.st.v_cache[blocks].permute(0, 2, 1)[tok]                              # [tokens, D]
+        vb = b.st.v_cache[blocks].permute(0, 2, 1)[tok]
+        assert torch.equal(va, vb), tag
+
+    parked = 0
+    for i in range(steps):
+        qkv.copy_(qkv_all[i % nvar])
+        if graph:
+            a.replay(), b.replay()
+        else:
+            a.step(qkv, out_a), b.step(qkv, out_b)
+        torch.cuda.synchronize()
+        assert torch.equal(a.st.context_lens, b.st.context_lens), f"step {i}"
+        assert torch.equal(a.st.block_tables, b.st.block_tables), f"step {i}"
+        assert torch.equal(out_a, out_b), f"step {i}"
+        parked += int((b.pend_slot >= 0).sum())
+        if i % 7 == 6 or i == steps - 1:
+            b.flush_pending()
+            torch.cuda.synchronize()
+            live_equal(f"after flush at step {i}")
+    assert parked > 0

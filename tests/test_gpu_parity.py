@@ -727,3 +727,97 @@ def test_fused_step_equals_cache_write_then_attention(capi, cfg):
     assert torch.equal(v1.view(torch.int16), v2.view(torch.int16))
     torch.testing.assert_close(out2.float(), out1.float(), atol=1e-3, rtol=1e-2)
     torch.testing.assert_close(m2, m1, atol=1e-6, rtol=1e-4)
+
+
+@pytest.mark.parametrize("deferred", [False, True])
+@pytest.mark.parametrize("fullrow", ["0", "1"])
+def test_execute_moves_many_heads_small_counts_vs_oracle(capi, O, deferred, fullrow):
+    """>= 4096 heads (the launch splits: heads with <= 1 move go to the light kernel, the rest to the run
+    kernel) with 0..5 moves per head, bit-exact against the C oracle.  deferred: every other head's newest
+    token is parked in pend_kv instead of the cache (garbage at its cache slot); the op must leave the cache
+    as if the token had been stored first -- except at the source slot of a parked token that a move consumed:
+    that slot is never written (its block is freed right after the compression), so it is left out."""
+    import subprocess, sys, textwrap
+    # KVC_MOVES_FULLROW is read once per process: run the body in a child so that both settings are covered
+    code = textwrap.dedent(f"""
+        import numpy as np, torch, sys
+        sys.path.insert(0, {ROOT!r})
+        from oracle import kvc_oracle as O
+        from vllm_kvcompress_b200 import capi
+        O.build()
+        rs = np.random.RandomState(5)
+        S, L, H, B, D = 6, 12, 64, 16, 128          # 4608 heads
+        heads = S * L * H
+        blocks_per_head = 3
+        NB = heads * blocks_per_head + 7
+        perm = rs.permutation(NB)[: heads * blocks_per_head].reshape(heads, blocks_per_head)
+        kc = rs.randint(0, 65536, size=(NB, D // 8, B, 8)).astype(np.uint16)
+        vc = rs.randint(0, 65536, size=(NB, D, B)).astype(np.uint16)
+        km = rs.rand(NB, B).astype(np.float32)
+        kp = rs.randint(0, 6000, size=(NB, B)).astype(np.int32)
+        cnt = rs.choice([0, 1, 1, 1, 2, 3, 5], size=heads).astype(np.int32)
+        offs = (np.arange(heads) * blocks_per_head * B).astype(np.int32)
+        moves = np.zeros((heads * blocks_per_head * B, 2), np.int32)
+        pend_slot = np.full(heads, -1, np.int64)
+        consumed = []
+        for g in range(heads):
+            # destinations in the first two blocks, sources in the last block (descending, like K4)
+            ctx_tail = rs.randint(1, B + 1)          # tokens in the last block
+            n = min(int(cnt[g]), ctx_tail)
+            cnt[g] = n
+            dst = np.sort(rs.choice(2 * B, size=n, replace=False))
+            top = ctx_tail - 1 if rs.rand() < 0.7 else rs.randint(max(n - 1, 0), ctx_tail)  # else: newest token may stay
+            src = 2 * B + (top - np.arange(n))
+            phys = lambda i: perm[g, i // B] * B + i % B
+            for k in range(n):
+                moves[offs[g] + k] = (phys(dst[k]), phys(src[k]))
+            if g % 2 == 0:
+                pend_slot[g] = phys(2 * B + ctx_tail - 1)     # the head's newest token
+                if n and top == ctx_tail - 1:
+                    consumed.append(pend_slot[g])
+        # oracle on the canonical cache
+        wk, wv, wm, wp = kc.copy(), vc.copy(), km.copy(), kp.copy()
+        O.execute_cache_moves(wk, wv, wm, wp, moves, cnt.reshape(S, L, H), offs.reshape(S, L, H))
+        dev = "cuda"
+        t16 = lambda a: torch.as_tensor(a.view(np.int16)).to(dev).view(torch.float16)
+        gk, gv = t16(kc), t16(vc)
+        gm, gp = torch.as_tensor(km).to(dev), torch.as_tensor(kp).to(dev)
+        gmoves, gcnt, goffs = (torch.as_tensor(moves).to(dev), torch.as_tensor(cnt.reshape(S, L, H)).to(dev),
+                               torch.as_tensor(offs.reshape(S, L, H)).to(dev))
+        if {deferred!r}:
+            # pend arrays are [L, S, H]; head g = (s * L + l) * H + h
+            ps = torch.as_tensor(pend_slot.reshape(S, L, H)).permute(1, 0, 2).contiguous().to(dev)
+            pkv = torch.zeros((L, S, H, 2 * D), dtype=torch.float16, device=dev)
+            sl = ps.clamp(min=0)
+            kflat = gk.permute(0, 2, 1, 3).reshape(NB * B, D)      # [slot, D]
+            vflat = gv.permute(0, 2, 1).reshape(NB * B, D)
+            pkv[..., :D] = kflat[sl]
+            pkv[..., D:] = vflat[sl]
+            # scribble over the cache copy of every parked token: the op must not depend on it
+            live = ps.reshape(-1)[ps.reshape(-1) >= 0]
+            kview = gk.view(torch.int16)
+            vview = gv.view(torch.int16)
+            blk, o = live // B, live % B
+            kview[blk, :, o, :] = 0x7e00
+            vview[blk, :, o] = 0x7e00
+            capi.execute_cache_moves_deferred(gk, gv, gm, gp, gmoves, gcnt, goffs, pkv, ps)
+        else:
+            capi.execute_cache_moves(gk, gv, gm, gp, gmoves, gcnt, goffs)
+        torch.cuda.synchronize()
+        b16 = lambda t: t.view(torch.int16).cpu().numpy().view(np.uint16)
+        rk, rv = b16(gk), b16(gv)
+        if {deferred!r}:
+            assert len(consumed) > 500
+            c = np.asarray(consumed)
+            assert (rk[c // B, :, c % B, :] == 0x7e00).all() and (rv[c // B, :, c % B] == 0x7e00).all()
+            rk[c // B, :, c % B, :] = wk[c // B, :, c % B, :]
+            rv[c // B, :, c % B] = wv[c // B, :, c % B]
+        assert np.array_equal(rk, wk), "k_cache"
+        assert np.array_equal(rv, wv), "v_cache"
+        assert np.array_equal(gm.cpu().numpy(), wm), "metrics"
+        assert np.array_equal(gp.cpu().numpy(), wp), "positions"
+        print("ok")
+    """)
+    env = dict(os.environ, KVC_MOVES_FULLROW=fullrow)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -119,6 +119,20 @@ def execute_cache_moves(k_cache, v_cache, kv_metrics, kv_position, cache_moves_i
         k_cache.shape[3], B, _DT[k_cache.dtype], blocks_per_head, threads_per_head, _stream()))
 
 
+def execute_cache_moves_deferred(k_cache, v_cache, kv_metrics, kv_position, cache_moves_idx,
+                                 cache_moves_count, evicted_kv_offsets, pend_kv, pend_slot):
+    S, L, H = cache_moves_count.shape
+    NB, D, B = v_cache.shape
+    assert k_cache.is_contiguous() and v_cache.is_contiguous() and kv_metrics.dtype == torch.float32
+    assert pend_kv.is_contiguous() and pend_kv.dtype == k_cache.dtype and pend_kv.numel() == S * L * H * 2 * D
+    assert pend_slot.is_contiguous() and pend_slot.dtype == torch.int64 and pend_slot.numel() == S * L * H
+    _check(native.load_lib().kvc_execute_cache_moves_deferred(
+        _ptr(k_cache), _ptr(v_cache), _ptr(kv_metrics), _ptr(_i32(kv_position, "kv_position")),
+        _ptr(_i32(cache_moves_idx, "cache_moves_idx")), _ptr(_i32(cache_moves_count, "cache_moves_count")),
+        _ptr(_i32(evicted_kv_offsets, "evicted_kv_offsets")), _ptr(pend_kv), _ptr(pend_slot), S, L, H,
+        ctypes.c_int64(NB), D, k_cache.shape[3], B, _DT[k_cache.dtype], _stream()))
+
+
 def reshape_and_cache(key, value, key_cache, value_cache, kv_metrics, slot_mapping,
                       kv_metric_head_bias):
     T, H, D = key.shape

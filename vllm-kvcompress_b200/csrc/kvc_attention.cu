@@ -68,6 +68,11 @@ struct AttnParams {
   int64_t new_k_stride, new_v_stride;
   const int64_t* slot_mapping;  // [S, H]; < 0 = no new token for this head
   const float* head_bias;       // [H]
+  // deferred append (kModeFusedWrite, optional): a new token that opens a fresh block is parked in
+  // pend_kv [S, H, 2 * D] (K | V, compact) with its slot in pend_slot [S, H] instead of being stored to the
+  // cache; kvc_execute_cache_moves_deferred of the next step puts it where it finally belongs
+  uint16_t* pend_kv;
+  int64_t* pend_slot;
 };
 
 template <bool BF16>
@@ -530,6 +535,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   uint16_t* outp = reinterpret_cast<uint16_t*>(p.out) + ((int64_t)s * p.num_heads + h * Q) * kD;
   if (ctx <= 0) {
     for (int i = lane; i < Q * kD; i += kWarp) outp[i] = 0;
+    if (MODE == kModeFusedWrite && p.pend_slot != nullptr && lane == 0) p.pend_slot[item] = -1;
     return;
   }
   unsigned char* ring = ring_of(wid);
@@ -814,12 +820,26 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     }
   if (MODE == kModeFusedWrite && new_slot >= 0) {
     // reference csrc/kvcompress_cache_kernels.cu:55-88: K chunks, V elements, metric := head bias
-    uint16_t* kcw = reinterpret_cast<uint16_t*>(const_cast<void*>(p.k_cache)) + (new_slot >> 4) * p.kv_block_stride;
-    uint16_t* vcw = reinterpret_cast<uint16_t*>(const_cast<void*>(p.v_cache)) + (new_slot >> 4) * p.kv_block_stride;
-    if (lane < 16) *reinterpret_cast<uint4*>(kcw + lane * (kB * 8) + new_o * 8) = newk;
+    if (p.pend_kv != nullptr && new_o == 0) {
+      // deferred append: the token sits alone in a fresh block, which the next compression most likely
+      // drops again (the token is moved into an evicted slot): 2 x 128 partial-sector stores now and a
+      // 4 KB block read then are replaced by 512 B of compact traffic each way
+      uint16_t* pk = p.pend_kv + (int64_t)item * (2 * kD);
+      if (lane < 16) *reinterpret_cast<uint4*>(pk + lane * 8) = newk;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) vcw[(lane + 32 * r) * kB + new_o] = newv[r];
+      for (int r = 0; r < 4; ++r) pk[kD + lane + 32 * r] = newv[r];
+      if (lane == 0) p.pend_slot[item] = new_slot;
+    } else {
+      uint16_t* kcw = reinterpret_cast<uint16_t*>(const_cast<void*>(p.k_cache)) + (new_slot >> 4) * p.kv_block_stride;
+      uint16_t* vcw = reinterpret_cast<uint16_t*>(const_cast<void*>(p.v_cache)) + (new_slot >> 4) * p.kv_block_stride;
+      if (lane < 16) *reinterpret_cast<uint4*>(kcw + lane * (kB * 8) + new_o * 8) = newk;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) vcw[(lane + 32 * r) * kB + new_o] = newv[r];
+      if (p.pend_slot != nullptr && lane == 0) p.pend_slot[item] = -1;
+    }
     if (lane == 0) p.metric[new_slot] = p.head_bias[h];  // ordered before the reductions below by __syncwarp
+  } else if (MODE == kModeFusedWrite && p.pend_slot != nullptr && lane == 0) {
+    p.pend_slot[item] = -1;
   }
   if (smem_logits) {
     // metrics[slot] += sum_q p^2 from the warp's own shared-memory logits; every lane finalises the two
@@ -1124,6 +1144,7 @@ static int fill_params(AttnParams& p, void* out, float* metric, const void* quer
   p.record = record ? 1 : 0; p.max_partitions = 1; p.num_seqs = num_seqs;
   p.new_k = nullptr; p.new_v = nullptr; p.new_k_stride = 0; p.new_v_stride = 0;
   p.slot_mapping = nullptr; p.head_bias = nullptr;
+  p.pend_kv = nullptr; p.pend_slot = nullptr;
   return KVC_OK;
 }
 
@@ -1240,6 +1261,39 @@ extern "C" int kvc_paged_attention_fused_step(
   if (num_seqs == 0) return KVC_OK;
   p.new_k = key; p.new_v = value; p.new_k_stride = key_stride; p.new_v_stride = value_stride;
   p.slot_mapping = slot_mapping; p.head_bias = kv_metric_head_bias;
+  const int padded = (max_context_len + kB - 1) / kB * kB;
+  const size_t need = kvc_paged_attention_fused_metrics_workspace_bytes(num_seqs, num_heads, max_context_len);
+  KVC_REQUIRE(workspace && workspace_bytes >= need, KVC_ERR_WORKSPACE,
+              "fused attention step: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+  return dispatch_stream<kModeFusedWrite>(p, num_seqs, reinterpret_cast<float*>(workspace), padded, dtype,
+                                          as_stream(stream));
+}
+
+extern "C" int kvc_paged_attention_fused_step_deferred(
+    void* out, float* kv_metrics, const void* query, const void* key, const void* value, void* key_cache,
+    void* value_cache, const int64_t* slot_mapping, const float* kv_metric_head_bias, void* pend_kv,
+    int64_t* pend_slot, int num_seqs, int num_heads, int num_kv_heads, int head_size, float scale,
+    const int* block_tables, const int* context_lens, const int* kv_position, const int* last_position,
+    const int* kv_metric_buffer_len, int block_size, int max_context_len, int max_num_blocks_per_seq,
+    int64_t q_stride, int64_t key_stride, int64_t value_stride, int64_t kv_block_stride,
+    const float* alibi_slopes, int dtype, void* workspace, size_t workspace_bytes, kvc_stream_t stream) {
+  AttnParams p;
+  int rc = fill_params(p, out, kv_metrics, query, key_cache, value_cache, num_seqs, num_heads,
+                       num_kv_heads, head_size, scale, block_tables, context_lens, kv_position,
+                       last_position, kv_metric_buffer_len, block_size, max_num_blocks_per_seq,
+                       q_stride, kv_block_stride, alibi_slopes, dtype, 1);
+  if (rc != KVC_OK) return rc;
+  KVC_REQUIRE(key && value && slot_mapping && kv_metric_head_bias, KVC_ERR_INVALID,
+              "fused attention step: null key / value / slot_mapping / head bias");
+  KVC_REQUIRE(pend_kv && pend_slot && (reinterpret_cast<uintptr_t>(pend_kv) & 15) == 0, KVC_ERR_INVALID,
+              "fused attention step (deferred): pend_kv (16-byte aligned) and pend_slot are required");
+  KVC_REQUIRE(key_stride % 8 == 0 && value_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(key) & 15) == 0,
+              KVC_ERR_INVALID, "fused attention step: key must be 16-byte aligned");
+  KVC_REQUIRE(max_context_len > 0, KVC_ERR_INVALID, "fused attention step: max_context_len <= 0");
+  if (num_seqs == 0) return KVC_OK;
+  p.new_k = key; p.new_v = value; p.new_k_stride = key_stride; p.new_v_stride = value_stride;
+  p.slot_mapping = slot_mapping; p.head_bias = kv_metric_head_bias;
+  p.pend_kv = reinterpret_cast<uint16_t*>(pend_kv); p.pend_slot = pend_slot;
   const int padded = (max_context_len + kB - 1) / kB * kB;
   const size_t need = kvc_paged_attention_fused_metrics_workspace_bytes(num_seqs, num_heads, max_context_len);
   KVC_REQUIRE(workspace && workspace_bytes >= need, KVC_ERR_WORKSPACE,

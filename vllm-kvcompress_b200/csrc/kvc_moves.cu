@@ -23,6 +23,8 @@
 //   - metric (f32) and position (i32): lanes 0-15 / 16-31, one element each.
 // Algorithmic bytes per move: 2*(2*128*2 + 4 + 4) + 8 = 1048.
 // Physical floor: >= 4 KB (whole V block) + 16 half-sectors of K per isolated source token.
+#include <stdlib.h>
+
 #include "kvc_common.cuh"
 
 namespace kvc {
@@ -58,6 +60,11 @@ __device__ __forceinline__ void store_v_row_partial(uint16_t* __restrict__ row, 
   }
 }
 
+// PEND (deferred append, see kvc_paged_attention_fused_step_deferred): the K/V of the head's newest
+// token may live in pend_kv [L, S, H, 2 * D] instead of the cache (its slot in pend_slot [L, S, H], -1 =
+// none).  A move whose source is that slot reads the compact copy; a pending token that no move
+// consumes is stored to its own slot, so the cache is canonical when the kernel completes.
+template <bool PEND>
 __global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_kernel(
     uint16_t* __restrict__ k_cache,        // [NB, 16, 16, 8]
     uint16_t* __restrict__ v_cache,        // [NB, 128, 16]
@@ -66,7 +73,9 @@ __global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_ker
     const int2* __restrict__ moves,        // [max_evicted_kv] (dst, src)
     const int* __restrict__ move_count,    // [S*L*H]
     const int* __restrict__ move_offsets,  // [S*L*H]
-    int total_heads) {
+    int total_heads,
+    const uint16_t* __restrict__ pend_kv, const int64_t* __restrict__ pend_slot, int num_seqs,
+    int num_layers, int num_kv_heads, int skip_single) {
   constexpr int B = 16, D = 128;
   constexpr int kBlockElems = B * D;  // 2048 two-byte elements = 4 KB
   // one WARP per head (steady-state compression schedules ~1 run per head: a CTA per head would
@@ -75,9 +84,20 @@ __global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_ker
   const int g = blockIdx.x * kMoveWarps + wid;
   if (g >= total_heads) return;
   const int cnt = move_count[g];
+  if (skip_single && cnt <= 1) return;  // execute_moves_single_kernel owns heads with at most one move
   const int off = move_offsets[g];
   const int nseg = (cnt + kMovesPerSegment - 1) / kMovesPerSegment;
   const int2* __restrict__ mv = moves + off;
+  int pslot = -1;                           // slot of the head's pending token (PEND)
+  const uint16_t* __restrict__ pk = nullptr;
+  bool consumed = false;
+  if (PEND) {
+    const int sq = g / (num_layers * num_kv_heads);
+    const int ly = (g / num_kv_heads) % num_layers;
+    const int64_t pidx = ((int64_t)ly * num_seqs + sq) * num_kv_heads + (g % num_kv_heads);
+    pslot = (int)pend_slot[pidx];
+    pk = pend_kv + pidx * (2 * D);
+  }
 
   for (int seg = blockIdx.y; seg < nseg; seg += gridDim.y) {
     const int base = seg * kMovesPerSegment;
@@ -144,12 +164,21 @@ __global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_ker
       for (int o = 0; o < 16; ++o) {
         const int s = src[o];
         if (s >= 0) {  // warp-uniform
-          const uint16_t* __restrict__ sp =
-              v_cache + (int64_t)(s >> 4) * kBlockElems + (s & 15) + lane * B;
+          if (PEND && s == pslot) {
+            consumed = true;
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const uint32_t x = sp[r * 32 * B];  // reference :426-431, element d = lane + 32 r
-            w[r][o >> 1] |= (o & 1) ? (x << 16) : x;
+            for (int r = 0; r < 4; ++r) {
+              const uint32_t x = pk[D + lane + 32 * r];
+              w[r][o >> 1] |= (o & 1) ? (x << 16) : x;
+            }
+          } else {
+            const uint16_t* __restrict__ sp =
+                v_cache + (int64_t)(s >> 4) * kBlockElems + (s & 15) + lane * B;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const uint32_t x = sp[r * 32 * B];  // reference :426-431, element d = lane + 32 r
+              w[r][o >> 1] |= (o & 1) ? (x << 16) : x;
+            }
           }
         }
       }
@@ -163,8 +192,12 @@ __global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_ker
         for (int i = 0; i < 8; ++i) {
           const int s = half ? src[2 * i + 1] : src[2 * i];
           kp[i] = s >= 0;
-          if (kp[i])
-            kv[i] = ld_stream16(k_cache + (int64_t)(s >> 4) * kBlockElems + j * (B * 8) + (s & 15) * 8);
+          if (kp[i]) {
+            if (PEND && s == pslot)
+              kv[i] = *reinterpret_cast<const uint4*>(pk + j * 8);
+            else
+              kv[i] = ld_stream16(k_cache + (int64_t)(s >> 4) * kBlockElems + j * (B * 8) + (s & 15) * 8);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -187,6 +220,124 @@ __global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_ker
         for (int r = 0; r < 4; ++r) store_v_row_partial(dp + r * 32 * B, w[r], mask);
       }
     }
+  }
+  if (PEND && pslot >= 0 && blockIdx.y == 0) {
+    // With gridDim.y > 1 other warps own some of the head's segments: look through the whole list.
+    if (gridDim.y > 1) {
+      bool hit = false;
+      for (int i = lane; i < cnt; i += kWarp) hit |= (mv[i].y == pslot);
+      consumed = __any_sync(0xffffffffu, hit);
+    }
+    if (!consumed) {  // not moved: the token stays where batch_append_slots put it
+      uint16_t* kd = k_cache + (int64_t)(pslot >> 4) * kBlockElems + (pslot & 15) * 8;
+      uint16_t* vd = v_cache + (int64_t)(pslot >> 4) * kBlockElems + (pslot & 15);
+      if (lane < 16) *reinterpret_cast<uint4*>(kd + lane * (B * 8)) = *reinterpret_cast<const uint4*>(pk + lane * 8);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) vd[(lane + 32 * r) * B] = pk[D + lane + 32 * r];
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------
+// Heads with at most ONE move: the steady state of continual compression (every head evicts one token
+// per step and the newest token takes its slot).  The run kernel above carries 128 registers for its
+// 16-token gather and keeps 16 warps per SM in flight, which makes a launch of 65 536 one-move heads
+// latency bound; here a warp moves one token with ~32 registers (64 warps per SM) and three dependent
+// round trips (count -> move -> source).  cnt == 0 heads only resolve their pending token (PEND).
+// FULLROW: the destination V rows are read, patched and written back as whole 32 B sectors instead
+// of 128 two-byte partial-sector stores (same DRAM traffic -- the partial stores make L2 fetch the
+// sectors -- but full-sector transactions).
+// -----------------------------------------------------------------------------
+constexpr int kSingleWarps = 8;
+
+template <bool PEND, bool FULLROW>
+__global__ void __launch_bounds__(kSingleWarps * kWarp) execute_moves_single_kernel(
+    uint16_t* __restrict__ k_cache, uint16_t* __restrict__ v_cache, float* __restrict__ kv_metrics,
+    int* __restrict__ kv_position, const int2* __restrict__ moves, const int* __restrict__ move_count,
+    const int* __restrict__ move_offsets, int total_heads, const uint16_t* __restrict__ pend_kv,
+    const int64_t* __restrict__ pend_slot, int num_seqs, int num_layers, int num_kv_heads) {
+  constexpr int B = 16, D = 128;
+  constexpr int kBlockElems = B * D;
+  const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int g = blockIdx.x * kSingleWarps + wid;
+  if (g >= total_heads) return;
+  const int cnt = move_count[g];
+  if (cnt > 1) return;
+  int pslot = -1;
+  const uint16_t* __restrict__ pk = nullptr;
+  if (PEND) {
+    const int sq = g / (num_layers * num_kv_heads);
+    const int ly = (g / num_kv_heads) % num_layers;
+    const int64_t pidx = ((int64_t)ly * num_seqs + sq) * num_kv_heads + (g % num_kv_heads);
+    pslot = (int)pend_slot[pidx];
+    pk = pend_kv + pidx * (2 * D);
+  }
+  int dst, src;
+  if (cnt == 1) {
+    const int2 m = moves[move_offsets[g]];
+    dst = m.x;
+    src = m.y;
+  } else {
+    if (!PEND || pslot < 0) return;
+    dst = src = pslot;  // nothing moved: the parked token goes to its own slot
+  }
+  const bool from_pend = PEND && src == pslot;
+  // a parked token that the head's only move does not consume (its source is an older token)
+  const bool flush_too = PEND && pslot >= 0 && !from_pend;
+  // ---- loads ----
+  uint4 kx = make_uint4(0, 0, 0, 0);
+  uint16_t vx[4];
+  if (from_pend) {
+    if (lane < 16) kx = *reinterpret_cast<const uint4*>(pk + lane * 8);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) vx[r] = pk[D + lane + 32 * r];
+  } else {
+    if (lane < 16) kx = ld_stream16(k_cache + (int64_t)(src >> 4) * kBlockElems + lane * (B * 8) + (src & 15) * 8);
+    const uint16_t* __restrict__ sp = v_cache + (int64_t)(src >> 4) * kBlockElems + (src & 15) + lane * B;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) vx[r] = sp[r * 32 * B];
+  }
+  float mt = 0.f;
+  int ps = 0;
+  if (cnt == 1) {  // metric and position of a parked token are already at its slot
+    if (lane == 16) mt = kv_metrics[src];
+    if (lane == 17) ps = kv_position[src];
+  }
+  uint16_t* __restrict__ vd = v_cache + (int64_t)(dst >> 4) * kBlockElems + lane * B;
+  const int o = dst & 15;
+  if (FULLROW) {
+    uint4 ra[4], rb[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      ra[r] = *reinterpret_cast<const uint4*>(vd + r * 32 * B);
+      rb[r] = *reinterpret_cast<const uint4*>(vd + r * 32 * B + 8);
+    }
+    const int wi = o >> 1;
+    const uint32_t keep = (o & 1) ? 0xffffu : 0xffff0000u;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t x = (o & 1) ? ((uint32_t)vx[r] << 16) : (uint32_t)vx[r];
+      uint32_t w[8] = {ra[r].x, ra[r].y, ra[r].z, ra[r].w, rb[r].x, rb[r].y, rb[r].z, rb[r].w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = (i == wi) ? ((w[i] & keep) | x) : w[i];
+      *reinterpret_cast<uint4*>(vd + r * 32 * B) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(vd + r * 32 * B + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) vd[r * 32 * B + o] = vx[r];
+  }
+  if (lane < 16) st_stream16(k_cache + (int64_t)(dst >> 4) * kBlockElems + lane * (B * 8) + o * 8, kx);
+  if (cnt == 1) {
+    if (lane == 16) kv_metrics[dst] = mt;
+    if (lane == 17) kv_position[dst] = ps;
+  }
+  if (flush_too) {
+    uint16_t* kd = k_cache + (int64_t)(pslot >> 4) * kBlockElems + (pslot & 15) * 8;
+    uint16_t* pd = v_cache + (int64_t)(pslot >> 4) * kBlockElems + (pslot & 15);
+    if (lane < 16) *reinterpret_cast<uint4*>(kd + lane * (B * 8)) = *reinterpret_cast<const uint4*>(pk + lane * 8);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) pd[(lane + 32 * r) * B] = pk[D + lane + 32 * r];
   }
 }
 
@@ -227,12 +378,12 @@ __global__ void execute_moves_generic_kernel(T* __restrict__ k_cache, T* __restr
 
 using namespace kvc;
 
-extern "C" int kvc_execute_cache_moves(
+static int execute_moves_impl(
     void* k_cache, void* v_cache, float* kv_metrics, int* kv_position,
     const int* cache_moves_idx, const int* cache_moves_count, const int* evicted_kv_offsets,
     int num_seqs, int num_layers, int num_kv_heads, int64_t num_blocks, int head_size,
     int vec_size, int block_size, int dtype, int blocks_per_head, int threads_per_head,
-    kvc_stream_t stream) {
+    const void* pend_kv, const int64_t* pend_slot, kvc_stream_t stream) {
   (void)blocks_per_head;
   (void)threads_per_head;  // launch hints in the reference; results never depend on them
   (void)num_blocks;
@@ -263,12 +414,51 @@ extern "C" int kvc_execute_cache_moves(
   const bool two_byte = (dtype == KVC_F16 || dtype == KVC_BF16);
   if (two_byte && head_size == 128 && vec_size == 8 && block_size == 16 &&
       (reinterpret_cast<uintptr_t>(k_cache) & 15) == 0 && (reinterpret_cast<uintptr_t>(v_cache) & 15) == 0) {
-    execute_moves_b16_d128_kernel<<<dim3((total_heads + kMoveWarps - 1) / kMoveWarps, gy), kMoveWarps * kWarp, 0, st>>>(
-        reinterpret_cast<uint16_t*>(k_cache), reinterpret_cast<uint16_t*>(v_cache), kv_metrics,
-        kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads);
+    const dim3 grid((total_heads + kMoveWarps - 1) / kMoveWarps, gy);
+    // many heads (decode-time compression of a whole batch): heads with <= 1 move go to the light kernel
+    const int split = total_heads >= 4096 ? 1 : 0;
+    uint16_t* kc = reinterpret_cast<uint16_t*>(k_cache);
+    uint16_t* vc = reinterpret_cast<uint16_t*>(v_cache);
+    const uint16_t* pkv = reinterpret_cast<const uint16_t*>(pend_kv);
+    if (split) {
+      static const int fullrow = [] { const char* e = getenv("KVC_MOVES_FULLROW"); return e ? atoi(e) : 0; }();
+      const dim3 sgrid((total_heads + kSingleWarps - 1) / kSingleWarps);
+      const int sthreads = kSingleWarps * kWarp;
+      if (pend_slot != nullptr) {
+        if (fullrow)
+          execute_moves_single_kernel<true, true><<<sgrid, sthreads, 0, st>>>(
+              kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, pkv,
+              pend_slot, num_seqs, num_layers, num_kv_heads);
+        else
+          execute_moves_single_kernel<true, false><<<sgrid, sthreads, 0, st>>>(
+              kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, pkv,
+              pend_slot, num_seqs, num_layers, num_kv_heads);
+      } else {
+        if (fullrow)
+          execute_moves_single_kernel<false, true><<<sgrid, sthreads, 0, st>>>(
+              kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, nullptr,
+              nullptr, 0, 0, 0);
+        else
+          execute_moves_single_kernel<false, false><<<sgrid, sthreads, 0, st>>>(
+              kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, nullptr,
+              nullptr, 0, 0, 0);
+      }
+      KVC_CHECK_LAUNCH("execute_moves_single_kernel");
+    }
+    if (pend_slot != nullptr)
+      execute_moves_b16_d128_kernel<true><<<grid, kMoveWarps * kWarp, 0, st>>>(
+          kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, pkv, pend_slot,
+          num_seqs, num_layers, num_kv_heads, split);
+    else
+      execute_moves_b16_d128_kernel<false><<<grid, kMoveWarps * kWarp, 0, st>>>(
+          kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, nullptr,
+          nullptr, 0, 0, 0, split);
     KVC_CHECK_LAUNCH("execute_moves_b16_d128_kernel");
     return KVC_OK;
   }
+  KVC_REQUIRE(pend_slot == nullptr, KVC_ERR_UNSUPPORTED,
+              "execute_cache_moves_deferred: only the production layout (2-byte cache, head size 128, "
+              "block size 16, x = 8) supports deferred appends");
   const dim3 grid(total_heads, gy), block(128);
   if (two_byte) {
     execute_moves_generic_kernel<uint16_t><<<grid, block, 0, st>>>(
@@ -288,4 +478,30 @@ extern "C" int kvc_execute_cache_moves(
   }
   KVC_CHECK_LAUNCH("execute_moves_generic_kernel");
   return KVC_OK;
+}
+
+extern "C" int kvc_execute_cache_moves(
+    void* k_cache, void* v_cache, float* kv_metrics, int* kv_position,
+    const int* cache_moves_idx, const int* cache_moves_count, const int* evicted_kv_offsets,
+    int num_seqs, int num_layers, int num_kv_heads, int64_t num_blocks, int head_size,
+    int vec_size, int block_size, int dtype, int blocks_per_head, int threads_per_head,
+    kvc_stream_t stream) {
+  return execute_moves_impl(k_cache, v_cache, kv_metrics, kv_position, cache_moves_idx, cache_moves_count,
+                            evicted_kv_offsets, num_seqs, num_layers, num_kv_heads, num_blocks, head_size,
+                            vec_size, block_size, dtype, blocks_per_head, threads_per_head, nullptr, nullptr,
+                            stream);
+}
+
+extern "C" int kvc_execute_cache_moves_deferred(
+    void* k_cache, void* v_cache, float* kv_metrics, int* kv_position,
+    const int* cache_moves_idx, const int* cache_moves_count, const int* evicted_kv_offsets,
+    const void* pend_kv, const int64_t* pend_slot, int num_seqs, int num_layers, int num_kv_heads,
+    int64_t num_blocks, int head_size, int vec_size, int block_size, int dtype, kvc_stream_t stream) {
+  KVC_REQUIRE(num_seqs == 0 || (pend_kv && pend_slot), KVC_ERR_INVALID,
+              "execute_cache_moves_deferred: pend_kv / pend_slot are required");
+  KVC_REQUIRE((reinterpret_cast<uintptr_t>(pend_kv) & 15) == 0, KVC_ERR_INVALID,
+              "execute_cache_moves_deferred: pend_kv must be 16-byte aligned");
+  return execute_moves_impl(k_cache, v_cache, kv_metrics, kv_position, cache_moves_idx, cache_moves_count,
+                            evicted_kv_offsets, num_seqs, num_layers, num_kv_heads, num_blocks, head_size,
+                            vec_size, block_size, dtype, 1, 16, pend_kv, pend_slot, stream);
 }

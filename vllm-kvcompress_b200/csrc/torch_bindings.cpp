@@ -156,6 +156,36 @@ void execute_cache_moves(torch::Tensor& k_cache, torch::Tensor& v_cache, torch::
                "execute_cache_moves");
 }
 
+// additive op: see include/kvc_b200.h kvc_execute_cache_moves_deferred
+void execute_cache_moves_deferred(torch::Tensor& k_cache, torch::Tensor& v_cache, torch::Tensor& kv_metrics,
+                                  torch::Tensor& kv_position, torch::Tensor& cache_moves_idx,
+                                  torch::Tensor& cache_moves_count, torch::Tensor& evicted_kv_offsets,
+                                  torch::Tensor& pend_kv, torch::Tensor& pend_slot) {
+  TORCH_CHECK(k_cache.dim() == 4 && v_cache.dim() == 3, "k_cache [NB, D/x, B, x], v_cache [NB, D, B] expected");
+  TORCH_CHECK(k_cache.is_cuda() && v_cache.is_cuda() && k_cache.is_contiguous() && v_cache.is_contiguous(),
+              "k_cache / v_cache must be contiguous CUDA tensors");
+  TORCH_CHECK(k_cache.scalar_type() == v_cache.scalar_type(), "k_cache / v_cache dtype mismatch");
+  TORCH_CHECK(kv_metrics.scalar_type() == at::kFloat && kv_metrics.is_contiguous() && kv_metrics.is_cuda(),
+              "kv_metrics must be a contiguous float32 CUDA tensor");
+  TORCH_CHECK(cache_moves_count.dim() == 3, "cache_moves_count must be [num_seqs, num_layers, num_kv_heads]");
+  const int64_t heads = cache_moves_count.numel();
+  TORCH_CHECK(pend_kv.scalar_type() == k_cache.scalar_type() && pend_kv.is_contiguous() && pend_kv.is_cuda() &&
+                  pend_kv.numel() == heads * 2 * v_cache.size(1),
+              "pend_kv must be contiguous [num_layers, num_seqs, num_kv_heads, 2 * head_size] of the cache dtype");
+  TORCH_CHECK(pend_slot.scalar_type() == at::kLong && pend_slot.is_contiguous() && pend_slot.is_cuda() &&
+                  pend_slot.numel() == heads,
+              "pend_slot must be contiguous int64 [num_layers, num_seqs, num_kv_heads]");
+  const at::cuda::OptionalCUDAGuard guard(device_of(cache_moves_idx));
+  check_status(kvc_execute_cache_moves_deferred(
+                   k_cache.data_ptr(), v_cache.data_ptr(), kv_metrics.data_ptr<float>(),
+                   i32_mut(kv_position, "kv_position"), i32(cache_moves_idx, "cache_moves_idx"),
+                   i32(cache_moves_count, "cache_moves_count"), i32(evicted_kv_offsets, "evicted_kv_offsets"),
+                   pend_kv.data_ptr(), pend_slot.data_ptr<int64_t>(), cache_moves_count.size(0),
+                   cache_moves_count.size(1), cache_moves_count.size(2), v_cache.size(0), v_cache.size(1),
+                   k_cache.size(3), v_cache.size(2), cache_dtype(k_cache), cur_stream()),
+               "execute_cache_moves_deferred");
+}
+
 // additive op: see include/kvc_b200.h kvc_select_evictions
 void select_evictions(torch::Tensor& evicted_logical_indices, torch::Tensor& evicted_kv_count,
                       torch::Tensor& evicted_block_count, torch::Tensor& kv_metrics,
@@ -582,6 +612,44 @@ void kvcompress_paged_attention_fused_step(
                "kvcompress_paged_attention_fused_step");
 }
 
+
+// additive op: see include/kvc_b200.h kvc_paged_attention_fused_step_deferred
+void kvcompress_paged_attention_fused_step_deferred(
+    torch::Tensor& out, torch::Tensor& kv_metrics, torch::Tensor& query, torch::Tensor& key, torch::Tensor& value,
+    torch::Tensor& key_cache, torch::Tensor& value_cache, torch::Tensor& slot_mapping,
+    torch::Tensor& kv_metric_head_bias, torch::Tensor& pend_kv, torch::Tensor& pend_slot, int64_t num_kv_heads,
+    double scale, torch::Tensor& block_tables, torch::Tensor& context_lens, torch::Tensor& kv_position,
+    torch::Tensor& last_position, torch::Tensor& kv_metric_buffer_len, int64_t block_size, int64_t max_context_len,
+    const c10::optional<torch::Tensor>& alibi_slopes, const std::string& kv_cache_dtype) {
+  AttnCommon c = attn_common(out, query, key_cache, value_cache, block_tables, alibi_slopes, kv_cache_dtype);
+  TORCH_CHECK(kv_metrics.scalar_type() == at::kFloat && kv_metrics.is_contiguous(), "kv_metrics must be contiguous float32");
+  TORCH_CHECK(key.dim() == 3 && value.dim() == 3 && key.stride(2) == 1 && key.stride(1) == key.size(2) &&
+                  value.stride(2) == 1 && value.stride(1) == value.size(2),
+              "key / value must be [num_seqs, num_kv_heads, head_size] with dense heads");
+  TORCH_CHECK(key.scalar_type() == query.scalar_type() && value.scalar_type() == query.scalar_type(), "key/value dtype");
+  TORCH_CHECK(slot_mapping.scalar_type() == at::kLong && slot_mapping.is_contiguous() &&
+                  slot_mapping.numel() == key.size(0) * key.size(1), "slot_mapping must be contiguous int64 [num_seqs*num_kv_heads]");
+  TORCH_CHECK(kv_metric_head_bias.scalar_type() == at::kFloat, "kv_metric_head_bias must be float32");
+  TORCH_CHECK(pend_kv.scalar_type() == key_cache.scalar_type() && pend_kv.is_contiguous() &&
+                  pend_kv.numel() == key.size(0) * key.size(1) * 2 * key.size(2),
+              "pend_kv must be contiguous [num_seqs, num_kv_heads, 2 * head_size] of the cache dtype");
+  TORCH_CHECK(pend_slot.scalar_type() == at::kLong && pend_slot.is_contiguous() &&
+                  pend_slot.numel() == key.size(0) * key.size(1), "pend_slot must be contiguous int64 [num_seqs, num_kv_heads]");
+  const at::cuda::OptionalCUDAGuard guard(device_of(query));
+  const size_t ws_bytes = kvc_paged_attention_fused_metrics_workspace_bytes(c.S, c.Hq, (int)max_context_len);
+  auto ws = torch::empty({(int64_t)ws_bytes}, query.options().dtype(at::kByte));
+  check_status(kvc_paged_attention_fused_step_deferred(
+                   out.data_ptr(), kv_metrics.data_ptr<float>(), query.data_ptr(), key.data_ptr(), value.data_ptr(),
+                   key_cache.data_ptr(), value_cache.data_ptr(), slot_mapping.data_ptr<int64_t>(),
+                   kv_metric_head_bias.data_ptr<float>(), pend_kv.data_ptr(), pend_slot.data_ptr<int64_t>(), c.S, c.Hq,
+                   (int)num_kv_heads, c.D, (float)scale, i32(block_tables, "block_tables"),
+                   i32(context_lens, "context_lens"), i32(kv_position, "kv_position"),
+                   i32(last_position, "last_position"), i32(kv_metric_buffer_len, "kv_metric_buffer_len"),
+                   (int)block_size, (int)max_context_len, c.MB, c.q_stride, key.stride(0), value.stride(0),
+                   c.kv_block_stride, c.alibi, c.dtype, ws.data_ptr(), ws_bytes, cur_stream()),
+               "kvcompress_paged_attention_fused_step_deferred");
+}
+
 }  // namespace
 
 // FRAGMENT so that the library can coexist with another extension that already owns `_C`.
@@ -634,6 +702,18 @@ TORCH_LIBRARY_FRAGMENT(_C, ops) {
       "    int max_context_len, Tensor? alibi_slopes,"
       "    str kv_cache_dtype) -> ()");
   ops.impl("kvcompress_paged_attention_fused_step", torch::kCUDA, &kvcompress_paged_attention_fused_step);
+  ops.def(
+      "kvcompress_paged_attention_fused_step_deferred("
+      "    Tensor! out, Tensor! kv_metrics, Tensor query, Tensor key, Tensor value,"
+      "    Tensor! key_cache, Tensor! value_cache, Tensor slot_mapping,"
+      "    Tensor kv_metric_head_bias, Tensor! pend_kv, Tensor! pend_slot,"
+      "    int num_kv_heads, float scale,"
+      "    Tensor block_tables, Tensor context_lens,"
+      "    Tensor kv_position, Tensor last_position,"
+      "    Tensor kv_metric_buffer_len, int block_size,"
+      "    int max_context_len, Tensor? alibi_slopes,"
+      "    str kv_cache_dtype) -> ()");
+  ops.impl("kvcompress_paged_attention_fused_step_deferred", torch::kCUDA, &kvcompress_paged_attention_fused_step_deferred);
   // the reference wrapper calls torch.ops._C.schedule_cache_evictions although the op is
   // registered under _C_kvc_ops (vllm/_custom_ops.py:982 vs torch_bindings.cpp:372-386):
   // export it under both names so either resolves.
@@ -700,6 +780,12 @@ TORCH_LIBRARY_FRAGMENT(_C_kvc_ops, kvc_ops) {
       "                      Tensor cache_moves_count, Tensor evicted_kv_offsets,"
       "                      int blocks_per_head, int threads_per_head) -> ()");
   kvc_ops.impl("execute_cache_moves", torch::kCUDA, &execute_cache_moves);
+  kvc_ops.def(
+      "execute_cache_moves_deferred(Tensor! k_cache, Tensor! v_cache, Tensor! kv_metrics,"
+      "                             Tensor! kv_position, Tensor cache_moves_idx,"
+      "                             Tensor cache_moves_count, Tensor evicted_kv_offsets,"
+      "                             Tensor pend_kv, Tensor pend_slot) -> ()");
+  kvc_ops.impl("execute_cache_moves_deferred", torch::kCUDA, &execute_cache_moves_deferred);
   // additive (not in the reference op list)
   kvc_ops.def(
       "select_evictions(Tensor! evicted_logical_indices, Tensor! evicted_kv_count,"

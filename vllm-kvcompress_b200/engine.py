@@ -63,6 +63,11 @@ class HotPathConfig:
     # compressed trailing blocks, allocate for heads crossing a block boundary, tables rewritten in place);
     # "static": every head owns a fixed slab and only context_lens moves (round-1 harness)
     allocator: str = "device"
+    # deferred append: a new token that opens a fresh block (every head, every step, once continual compression
+    # has reached its steady state) is parked in a compact side buffer by the fused step kernel and stored once,
+    # at its final slot, by the next step's execute_cache_moves_deferred (see include/kvc_b200.h).  Needs the
+    # fused cache write.  flush_pending() makes the cache canonical at any point.
+    deferred_append: bool = True
     host_copy_layers: int = 4          # step_host: layers per H2D / D2H copy
     seed: int = 0
 
@@ -126,6 +131,10 @@ class DecodeHotPath:
         self.arangeB = torch.arange(B, dtype=torch.int32, device=device)
         if not cfg.fused_metrics:
             self.temp_metrics = torch.zeros((st.NB, B, cfg.queries_per_kv), dtype=torch.float32, device=device)
+        self.deferred = bool(cfg.deferred_append and cfg.fused_metrics and cfg.fused_cache_write)
+        if self.deferred:
+            self.pend_kv = torch.zeros((L, S, H, 2 * D), dtype=cfg.dtype, device=device)
+            self.pend_slot = torch.full((L, S, H), -1, dtype=torch.int64, device=device)
         self.alloc = None
         if cfg.allocator == "device":
             self.alloc = capi.DeviceBlockAllocator(st.NB, st.block_tables, st.context_lens, st.kv_position, B)
@@ -179,9 +188,23 @@ class DecodeHotPath:
         # first (vllm/_custom_ops.py:1168, 100 MB per call here); only [0, count) per head is ever read
         torch.ops._C_kvc_ops.schedule_t1_cache_moves(self.cache_moves, self.moves_count, logical,
                                                      self.evicted_kv_count, offs, st.block_tables, ctx, B)
-        ops.execute_cache_moves(st.k_cache, st.v_cache, st.kv_metrics, st.kv_position, self.cache_moves,
-                                self.moves_count, offs, 1, 16)
+        if self.deferred:
+            ops.execute_cache_moves_deferred(st.k_cache, st.v_cache, st.kv_metrics, st.kv_position,
+                                             self.cache_moves, self.moves_count, offs, self.pend_kv, self.pend_slot)
+        else:
+            ops.execute_cache_moves(st.k_cache, st.v_cache, st.kv_metrics, st.kv_position, self.cache_moves,
+                                    self.moves_count, offs, 1, 16)
         self.launches += 2
+
+    def flush_pending(self) -> None:
+        """Store every parked token to its slot (deferred append): afterwards the cache holds exactly what
+        the reference's reshape_and_cache + execute_cache_moves sequence leaves."""
+        if not self.deferred:
+            return
+        self.moves_count.zero_()
+        ops.execute_cache_moves_deferred(self.st.k_cache, self.st.v_cache, self.st.kv_metrics, self.st.kv_position,
+                                         self.cache_moves, self.moves_count, self.offs, self.pend_kv, self.pend_slot)
+        self.pend_slot.fill_(-1)
 
     # ------------------------------------------------------------------ append + forward
     def append_slots(self) -> None:
@@ -210,6 +233,14 @@ class DecodeHotPath:
         k = x[:, Hq * D: (Hq + H) * D].view(-1, H, D)
         v = x[:, (Hq + H) * D:].view(-1, H, D)
         o = o.view(-1, Hq, D)
+        if self.deferred:
+            ops.paged_attention_kvc_fused_step_deferred(o, st.kv_metrics, q, k, v, st.k_cache, st.v_cache,
+                                                        self.slot_mapping[l].reshape(-1), self.head_bias[l],
+                                                        self.pend_kv[l], self.pend_slot[l], H, self.scale,
+                                                        st.block_tables[l], st.context_lens[l], st.kv_position,
+                                                        last_pos, self.zeros_s, B, self.max_ctx)
+            self.launches += 1
+            return
         if cfg.fused_metrics and cfg.fused_cache_write:
             ops.paged_attention_kvc_fused_step(o, st.kv_metrics, q, k, v, st.k_cache, st.v_cache,
                                                self.slot_mapping[l].reshape(-1), self.head_bias[l], H, self.scale,
@@ -343,7 +374,14 @@ class DecodeHotPath:
             for l in range(L):
                 q = qkv[l][:, : Hq * D].view(-1, Hq, D)
                 o = out[l].view(-1, Hq, D)
-                if cfg.fused_metrics and cfg.fused_cache_write:
+                if self.deferred:
+                    k = qkv[l][:, Hq * D: (Hq + H) * D].view(-1, H, D)
+                    v = qkv[l][:, (Hq + H) * D:].view(-1, H, D)
+                    ops.paged_attention_kvc_fused_step_deferred(
+                        o, st.kv_metrics, q, k, v, st.k_cache, st.v_cache, self.slot_mapping[l].reshape(-1),
+                        self.head_bias[l], self.pend_kv[l], self.pend_slot[l], H, self.scale, st.block_tables[l],
+                        st.context_lens[l], st.kv_position, last_pos, self.zeros_s, B, self.max_ctx)
+                elif cfg.fused_metrics and cfg.fused_cache_write:
                     k = qkv[l][:, Hq * D: (Hq + H) * D].view(-1, H, D)
                     v = qkv[l][:, (Hq + H) * D:].view(-1, H, D)
                     ops.paged_attention_kvc_fused_step(o, st.kv_metrics, q, k, v, st.k_cache, st.v_cache,
