@@ -362,6 +362,14 @@ KVC_API int kvc_get_attention_pdl(void);
  * (csrc/kvcompress_eviction_kernels.cu:136-153); ties by (metric, logical index).
  * Head-bias / use_average / attention-sink terms: kvc_select_evictions_ex below.
  * ------------------------------------------------------------------------- */
+/* Launch shape of kvc_select_evictions[_ex] (process-wide): 0 = by shape (default): calls with >= 96
+ * sequences, block size 16 and <= 512 slots per head run as ONE launch, a CTA per sequence, whose sort is
+ * pruned to the keys at or below a per-sequence bound on the E-th completion key (see kvc_select.cu);
+ * 1 = always the three launches (rank, threshold, emit); 2 = the single launch whenever the shape
+ * allows.  Results are identical in every mode. */
+KVC_API int kvc_set_select_mode(int mode);
+KVC_API int kvc_get_select_mode(void);
+
 KVC_API size_t kvc_select_evictions_workspace_bytes(int64_t max_evicted_kv, int block_size);
 
 KVC_API int kvc_select_evictions(

@@ -526,6 +526,15 @@ def test_attention_vs_reference_cuda(capi, ref_ops, cfg, version):
 # ---------------------------------------------------------------------------
 # D. fused selection (additive op) == sort -> K1+K2 -> re-sort chain of the reference
 # ---------------------------------------------------------------------------
+@pytest.fixture(params=[1, 2], ids=["three_kernels", "fused_per_sequence"])
+def select_mode(request, capi):
+    """kvc_set_select_mode: 1 = rank / threshold / emit launches, 2 = the one-CTA-per-sequence kernel with the
+    pruned sort wherever the shape allows it (block size 16, <= 512 slots per head)."""
+    capi.set_select_mode(request.param)
+    yield request.param
+    capi.set_select_mode(0)
+
+
 def selection_case(seed, S, L, H, B, max_blocks, prot, frac):
     """State in engine layout (block tables + paged metrics) plus the K1 view of it."""
     from vllm_kvcompress_b200 import workload as W
@@ -558,7 +567,7 @@ def selection_case(seed, S, L, H, B, max_blocks, prot, frac):
     (75, 2, 2, 2, 1, 100, 7, 0.5),
     (76, 2, 32, 8, 16, 9, 32, 0.12),     # Llama-3-8B head count, steady-state-like budget
 ])
-def test_select_evictions_equals_reference_chain(capi, O, cfg):
+def test_select_evictions_equals_reference_chain(capi, O, cfg, select_mode):
     from vllm_kvcompress_b200 import workload as W
     seed, S, L, H, B = cfg[:5]
     st, ctx, last, protected, budgets = selection_case(*cfg)
@@ -594,7 +603,7 @@ SELV2 = load_cases("selection_v2.npz")
 
 
 @pytest.mark.parametrize("name", sorted(SELV2))
-def test_select_evictions_v2_golden(capi, name):
+def test_select_evictions_v2_golden(capi, name, select_mode):
     """bit-exact against CompressionMetrics.schedule_evictions (metrics.py:441-847) run on CPU,
     incl. head bias, use_average and attention sinks."""
     c = SELV2[name]
@@ -622,7 +631,7 @@ def test_select_evictions_v2_golden(capi, name):
     (93, 2, 2, 4, 16, 70, 32, 0.7, [0, 300], 1.5, True, 5),         # CTA sort path
     (94, 2, 1, 2, 16, 400, 32, 0.9, None, 0.0, False, 0),           # CTA sort path, 6400 slots per head
 ])
-def test_select_evictions_options_vs_oracle(capi, O, cfg):
+def test_select_evictions_options_vs_oracle(capi, O, cfg, select_mode):
     from vllm_kvcompress_b200 import workload as W
     seed, S, L, H, B, max_blocks, prot, frac, bins, weight, use_avg, sinks = cfg
     st, ctx, last, protected, budgets = selection_case(seed, S, L, H, B, max_blocks, prot, frac)
@@ -646,6 +655,69 @@ def test_select_evictions_options_vs_oracle(capi, O, cfg):
     np.testing.assert_array_equal(out_cnt.cpu().numpy(), want_cnt)
     np.testing.assert_array_equal(out_blk.cpu().numpy(), want_blk)
     np.testing.assert_array_equal(out_logical.cpu().numpy(), want_logical)
+
+
+@pytest.mark.parametrize("quantize", [False, True])
+@pytest.mark.parametrize("cfg", [
+    # S, L, H, base ctx, budget per head, protected
+    (100, 4, 8, 128, 1.0, 32),     # steady state of continual compression: every head one token past a block
+    (97, 2, 8, 368, 0.9, 32),      # 16 keys per lane (70B-like contexts)
+    (96, 3, 4, 64, 2.5, 8),        # budget beyond one block per head
+])
+def test_select_evictions_fused_steady_state(capi, O, cfg, quantize):
+    """Decode-time shape (many sequences, heads mostly at 16k+1 tokens, budget ~ one block per head): the
+    per-sequence kernel with its pruned sort against the three-kernel path and the numpy oracle, bit-exact,
+    also with heavily tied metrics (quantize: 8 distinct values) where the tie rules decide."""
+    from vllm_kvcompress_b200 import workload as W
+    S, L, H, base, per_head, prot = cfg
+    B = 16
+    g = torch.Generator().manual_seed(S + L)
+    ctx = torch.full((L, S, H), base + 1, dtype=torch.int32)
+    r = torch.rand((L, S, H), generator=g)
+    ctx[r < 0.10] += torch.randint(1, 15, (int((r < 0.10).sum()),), generator=g, dtype=torch.int32)
+    ctx[r > 0.95] -= 17
+    st = W.make_state(S, L, H, B, 16, ctx, dtype=torch.float16, device="cpu", seed=7, fill_cache=False)
+    if quantize:
+        st.kv_metrics = (st.kv_metrics * 8).floor() / 8
+    heads = L * S * H
+    n = int(ctx.max())
+    pos = torch.full((st.NB * B,), -1, dtype=torch.int32)
+    bt = st.block_tables.view(heads, -1)
+    for i in range(heads):
+        c = int(ctx.view(-1)[i])
+        slots = bt[i, torch.arange(c) // B].long() * B + torch.arange(c) % B
+        pos[slots] = torch.cat([torch.randperm(5000, generator=g)[: c - prot // 2].sort().values,
+                                5000 + torch.arange(prot // 2)]).to(torch.int32)
+    st.kv_position = pos.view(st.NB, B)
+    last = torch.full((S,), 5000 + prot // 2 - 1, dtype=torch.int32)
+    protected = torch.full((S,), prot, dtype=torch.int32)
+    budgets = torch.full((S,), int(per_head * L * H), dtype=torch.int32)
+    budgets[::7] = 0
+    budgets[3::11] = 5
+    hanging = W.hanging_token_counts(ctx, B).transpose(0, 1).contiguous()
+    offs = W.evicted_kv_offsets(ctx, B)
+    N = int(((ctx + B - 1) // B).sum()) * B
+    outs = {}
+    for mode in (1, 2):
+        capi.set_select_mode(mode)
+        out_logical = torch.full((N,), -5, dtype=torch.int32, device="cuda")
+        out_cnt = torch.full((S, L, H), -5, dtype=torch.int32, device="cuda")
+        out_blk = torch.full((S, L, H), -5, dtype=torch.int32, device="cuda")
+        capi.select_evictions(out_logical, out_cnt, out_blk, st.kv_metrics.cuda(), st.kv_position.cuda(),
+                              st.block_tables.cuda(), ctx.cuda(), hanging.cuda(), offs.cuda(), budgets.cuda(),
+                              last.cuda(), protected.cuda(), B, MAX_INT)
+        outs[mode] = [t.cpu().numpy() for t in (out_logical, out_cnt, out_blk)]
+    capi.set_select_mode(0)
+    for a, b in zip(outs[1], outs[2]):
+        np.testing.assert_array_equal(a, b)
+    nn = lambda t: t.numpy()
+    want_logical, want_cnt, want_blk = O.select_evictions(
+        nn(st.kv_metrics), nn(st.kv_position), nn(st.block_tables), nn(ctx), nn(hanging), nn(offs), nn(budgets),
+        nn(last), nn(protected), B, MAX_INT, None, None, 0.0, False, 0)
+    np.testing.assert_array_equal(outs[2][1], want_cnt)
+    np.testing.assert_array_equal(outs[2][2], want_blk)
+    np.testing.assert_array_equal(outs[2][0], want_logical)
+    assert int(want_cnt.sum()) > 0
 
 
 def test_block_state_ops_match_reference_formulas(capi):

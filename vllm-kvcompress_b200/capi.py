@@ -265,6 +265,16 @@ def get_attention_pdl() -> int:
     return int(native.load_lib().kvc_get_attention_pdl())
 
 
+def set_select_mode(mode: int) -> None:
+    """kvc_set_select_mode: 0 = choose by shape (default), 1 = rank / threshold / emit launches,
+    2 = one CTA per sequence with the pruned sort whenever block size and context lengths allow."""
+    _check(native.load_lib().kvc_set_select_mode(int(mode)))
+
+
+def get_select_mode() -> int:
+    return int(native.load_lib().kvc_get_select_mode())
+
+
 class DeviceBlockAllocator:
     """The allocator / block-state ops of include/kvc_b200.h (kvc_alloc_*) bound to one set of state
     tensors -- the same tensors the reference keeps in ParallelBlockAllocator, BlockState and

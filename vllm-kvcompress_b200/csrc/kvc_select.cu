@@ -32,6 +32,8 @@
 //              completion key (ties at that key in logical order); ordered compaction by prefix sums.
 // All of it is int32/fp32 gather traffic: 2 x 8 B read per slot, 4 B per evicted index, 4 B per
 // block of completion keys; HBM/L2-bound, no tensor-core shapes.
+#include <stdlib.h>
+
 #include "kvc_common.cuh"
 
 namespace kvc {
@@ -84,6 +86,11 @@ __device__ __forceinline__ unsigned slot_key(const SelectParams& p, float m, int
     m = __fadd_rn(m, __fmul_rn(b, p.bias_weight));
   }
   return orderable(m);
+}
+
+// default selection (no head bias, no averaging, no sinks): the key is the metric itself
+__device__ __forceinline__ unsigned slot_key_plain(float m, int pos, int max_pos) {
+  return (pos > max_pos || pos < 0) ? kInfKey : orderable(m);
 }
 
 // load the (up to) 8 consecutive logical slots i0..i0+7 of a head as orderable keys
@@ -237,18 +244,11 @@ __global__ void __launch_bounds__(128) select_sort_kernel(SelectParams p) {
   for (int q = nev + lane; q < nblk; q += kWarp) ev[q] = kInfKey;
 }
 
+// evicted logical indices of one head, ascending, NULL after them (one warp)
 template <int B, int KPL>
-__global__ void __launch_bounds__(128) select_emit_warp_kernel(SelectParams p) {
-  const int lane = threadIdx.x % kWarp;
-  const int g = blockIdx.x * 4 + threadIdx.x / kWarp;
-  if (g >= p.S * p.L * p.H) return;
-  const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
-  const int lsh = (l * p.S + s) * p.H + h;
-  const int n = p.context_lens[lsh];
+__device__ __forceinline__ void emit_head(const SelectParams& p, int s, int l, int h, int lsh, int n, int off,
+                                          int cnt, int kblk, int lane) {
   const int nblk = (n + B - 1) / B;
-  const int off = p.offsets[g];
-  const int cnt = p.evicted_kv_count[g];
-  const int kblk = p.evicted_block_count[g];
   int* __restrict__ out = p.evicted_logical_indices + off;
   if (cnt > 0) {
     const int last_pos = p.last_position[s];
@@ -299,6 +299,17 @@ __global__ void __launch_bounds__(128) select_emit_warp_kernel(SelectParams p) {
       if (evict[r]) out[pos++] = lane * KPL + r;
   }
   for (int i = cnt + lane; i < nblk * B; i += kWarp) out[i] = p.null_index;
+}
+
+template <int B, int KPL>
+__global__ void __launch_bounds__(128) select_emit_warp_kernel(SelectParams p) {
+  const int lane = threadIdx.x % kWarp;
+  const int g = blockIdx.x * 4 + threadIdx.x / kWarp;
+  if (g >= p.S * p.L * p.H) return;
+  const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
+  const int lsh = (l * p.S + s) * p.H + h;
+  emit_head<B, KPL>(p, s, l, h, lsh, p.context_lens[lsh], p.offsets[g], p.evicted_kv_count[g],
+                    p.evicted_block_count[g], lane);
 }
 
 // ---- CTA-per-head path (long contexts): rank by counting over keys staged in shared memory ----
@@ -561,9 +572,360 @@ __global__ void __launch_bounds__(256) select_threshold_kernel(SelectParams p) {
   }
 }
 
+
+// =====================================================================================================
+// One launch for the whole selection when a call carries many sequences of compressed contexts (decode-time
+// continual compression: 256 sequences x 256 heads x ~9 blocks): ONE CTA PER SEQUENCE, a warp per head
+// round-robin, the per-sequence top-E step done in the same CTA between two __syncthreads, and -- the point
+// of it -- a PRUNED sort.  A head with r0 hanging tokens frees its first block once its r0 cheapest
+// candidates go, so u = (r0-th smallest of the head's 32 per-lane minima) >= that block's completion key;
+// T1 = the E-th smallest u over the sequence's heads is therefore >= the E-th smallest completion key K of
+// the sequence, and no key above T1 can be evicted or decide a granted completion.  Only keys <= T1 (a
+// handful per head in the steady state, where E ~ number of heads) are compacted and sorted, on a 32/64/...
+// key network instead of the full 128/256.  Results are identical to the three-kernel path by construction
+// (same keys, same tie rules, same threshold code on the same completion keys <= K).
+//   A  load keys (DRAM), per-lane minimum -> 32-key network -> u, argmin (first index attaining the minimum)
+//   B  T1 = E-th smallest u                                  (block radix select in shared memory)
+//   C  reload keys (L2), keep <= T1, compact, small sort -> completion keys
+//   D  K = E-th smallest completion key; per-head grants     (= select_threshold_kernel)
+//   E  emit: a head granted its first block with r0 = 1 evicts exactly its argmin (no reload); other
+//      granted heads reload and emit as select_emit_warp_kernel does
+// =====================================================================================================
+constexpr int kSeqWarps = 16;
+constexpr int kSeqThreads = kSeqWarps * kWarp;
+
+// need-th smallest (1-based) of vals[0..M) for the whole CTA; need in [1, M].  hist: 256 ints, sh: 2 words.
+__device__ unsigned block_select_kth(const unsigned* vals, int M, int need, int* hist, unsigned* sh) {
+  const int tid = threadIdx.x;
+  unsigned prefix = 0, mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < M; i += blockDim.x) {
+      const unsigned k = vals[i];
+      if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    if (tid < kWarp) {  // warp 0: 8 bins per lane, exclusive scan over lanes, first bin reaching `need`
+      int loc[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { loc[j] = hist[tid * 8 + j]; sum += loc[j]; }
+      int incl = sum;
+#pragma unroll
+      for (int d = 1; d < kWarp; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (tid >= d) incl += v;
+      }
+      int acc = incl - sum, found = -1, before = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (found < 0 && acc + loc[j] >= need) { found = tid * 8 + j; before = acc; }
+        acc += loc[j];
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, found >= 0);
+      const int src = bal ? __ffs(bal) - 1 : 0;
+      const int b = __shfl_sync(0xffffffffu, found, src), ab = __shfl_sync(0xffffffffu, before, src);
+      if (tid == 0) {
+        sh[0] = prefix | ((unsigned)(bal ? b : 255) << shift);
+        sh[1] = (unsigned)(need - (bal ? ab : 0));
+      }
+    }
+    __syncthreads();
+    prefix = sh[0];
+    need = (int)sh[1];
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  return prefix;
+}
+
+template <int B, int N>
+__device__ __forceinline__ void sort_row_write(const unsigned* row, int lane, int r0, int nev, unsigned* ev) {
+  unsigned kk[N];
+#pragma unroll
+  for (int r = 0; r < N; ++r) kk[r] = row[lane * N + r];
+  warp_bitonic_sort<N>(kk, lane);
+  write_completion_keys<B, N>(kk, lane, r0, nev, ev);
+}
+
+// BTS: the sequence's block-table rows are staged in shared memory first (LH * MB words), so that every
+// per-head step below is ONE round of independent loads instead of context length -> table -> data.
+// KEEP2: phase A leaves every lane's two smallest keys (and the head's smallest "third") in shared memory;
+// whenever that third is above T1 -- no lane holds three keys <= T1 -- phase C needs no second read of the
+// metrics at all.  PLAIN: no head bias / averaging / sinks (the reference defaults): option tests compiled out.
+// Lane <-> slot mapping in phases A / C: lane owns the 4-slot groups lane, lane + 32, ... (16 B of metrics and
+// of positions each), which spreads a head's candidates over all lanes.
+template <int KPL, bool BTS, bool KEEP2, bool PLAIN>
+__global__ void __launch_bounds__(kSeqThreads, 2) select_fused_seq_kernel(SelectParams p, int stop_after) {
+  constexpr int B = 16;
+  constexpr int NG = KPL / 4;                // 4-slot groups per lane
+  constexpr int kPair = (KPL == 8) ? 2 : 1;  // heads in flight per warp (register budget: 64)
+  extern __shared__ unsigned dyn[];
+  __shared__ int hist[256];
+  __shared__ unsigned sh[2];
+  __shared__ int s_wsum[kSeqWarps];
+  __shared__ int s_carry;
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid % kWarp, w = tid / kWarp;
+  const int LH = p.L * p.H;
+  unsigned* s_first = dyn;                                   // [LH] upper bound of the first completion key
+  int* s_argmin = reinterpret_cast<int*>(dyn + LH);          // [LH] first logical index attaining the minimum
+  int* s_k = s_argmin + LH;                                  // [LH] granted blocks
+  int* s_n = s_k + LH;                                       // [LH] context length
+  int* s_r0 = s_n + LH;                                      // [LH] hanging tokens
+  int* s_off = s_r0 + LH;                                    // [LH] segment offset
+  unsigned* s_third = dyn + 6 * LH;                          // [LH] smallest third-smallest key of a lane (KEEP2)
+  unsigned* row = dyn + 7 * LH + w * (32 * KPL);             // per-warp compaction row
+  unsigned* s_small = dyn + 7 * LH + kSeqWarps * 32 * KPL;   // [LH][64] two smallest keys per lane (KEEP2)
+  int* s_bt = reinterpret_cast<int*>(s_small + (KEEP2 ? LH * 64 : 0));  // [LH][MB] (BTS)
+  const int g0 = s * LH;
+  const int E = p.budgets[s];
+  const int last_pos = p.last_position[s];
+  const int max_pos = last_pos - p.protected_window[s];
+
+  for (int hd = tid; hd < LH; hd += kSeqThreads) {
+    s_n[hd] = p.context_lens[((hd / p.H) * p.S + s) * p.H + hd % p.H];
+    s_r0[hd] = p.hanging[g0 + hd];
+    s_off[hd] = p.offsets[g0 + hd];
+  }
+  if (BTS) {
+    for (int hd = w; hd < LH; hd += kSeqWarps) {
+      const int* __restrict__ src = p.block_tables + (int64_t)(((hd / p.H) * p.S + s) * p.H + hd % p.H) * p.MB;
+      for (int b = lane; b < p.MB; b += kWarp) s_bt[hd * p.MB + b] = src[b];
+    }
+  }
+  __syncthreads();
+  if (stop_after == 1) return;  // (profiling aid: KVC_SELECT_STOP_AFTER truncates the kernel after a phase)
+
+  // keys of the lane's slots of head hd: k[4 j + r] <-> logical index 4 (lane + 32 j) + r.  The loads are
+  // unconditional (lanes beyond the context read block 0), so nothing separates the loads of two heads.
+  auto head_keys = [&](int hd, int n, unsigned (&k)[KPL]) {
+    const int l = hd / p.H, h = hd % p.H;
+    const int* __restrict__ bt = p.block_tables + (int64_t)((l * p.S + s) * p.H + h) * p.MB;
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+      const int i0 = 4 * (lane + 32 * j);
+      const bool in = i0 < n;
+      const int bi = in ? (i0 >> 4) : 0;
+      const int phys = BTS ? s_bt[hd * p.MB + bi] : bt[bi];
+      const int64_t slot = in ? (int64_t)phys * 16 + (i0 & 15) : 0;
+      const float4 m4 = *reinterpret_cast<const float4*>(p.kv_metrics + slot);
+      const int4 q4 = *reinterpret_cast<const int4*>(p.kv_position + slot);
+      const float m[4] = {m4.x, m4.y, m4.z, m4.w};
+      const int q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const unsigned key = PLAIN ? slot_key_plain(m[r], q[r], max_pos) : slot_key(p, m[r], q[r], max_pos, last_pos, l, h);
+        k[4 * j + r] = (i0 + r < n) ? key : kInfKey;
+      }
+    }
+  };
+
+  // keep keys <= T1, compact, sort on the smallest network that holds them, write the completion keys
+  auto prune_sort_write = [&](auto& k, unsigned T1, int r0, int nblk, unsigned* ev) {
+    constexpr int NK = sizeof(k) / sizeof(unsigned);
+    int local = 0;
+#pragma unroll
+    for (int r = 0; r < NK; ++r) {
+      if (k[r] > T1) k[r] = kInfKey;
+      local += (k[r] != kInfKey);
+    }
+    int incl = local;
+#pragma unroll
+    for (int d = 1; d < kWarp; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const int ncand = __shfl_sync(0xffffffffu, incl, 31);
+    const int nev = (r0 >= 1 && ncand >= r0) ? (ncand - r0) / B + 1 : 0;
+    if (nev > 0) {  // warp-uniform
+      int size = 32;
+      while (size < ncand) size <<= 1;
+      int pos = incl - local;
+#pragma unroll
+      for (int r = 0; r < NK; ++r)
+        if (k[r] != kInfKey) row[pos++] = k[r];
+      for (int i = ncand + lane; i < size; i += kWarp) row[i] = kInfKey;
+      __syncwarp();
+      if (size == 32) sort_row_write<B, 1>(row, lane, r0, nev, ev);
+      else if (size == 64) sort_row_write<B, 2>(row, lane, r0, nev, ev);
+      else if (NK >= 4 && size == 128) sort_row_write<B, 4>(row, lane, r0, nev, ev);
+      else if (NK >= 8 && size == 256) sort_row_write<B, 8>(row, lane, r0, nev, ev);
+      else if (NK >= 16) sort_row_write<B, 16>(row, lane, r0, nev, ev);
+      __syncwarp();
+    }
+    for (int q = nev + lane; q < nblk; q += kWarp) ev[q] = kInfKey;
+  };
+
+  unsigned T1 = kInfKey;
+  if (E > 0) {
+    // ---- A: bounds ----
+    for (int hd0 = w; hd0 < LH; hd0 += kPair * kSeqWarps) {   // two heads per iteration: their loads overlap
+      const int hd1 = hd0 + kSeqWarps;
+      const bool two = kPair == 2 && hd1 < LH;
+      unsigned ka[KPL], kb[KPL];
+      head_keys(hd0, s_n[hd0], ka);
+      if (two) head_keys(hd1, s_n[hd1], kb);
+#pragma unroll
+      for (int t = 0; t < kPair; ++t) {
+        if (t == 1 && !two) break;
+        unsigned* kk = t ? kb : ka;
+        const int hd = t ? hd1 : hd0;
+        const int r0 = s_r0[hd];
+        unsigned m1 = kInfKey, m2 = kInfKey, m3 = kInfKey;
+        int idx = 0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < NG; ++j)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const unsigned k = kk[4 * j + r];
+            if (k < m1) idx = 4 * (lane + 32 * j) + r;   // strict: the lane's first index wins ties
+            const unsigned b1 = max(m1, k);
+            m1 = min(m1, k);
+            const unsigned b2 = max(m2, b1);
+            m2 = min(m2, b1);
+            m3 = min(m3, b2);
+          }
+        unsigned gm = m1;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) gm = min(gm, __shfl_xor_sync(0xffffffffu, gm, d));
+        int amin = (m1 == gm) ? idx : 0x7fffffff;       // smallest logical index attaining the minimum
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) amin = min(amin, __shfl_xor_sync(0xffffffffu, amin, d));
+        unsigned u = gm;                                // r0 == 1: the minimum itself
+        if (r0 != 1) {
+          unsigned sm1[1] = {m1};
+          warp_bitonic_sort<1>(sm1, lane);
+          u = (r0 >= 1 && r0 <= kWarp) ? __shfl_sync(0xffffffffu, sm1[0], (r0 - 1) & 31) : kInfKey;
+        }
+        if (KEEP2) {
+          unsigned t3 = m3;
+#pragma unroll
+          for (int d = 16; d >= 1; d >>= 1) t3 = min(t3, __shfl_xor_sync(0xffffffffu, t3, d));
+          *reinterpret_cast<uint2*>(s_small + hd * 64 + 2 * lane) = make_uint2(m1, m2);
+          if (lane == 0) s_third[hd] = t3;
+        }
+        if (lane == 0) { s_first[hd] = u; s_argmin[hd] = amin; }
+      }
+    }
+    __syncthreads();
+    if (stop_after == 2) return;
+    // ---- B: T1 ----
+    if (E <= LH) T1 = block_select_kth(s_first, LH, E, hist, sh);
+  }
+  if (stop_after == 3) return;
+
+  // ---- C: pruned sort -> completion keys ----
+  for (int hd = w; hd < LH; hd += kSeqWarps) {
+    const int nblk = (s_n[hd] + B - 1) / B;
+    unsigned* ev = p.events + s_off[hd] / B;
+    if (E <= 0) {
+      for (int q = lane; q < nblk; q += kWarp) ev[q] = kInfKey;
+    } else if (KEEP2 && s_third[hd] > T1) {   // every key <= T1 is among the lanes' two smallest
+      const uint2 v = *reinterpret_cast<const uint2*>(s_small + hd * 64 + 2 * lane);
+      unsigned k2[2] = {v.x, v.y};
+      prune_sort_write(k2, T1, s_r0[hd], nblk, ev);
+    } else {
+      unsigned k[KPL];
+      head_keys(hd, s_n[hd], k);
+      prune_sort_write(k, T1, s_r0[hd], nblk, ev);
+    }
+  }
+  __syncthreads();
+  if (stop_after == 4) return;
+
+  // ---- D: K and the per-head grants (select_threshold_kernel) ----
+  const int e0 = s_off[0] / B;
+  const int e1 = s_off[LH - 1] / B + (s_n[LH - 1] + B - 1) / B;   // segments of a sequence are contiguous
+  const int M = e1 - e0;
+  unsigned K = kInfKey;
+  int need = E;
+  if (E > 0 && E <= M) {
+    K = block_select_kth(p.events + e0, M, E, hist, sh);
+    need = (int)sh[1];   // how many of the keys equal to K are still wanted
+    __syncthreads();
+  }
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int h0 = 0; h0 < LH; h0 += kSeqThreads) {
+    const int hd = h0 + tid;
+    int less = 0, eq = 0, r0 = 0;
+    if (hd < LH) {
+      const int nblk = (s_n[hd] + B - 1) / B;
+      const unsigned* __restrict__ seg = p.events + s_off[hd] / B;
+      r0 = s_r0[hd];
+      if (E > 0) {
+        int lo = 0, hi = nblk;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (seg[mid] < K) lo = mid + 1; else hi = mid; }
+        less = lo;
+        if (K != kInfKey) {
+          hi = nblk;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (seg[mid] <= K) lo = mid + 1; else hi = mid; }
+          eq = lo - less;
+        }
+      }
+    }
+    // exclusive scan of eq in head order (ties at K are granted in head order)
+    int incl = eq;
+#pragma unroll
+    for (int d = 1; d < kWarp; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == kWarp - 1) s_wsum[w] = incl;
+    __syncthreads();
+    int before = s_carry;
+    for (int q = 0; q < w; ++q) before += s_wsum[q];
+    const int eq_before = before + incl - eq;
+    if (hd < LH) {
+      const int take = max(0, min(eq, need - eq_before));
+      const int k = less + ((K != kInfKey) ? take : 0);
+      const int g = g0 + hd;
+      s_k[hd] = k;
+      p.evicted_block_count[g] = k;
+      p.evicted_kv_count[g] = (k > 0) ? (k - 1) * B + r0 : 0;  // metrics.py:788-792
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int q = 0; q < kSeqWarps; ++q) tot += s_wsum[q];
+      s_carry += tot;
+    }
+    __syncthreads();
+  }
+
+  if (stop_after == 5) return;
+  // ---- E: emit ----
+  for (int hd = w; hd < LH; hd += kSeqWarps) {
+    const int n = s_n[hd];
+    const int off = s_off[hd];
+    const int k = s_k[hd];
+    const int r0 = s_r0[hd];
+    const int cnt = (k > 0) ? (k - 1) * B + r0 : 0;
+    if (cnt <= 1) {  // nothing, or the first block with one hanging token: the head's cheapest candidate goes
+      // the segment starts at a multiple of B = 16 entries: 16 B stores
+      int4* __restrict__ out4 = reinterpret_cast<int4*>(p.evicted_logical_indices + off);
+      const int nvec = ((n + B - 1) / B) * (B / 4);
+      const int nul = p.null_index;
+      for (int i = lane; i < nvec; i += kWarp)
+        out4[i] = make_int4((i == 0 && cnt == 1) ? s_argmin[hd] : nul, nul, nul, nul);
+    } else {
+      const int l = hd / p.H, h = hd % p.H;
+      emit_head<B, KPL>(p, s, l, h, (l * p.S + s) * p.H + h, n, off, cnt, k, lane);
+    }
+  }
+}
+
 }  // namespace kvc
 
 using namespace kvc;
+
+static int g_select_mode = 0;
+extern "C" int kvc_set_select_mode(int mode) {
+  KVC_REQUIRE(mode >= 0 && mode <= 2, KVC_ERR_INVALID, "select mode must be 0, 1 or 2, got %d", mode);
+  g_select_mode = mode;
+  return KVC_OK;
+}
+extern "C" int kvc_get_select_mode(void) { return g_select_mode; }
 
 extern "C" size_t kvc_select_evictions_workspace_bytes(int64_t max_evicted_kv, int block_size) {
   if (max_evicted_kv <= 0 || block_size <= 0) return 0;
@@ -627,6 +989,52 @@ extern "C" int kvc_select_evictions_ex(
   const int max_slots = max_num_blocks_per_seq * block_size;
   const bool warp_path = max_slots <= 512;  // compressed contexts: one warp per head, 8 or 16 keys per lane
   const dim3 wgrid(ceil_div(total, 4));
+  // many sequences of compressed contexts: one CTA per sequence does the whole selection with a pruned sort
+  {
+    const int LH = num_layers * num_kv_heads;
+    const int mode = g_select_mode;  // 0 auto, 1 three kernels, 2 fused whenever the shape allows
+    const bool can_fuse = warp_path && block_size == 16 && LH <= 8192;
+    if (can_fuse && mode != 1 && (mode == 2 || num_seqs >= 96)) {
+      const int kpl = max_slots <= 256 ? 8 : 16;
+      const size_t base_words = (size_t)7 * LH + (size_t)kSeqWarps * 32 * kpl;
+      const size_t bt_words = (size_t)LH * max_num_blocks_per_seq, small_words = (size_t)LH * 64;
+      const size_t budget = 100 * 1024 / sizeof(unsigned);   // two CTAs per SM must still fit
+      const bool keep2 = base_words + small_words <= budget;
+      const bool bts = base_words + (keep2 ? small_words : 0) + bt_words <= budget;
+      const size_t smem = (base_words + (keep2 ? small_words : 0) + (bts ? bt_words : 0)) * sizeof(unsigned);
+      KVC_REQUIRE((reinterpret_cast<uintptr_t>(evicted_logical_indices) & 15) == 0, KVC_ERR_INVALID,
+                  "select_evictions: evicted_logical_indices must be 16-byte aligned");
+      cudaError_t e = cudaSuccess;
+      const bool plain = head_bias == nullptr && !use_average && num_sinks <= 0;
+      const char* stop_env = getenv("KVC_SELECT_STOP_AFTER");
+      const int stop_after = stop_env ? atoi(stop_env) : 0;
+#define KVC_SEL_FUSED(KPL_, BTS_, KEEP_, PLAIN_)                                                       \
+  do {                                                                                                 \
+    auto kern = select_fused_seq_kernel<KPL_, BTS_, KEEP_, PLAIN_>;                                    \
+    if (smem > 48 * 1024)                                                                              \
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+    if (e == cudaSuccess) kern<<<num_seqs, kSeqThreads, smem, st>>>(p, stop_after);                    \
+  } while (0)
+#define KVC_SEL_FUSED3(KPL_, BTS_, KEEP_)                                                              \
+  do {                                                                                                 \
+    if (plain) KVC_SEL_FUSED(KPL_, BTS_, KEEP_, true); else KVC_SEL_FUSED(KPL_, BTS_, KEEP_, false);   \
+  } while (0)
+#define KVC_SEL_FUSED2(KPL_)                                                                           \
+  do {                                                                                                 \
+    if (bts && keep2) KVC_SEL_FUSED3(KPL_, true, true);                                                \
+    else if (bts) KVC_SEL_FUSED3(KPL_, true, false);                                                   \
+    else if (keep2) KVC_SEL_FUSED3(KPL_, false, true);                                                 \
+    else KVC_SEL_FUSED3(KPL_, false, false);                                                           \
+  } while (0)
+      if (kpl == 8) KVC_SEL_FUSED2(8); else KVC_SEL_FUSED2(16);
+#undef KVC_SEL_FUSED3
+#undef KVC_SEL_FUSED2
+#undef KVC_SEL_FUSED
+      if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "select_fused_seq smem attr: %s", cudaGetErrorString(e));
+      KVC_CHECK_LAUNCH("select_fused_seq_kernel");
+      return KVC_OK;
+    }
+  }
 #define KVC_SEL_WARP(KERNEL)                                                     \
   do {                                                                           \
     if (max_slots <= 256) {                                                      \

@@ -164,7 +164,11 @@ class DecodeHotPath:
             ops.select_evictions(self.evicted_logical, self.evicted_kv_count, self.evicted_block_count,
                                  st.kv_metrics, st.kv_position, st.block_tables, ctx, self.hanging, self.offs,
                                  self.budgets, last_pos, self.protected, B, MAX_INT)
-            self.launches += 2 + ops.SELECT_EVICTIONS_LAUNCHES
+            # prepare_compression = 2 launches; select_evictions = 1 (one CTA per sequence) for decode-sized
+            # batches of compressed contexts, else rank / threshold / emit
+            fused_sel = (cfg.num_seqs >= 96 and B == 16 and st.block_tables.shape[-1] * B <= 512
+                         and capi.get_select_mode() != 1) or capi.get_select_mode() == 2
+            self.launches += 2 + (1 if fused_sel else ops.SELECT_EVICTIONS_LAUNCHES)
             logical, hanging, offs = self.evicted_logical, self.hanging, self.offs
         else:
             hanging = W.hanging_token_counts(ctx, B).transpose(0, 1).contiguous()  # [S,L,H]
@@ -194,7 +198,8 @@ class DecodeHotPath:
         else:
             ops.execute_cache_moves(st.k_cache, st.v_cache, st.kv_metrics, st.kv_position, self.cache_moves,
                                     self.moves_count, offs, 1, 16)
-        self.launches += 2
+        # schedule_t1_cache_moves + execute_cache_moves (run kernel; + the one-move kernel from 4096 heads up)
+        self.launches += 2 + (1 if cfg.num_seqs * cfg.num_layers * cfg.num_kv_heads >= 4096 else 0)
 
     def flush_pending(self) -> None:
         """Store every parked token to its slot (deferred append): afterwards the cache holds exactly what
