@@ -307,12 +307,20 @@ KVC_API int kvc_paged_attention_fused_step(
  *     bit-identical to what reshape_and_cache + execute_cache_moves leave.  Must run before anything
  *     else reads K/V of the pending slots (the fused step kernel itself patches the staged block from
  *     registers).  Production layout only (2-byte cache, D=128, B=16, x=8).
+ *   Deferred MOVE (pend_dst [L, S, H] int64, optional in both calls, initialised to -1): when the head's only
+ *     move takes the parked token, kvc_execute_cache_moves_deferred moves metric and position only and
+ *     records the destination slot in pend_dst; the next kvc_paged_attention_fused_step_deferred patches the
+ *     parked K/V into its staged copy of that block (so its own attention already sees the token), writes
+ *     the block's touched 32 B sectors back whole -- no read-for-ownership of 144 partially written sectors
+ *     -- and resets pend_dst.  Between the two calls the cache lacks that token's K/V at the destination.
+ *   kvc_flush_deferred: stores every parked token where it belongs (pend_dst if set, else pend_slot) and
+ *     clears both markers: afterwards the cache is canonical.  pend arrays flattened [num_heads].
  * ------------------------------------------------------------------------- */
 KVC_API int kvc_paged_attention_fused_step_deferred(
     void* out, float* kv_metrics, const void* query, const void* key,
     const void* value, void* key_cache, void* value_cache,
     const int64_t* slot_mapping, const float* kv_metric_head_bias,
-    void* pend_kv, int64_t* pend_slot, int num_seqs,
+    void* pend_kv, int64_t* pend_slot, int64_t* pend_dst /* nullable */, int num_seqs,
     int num_heads, int num_kv_heads, int head_size, float scale,
     const int* block_tables, const int* context_lens, const int* kv_position,
     const int* last_position, const int* kv_metric_buffer_len, int block_size,
@@ -325,9 +333,14 @@ KVC_API int kvc_execute_cache_moves_deferred(
     void* k_cache, void* v_cache, float* kv_metrics, int* kv_position,
     const int* cache_moves_idx, const int* cache_moves_count,
     const int* evicted_kv_offsets, const void* pend_kv, const int64_t* pend_slot,
-    int num_seqs, int num_layers, int num_kv_heads, int64_t num_blocks,
-    int head_size, int vec_size, int block_size, int dtype /* kvc_dtype */,
-    kvc_stream_t stream);
+    int64_t* pend_dst /* nullable */, int num_seqs, int num_layers, int num_kv_heads,
+    int64_t num_blocks, int head_size, int vec_size, int block_size,
+    int dtype /* kvc_dtype */, kvc_stream_t stream);
+
+KVC_API int kvc_flush_deferred(
+    void* k_cache, void* v_cache, const void* pend_kv, int64_t* pend_slot,
+    int64_t* pend_dst /* nullable */, int64_t num_heads, int head_size, int vec_size,
+    int block_size, int dtype /* kvc_dtype */, kvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Launch mode of the streaming decode-attention kernel (process-wide; initial value from the

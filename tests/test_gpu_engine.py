@@ -9,6 +9,12 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def pend(e):
+    if not e.deferred:
+        return ()
+    return (e.pend_kv, e.pend_slot) + ((e.pend_dst,) if e.pend_dst is not None else ())
+
+
 def logical_view(eng, t, nblk):
     """[heads, nblk, ...] gather of a per-block tensor through the engine's block tables"""
     bt = eng.st.block_tables.view(-1, eng.st.block_tables.shape[-1])[:, :nblk].long()
@@ -36,7 +42,7 @@ def test_device_allocator_is_invisible_to_results(graph):
     out_b = torch.zeros_like(out_a)
     if graph:
         tensors = lambda e: (e.st.k_cache, e.st.v_cache, e.st.kv_metrics, e.st.kv_position, e.st.context_lens,
-                             e.st.block_tables, e.seq_len) + ((e.pend_kv, e.pend_slot) if e.deferred else ())
+                             e.st.block_tables, e.seq_len) + pend(e)
         state = lambda e: [t.clone() for t in tensors(e)]
         restore = lambda e, s: [t.copy_(v) for t, v in zip(tensors(e), s)]
         sa, sb = state(a), state(b)
@@ -76,7 +82,8 @@ def test_device_allocator_is_invisible_to_results(graph):
 @pytest.mark.parametrize("shape", [dict(num_seqs=2, num_layers=2), dict(num_seqs=5, num_layers=3),
                                    dict(num_seqs=40, num_layers=32)])
 @pytest.mark.parametrize("graph", [False, True])
-def test_deferred_append_is_invisible_to_results(shape, graph):
+@pytest.mark.parametrize("deferred_move", [False, True])
+def test_deferred_append_is_invisible_to_results(shape, graph, deferred_move):
     """Deferred append (new tokens that open a fresh block are parked in a compact buffer and stored by the
     next execute_cache_moves_deferred) against the plain fused step on the same allocator: identical
     attention outputs, tables and context lengths every step, and after flush_pending() bit-identical
@@ -86,8 +93,8 @@ def test_deferred_append_is_invisible_to_results(shape, graph):
     dev = torch.device("cuda", 0)
     kw = dict(max_cache_tokens=64, blocks_per_head=8, protected_window=16, seed=11, **shape)
     a = DecodeHotPath(HotPathConfig(deferred_append=False, **kw), dev)
-    b = DecodeHotPath(HotPathConfig(deferred_append=True, **kw), dev)
-    assert b.deferred and not a.deferred
+    b = DecodeHotPath(HotPathConfig(deferred_append=True, deferred_move=deferred_move, **kw), dev)
+    assert b.deferred and not a.deferred and (b.pend_dst is not None) == deferred_move
     for name in ("k_cache", "v_cache", "kv_metrics", "kv_position"):
         assert torch.equal(getattr(a.st, name), getattr(b.st, name))
     cfg = a.cfg
@@ -103,7 +110,7 @@ def test_deferred_append_is_invisible_to_results(shape, graph):
         def tensors(e):
             t = (e.st.k_cache, e.st.v_cache, e.st.kv_metrics, e.st.kv_position, e.st.context_lens,
                  e.st.block_tables, e.seq_len, e.alloc.free_mask, e.alloc.free_count)
-            return t + ((e.pend_kv, e.pend_slot) if e.deferred else ())
+            return t + pend(e)
         sa, sb = [t.clone() for t in tensors(a)], [t.clone() for t in tensors(b)]
         assert a.capture(qkv, out_a) and b.capture(qkv, out_b)
         [t.copy_(v) for t, v in zip(tensors(a), sa)]
@@ -142,3 +149,16 @@ def test_deferred_append_is_invisible_to_results(shape, graph):
             torch.cuda.synchronize()
             live_equal(f"after flush at step {i}")
     assert parked > 0
+    # a flush right after a compression (deferred moves outstanding) must land the tokens at their destinations
+    if deferred_move and not graph:
+        a.step(qkv, out_a), b.step(qkv, out_b)
+        a.compress(), b.compress()
+        assert int((b.pend_dst >= 0).sum()) > 0
+        b.flush_pending()
+        torch.cuda.synchronize()
+        assert int((b.pend_dst >= 0).sum()) == 0 and int((b.pend_slot >= 0).sum()) == 0
+        # compare at the post-compression lengths (free_compressed has not run: shrink them by hand)
+        for e in (a, b):
+            ev = e.evicted_kv_count.permute(1, 0, 2)
+            e.st.context_lens -= ev
+        live_equal("flush between compression and attention")

@@ -1,7 +1,7 @@
-"""Device time of every phase of one decode step (eager launches, CUDA events between phases):
+"""Device time of every phase of one decode step (eager launches, CUDA events between phases; medians of the LAST 10 steps):
     python tools/step_breakdown.py [steps] [--model llama3-70b]
 The stream is primed with a spin kernel before each step so the host runs ahead of the device and the
-events see kernel time, not launch gaps.  Medians over the steps after the first 10."""
+events see kernel time, not launch gaps."""
 import sys
 import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,6 +16,8 @@ if "llama3-70b" in sys.argv:
     preset = dict(num_layers=80, queries_per_kv=8, max_cache_tokens=368, blocks_per_head=28)
 if "--no-deferred" in sys.argv:
     preset["deferred_append"] = False
+if "--no-deferred-move" in sys.argv:
+    preset["deferred_move"] = False
 cfg = HotPathConfig(**preset)
 eng = DecodeHotPath(cfg, dev)
 H, Q, D, L, S, B = cfg.num_kv_heads, cfg.queries_per_kv, cfg.head_size, cfg.num_layers, cfg.num_seqs, cfg.block_size
@@ -42,7 +44,7 @@ for it in range(steps):
     evs[3].record()
     if eng.deferred:
         ops.execute_cache_moves_deferred(st.k_cache, st.v_cache, st.kv_metrics, st.kv_position, eng.cache_moves,
-                                         eng.moves_count, eng.offs, eng.pend_kv, eng.pend_slot)
+                                         eng.moves_count, eng.offs, eng.pend_kv, eng.pend_slot, eng.pend_dst)
     else:
         ops.execute_cache_moves(st.k_cache, st.v_cache, st.kv_metrics, st.kv_position, eng.cache_moves,
                                 eng.moves_count, eng.offs, 1, 16)
@@ -62,9 +64,10 @@ for it in range(steps):
               f"blocks {int(eng.evicted_block_count.sum()):7d} ctx mean {float(st.context_lens.float().mean()):6.1f} "
               f"min {int(st.context_lens.min())} max {int(st.context_lens.max())} "
               f"at 16k+1: {float(((st.context_lens % 16) == 1).float().mean()) * 100:5.1f} %")
+print("heads with > 1 move at the last step:", int((eng.moves_count > 1).sum()))
 tot = 0.0
 for n in names:
-    v = sorted(acc[n][10:] or acc[n])
+    v = sorted(acc[n][-10:])
     med = v[len(v) // 2]
     tot += med
     print(f"{n:16s} {med:9.1f} us")

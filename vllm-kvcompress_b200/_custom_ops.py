@@ -143,15 +143,25 @@ def execute_cache_moves(k_cache, v_cache, kv_metrics, kv_position, cache_moves_i
 
 
 def execute_cache_moves_deferred(k_cache, v_cache, kv_metrics, kv_position, cache_moves_indices,
-                                 cache_moves_count, evicted_kv_offsets, pend_kv, pend_slot) -> None:
+                                 cache_moves_count, evicted_kv_offsets, pend_kv, pend_slot,
+                                 pend_dst: Optional[torch.Tensor] = None) -> None:
     """ADDITIVE op: execute_cache_moves that also resolves the deferred appends of
     paged_attention_kvc_fused_step_deferred (pend_kv [L,S,H,2D], pend_slot [L,S,H] int64): a move
     whose source is a pending slot copies from the compact buffer, a pending token no move consumes
     is stored to its own slot.  The cache ends up bit-identical to reshape_and_cache_kvc +
-    execute_cache_moves."""
+    execute_cache_moves.  With pend_dst [L,S,H] int64 (initialised to -1) a head whose only move takes
+    its parked token only gets metric / position moved and the destination recorded there: the next
+    paged_attention_kvc_fused_step_deferred stores the K/V (deferred move); flush_deferred resolves
+    whatever is outstanding."""
     torch.ops._C_kvc_ops.execute_cache_moves_deferred(
         k_cache, v_cache, kv_metrics, kv_position, cache_moves_indices.contiguous(),
-        cache_moves_count.contiguous(), evicted_kv_offsets.contiguous(), pend_kv, pend_slot)
+        cache_moves_count.contiguous(), evicted_kv_offsets.contiguous(), pend_kv, pend_slot, pend_dst)
+
+
+def flush_deferred(k_cache, v_cache, pend_kv, pend_slot, pend_dst: Optional[torch.Tensor] = None) -> None:
+    """ADDITIVE op: store every parked token where it belongs (pend_dst if set, else pend_slot) and clear
+    the markers; afterwards the cache is what the reference's op sequence leaves."""
+    torch.ops._C_kvc_ops.flush_deferred(k_cache, v_cache, pend_kv, pend_slot, pend_dst)
 
 
 SELECT_EVICTIONS_LAUNCHES = 3  # rank, threshold, emit
@@ -211,17 +221,18 @@ def paged_attention_kvc_fused_step(out, kv_metrics, query, key, value, key_cache
 
 
 def paged_attention_kvc_fused_step_deferred(out, kv_metrics, query, key, value, key_cache, value_cache,
-                                            slot_mapping, kv_metric_head_bias, pend_kv, pend_slot,
+                                            slot_mapping, kv_metric_head_bias, pend_kv, pend_slot, pend_dst,
                                             num_kv_heads: int, scale: float, block_tables, context_lens,
                                             kv_position, last_position, kv_metric_buffer_len, block_size: int,
                                             max_context_len: int, alibi_slopes: Optional[torch.Tensor] = None,
                                             kv_cache_dtype: str = "auto") -> None:
     """ADDITIVE op: paged_attention_kvc_fused_step with deferred appends: a new token that opens a
     fresh block is parked in pend_kv [S,H,2D] / pend_slot [S,H] (this layer's slices) instead of being
-    stored to the cache; execute_cache_moves_deferred of the next step resolves it."""
+    stored to the cache; execute_cache_moves_deferred of the next step resolves it.  pend_dst [S,H] (or
+    None): destinations of deferred moves recorded by execute_cache_moves_deferred, applied and reset here."""
     torch.ops._C.kvcompress_paged_attention_fused_step_deferred(
         out, kv_metrics, query, key, value, key_cache, value_cache, slot_mapping, kv_metric_head_bias,
-        pend_kv, pend_slot, num_kv_heads, scale, block_tables, context_lens, kv_position, last_position,
+        pend_kv, pend_slot, pend_dst, num_kv_heads, scale, block_tables, context_lens, kv_position, last_position,
         kv_metric_buffer_len, block_size, max_context_len, alibi_slopes, kv_cache_dtype)
 
 

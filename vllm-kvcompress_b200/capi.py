@@ -120,7 +120,7 @@ def execute_cache_moves(k_cache, v_cache, kv_metrics, kv_position, cache_moves_i
 
 
 def execute_cache_moves_deferred(k_cache, v_cache, kv_metrics, kv_position, cache_moves_idx,
-                                 cache_moves_count, evicted_kv_offsets, pend_kv, pend_slot):
+                                 cache_moves_count, evicted_kv_offsets, pend_kv, pend_slot, pend_dst=None):
     S, L, H = cache_moves_count.shape
     NB, D, B = v_cache.shape
     assert k_cache.is_contiguous() and v_cache.is_contiguous() and kv_metrics.dtype == torch.float32
@@ -129,7 +129,7 @@ def execute_cache_moves_deferred(k_cache, v_cache, kv_metrics, kv_position, cach
     _check(native.load_lib().kvc_execute_cache_moves_deferred(
         _ptr(k_cache), _ptr(v_cache), _ptr(kv_metrics), _ptr(_i32(kv_position, "kv_position")),
         _ptr(_i32(cache_moves_idx, "cache_moves_idx")), _ptr(_i32(cache_moves_count, "cache_moves_count")),
-        _ptr(_i32(evicted_kv_offsets, "evicted_kv_offsets")), _ptr(pend_kv), _ptr(pend_slot), S, L, H,
+        _ptr(_i32(evicted_kv_offsets, "evicted_kv_offsets")), _ptr(pend_kv), _ptr(pend_slot), _ptr(pend_dst), S, L, H,
         ctypes.c_int64(NB), D, k_cache.shape[3], B, _DT[k_cache.dtype], _stream()))
 
 

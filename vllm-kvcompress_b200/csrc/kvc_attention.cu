@@ -38,7 +38,9 @@ constexpr int kB = 16;
 constexpr int kPartition = 512;  // reference PARTITION_SIZE, :866
 constexpr int kOStride = 132;    // padded d-stride of the cross-warp merge buffer (bank-conflict free)
 
-enum AttnMode { kModeV1 = 0, kModeV2 = 1, kModeFused = 2, kModeFusedWrite = 3 };
+// kModeFusedWriteMove = kModeFusedWrite + deferred moves applied from pend_dst (its own instantiation: the
+// extra code must not cost the plain fused step anything)
+enum AttnMode { kModeV1 = 0, kModeV2 = 1, kModeFused = 2, kModeFusedWrite = 3, kModeFusedWriteMove = 4 };
 
 struct AttnParams {
   void* out;
@@ -73,6 +75,9 @@ struct AttnParams {
   // cache; kvc_execute_cache_moves_deferred of the next step puts it where it finally belongs
   uint16_t* pend_kv;
   int64_t* pend_slot;
+  // deferred move (optional, with pend_kv): pend_dst [S, H] >= 0 = slot where the token parked by the PREVIOUS
+  // step now belongs (set by kvc_execute_cache_moves_deferred); applied while that block is staged
+  int64_t* pend_dst;
 };
 
 template <bool BF16>
@@ -438,6 +443,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
                                                                                    int scratch_tokens,
                                                                                    int smem_logit_tokens, int pdl_late) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr bool kWrite = (MODE == kModeFusedWrite || MODE == kModeFusedWriteMove);
+  constexpr bool kMove = (MODE == kModeFusedWriteMove);
   // Programmatic dependent launch: the next kernel in the stream may start occupying SMs as this grid's
   // CTAs retire (its producers then stream cache blocks under this grid's tail).  No-ops without the
   // launch attribute.
@@ -446,7 +453,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   constexpr int kPsBytes = NT * 8 * 16 * 2;
   const int H = p.num_kv_heads, Q = p.Q;
   // per-warp smem: ring | P^T | full/empty barriers | (fused, short contexts) raw logits [Q][smem_logit_tokens]
-  const int kPerWarp = kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32 + smem_logit_tokens * Q * 4;
+  constexpr int kPendBytes = kMove ? 2 * kD * 2 : 0;  // the parked token of a deferred move (K | V)
+  const int kPerWarp = kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32 + kPendBytes + smem_logit_tokens * Q * 4;
   const int num_items = p.num_kv_heads * p.num_seqs;
   auto ring_of = [&](int w) { return smem_raw + (size_t)w * kPerWarp; };
   auto full_of = [&](int w) { return smem_u32(ring_of(w) + kNUnit * kUnitBytes + kPsBytes); };
@@ -485,7 +493,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     // Its 4 units are released with a plain arrive; whatever the ring slot still holds is masked like any
     // other slot beyond the context length.
     bool skip_last = false;
-    if (MODE == kModeFusedWrite) {
+    if (kWrite) {
       const int64_t nslot = p.slot_mapping[item];
       skip_last = nslot >= 0 && (nslot & (kB - 1)) == 0 && ctx == (nblk - 1) * kB + 1;
     }
@@ -531,11 +539,15 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   if (item >= num_items) return;
   const int s = item / H, h = item - s * H;
   const int ctx = p.context_lens[item];
+  // destination of a deferred move (see below); loaded with the context length so the two latencies overlap
+  const int64_t pd = kMove ? p.pend_dst[item] : -1;
+  const int bt_mine = (kMove && lane < p.max_num_blocks_per_seq)
+                          ? p.block_tables[(int64_t)item * p.max_num_blocks_per_seq + lane] : -1;
   const int nblk = (ctx + kB - 1) / kB;
   uint16_t* outp = reinterpret_cast<uint16_t*>(p.out) + ((int64_t)s * p.num_heads + h * Q) * kD;
   if (ctx <= 0) {
     for (int i = lane; i < Q * kD; i += kWarp) outp[i] = 0;
-    if (MODE == kModeFusedWrite && p.pend_slot != nullptr && lane == 0) p.pend_slot[item] = -1;
+    if (kWrite && p.pend_slot != nullptr && lane == 0) p.pend_slot[item] = -1;
     return;
   }
   unsigned char* ring = ring_of(wid);
@@ -547,7 +559,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   // v1 mode parks them in kv_metric_out itself
   float* lg0 = nullptr;
   float* lg1 = nullptr;
-  constexpr bool kFusedMetrics = (MODE == kModeFused || MODE == kModeFusedWrite);
+  constexpr bool kFusedMetrics = (MODE == kModeFused || kWrite);
   // short contexts: logits stay in this warp's shared memory and the recording rule is evaluated
   // block by block during the sweep (bit 2b / 2b+1 of `passbits`), so the epilogue has no dependent
   // global loads; long contexts park them in the global scratch row instead
@@ -555,7 +567,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   const int lg_stride = smem_logits ? smem_logit_tokens : scratch_tokens;
   unsigned long long passbits = 0ull;
   if (kFusedMetrics) {
-    float* base = smem_logits ? reinterpret_cast<float*>(ring + kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32)
+    float* base = smem_logits ? reinterpret_cast<float*>(ring + kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32 + kPendBytes)
                               : scratch + (int64_t)item * Q * scratch_tokens;
     lg0 = base + (2 * c) * lg_stride;  // column q = 2c (nt = 0)
     lg1 = lg0 + lg_stride;
@@ -571,7 +583,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   uint16_t newv[4] = {0, 0, 0, 0};       // rows d = lane + 32 r of the new V
   int new_o = -1;                        // block offset of the new token, -1 = none
   int64_t new_slot = -1;
-  if (MODE == kModeFusedWrite) {
+  if (kWrite) {
     const int64_t nslot = p.slot_mapping[item];
     if (nslot >= 0) {
       new_o = (int)(nslot & (kB - 1));
@@ -603,6 +615,30 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
       slope[nt][i] = (ALIBI && qc < Q) ? p.alibi_slopes[h * Q + qc] : 0.f;
     }
   }
+  // deferred move: the token this head parked last step was granted an evicted slot by the compression that
+  // ran since (execute_cache_moves_deferred left only its destination).  It is patched into the staged copy
+  // of that block -- so this step's attention already sees it -- and the block's touched sectors go back to
+  // the cache as WHOLE 32 B sectors (a lone 2-byte store per V row would make L2 fetch every sector first).
+  // The parked K/V (512 B) is staged in this warp's shared memory now and read when its block comes up.
+  int pd_blk = -1, pd_o = 0, pd_phys = 0;
+  const uint16_t* pend_sm = reinterpret_cast<const uint16_t*>(ring + kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32);
+  if (kMove) {
+    if (pd >= 0) {
+      pd_phys = (int)(pd >> 4);
+      pd_o = (int)(pd & (kB - 1));
+      int hit = (lane < nblk && bt_mine == pd_phys) ? lane + 1 : 0;
+      for (int b = lane + kWarp; b < nblk; b += kWarp)
+        if (bt[b] == pd_phys) hit = b + 1;
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) hit = max(hit, __shfl_xor_sync(0xffffffffu, hit, d));
+      pd_blk = hit - 1;
+      // asynchronous copy (LDGSTS): the wait sits where the parked token is first used
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(pend_sm + lane * 8)),
+                   "l"(p.pend_kv + (int64_t)item * (2 * kD) + lane * 8) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  }
+
   float m_run[NT][2], l_part[NT][2];  // running max per column; per-lane PARTIAL sums (reduced at the end)
   float oacc[NT][8][4];
 #pragma unroll
@@ -636,11 +672,26 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
       const unsigned char* kU = next_unit();
-      if (MODE == kModeFusedWrite && klast && new_o >= 0) {  // patch the new token into the staged K half
+      if (kWrite && klast && new_o >= 0) {  // patch the new token into the staged K half
         if ((lane >> 3) == hf && lane < 16)
           *reinterpret_cast<uint4*>(const_cast<unsigned char*>(kU) + (lane & 7) * (kB * 16) + new_o * 16) = newk;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic write, slot later refilled by TMA
         __syncwarp();
+      }
+      if (kMove && kblk == pd_blk) {  // deferred move: chunks 8 hf .. 8 hf + 7 of the parked K
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        unsigned char* kW = const_cast<unsigned char*>(kU);
+        if (lane < 8) *reinterpret_cast<uint4*>(kW + lane * (kB * 16) + pd_o * 16) =
+            *reinterpret_cast<const uint4*>(pend_sm + (8 * hf + lane) * 8);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane < 16) {  // the 32 B sector (two tokens) of every chunk row goes back whole
+          const int rowi = lane >> 1, off = rowi * (kB * 16) + (pd_o >> 1) * 32 + (lane & 1) * 16;
+          unsigned char* kg = reinterpret_cast<unsigned char*>(const_cast<void*>(p.k_cache)) +
+                              ((int64_t)pd_phys * p.kv_block_stride) * 2 + hf * kUnitBytes + off;
+          *reinterpret_cast<uint4*>(kg) = *reinterpret_cast<const uint4*>(kW + off);
+        }
       }
       // four k-steps per half; one conflict-free ldmatrix.x4 per step: (chunk 2j, tok 0-7), (chunk 2j, tok 8-15),
       // (chunk 2j+1, tok 0-7), (chunk 2j+1, tok 8-15) = a0..a3 of the m16n8k16 A fragment
@@ -749,12 +800,24 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
       const unsigned char* vU = next_unit();
-      if (MODE == kModeFusedWrite && last && new_o >= 0) {  // rows 64*hf + lane, 64*hf + 32 + lane of the new V
+      if (kWrite && last && new_o >= 0) {  // rows 64*hf + lane, 64*hf + 32 + lane of the new V
         uint16_t* vw = reinterpret_cast<uint16_t*>(const_cast<unsigned char*>(vU));
         vw[lane * kB + new_o] = newv[2 * hf];
         vw[(lane + 32) * kB + new_o] = newv[2 * hf + 1];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
+      }
+      if (kMove && b == pd_blk) {  // deferred move: rows 64 hf .. 64 hf + 63 of the parked V
+        uint16_t* vw = reinterpret_cast<uint16_t*>(const_cast<unsigned char*>(vU));
+        vw[lane * kB + pd_o] = pend_sm[kD + 64 * hf + lane];
+        vw[(lane + 32) * kB + pd_o] = pend_sm[kD + 64 * hf + 32 + lane];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        unsigned char* vg = reinterpret_cast<unsigned char*>(const_cast<void*>(p.v_cache)) +
+                            ((int64_t)pd_phys * p.kv_block_stride) * 2 + hf * kUnitBytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(vg + (lane + 32 * i) * 16) = *reinterpret_cast<const uint4*>(vU + (lane + 32 * i) * 16);
       }
       const unsigned char* vS = vU + voff;
       uint2 va[4], vb[4];
@@ -818,7 +881,8 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
         }
       }
     }
-  if (MODE == kModeFusedWrite && new_slot >= 0) {
+  if (kMove && pd_blk >= 0 && lane == 0) p.pend_dst[item] = -1;  // applied
+  if (kWrite && new_slot >= 0) {
     // reference csrc/kvcompress_cache_kernels.cu:55-88: K chunks, V elements, metric := head bias
     if (p.pend_kv != nullptr && new_o == 0) {
       // deferred append: the token sits alone in a fresh block, which the next compression most likely
@@ -838,7 +902,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
       if (p.pend_slot != nullptr && lane == 0) p.pend_slot[item] = -1;
     }
     if (lane == 0) p.metric[new_slot] = p.head_bias[h];  // ordered before the reductions below by __syncwarp
-  } else if (MODE == kModeFusedWrite && p.pend_slot != nullptr && lane == 0) {
+  } else if (kWrite && p.pend_slot != nullptr && lane == 0) {
     p.pend_slot[item] = -1;
   }
   if (smem_logits) {
@@ -1058,10 +1122,11 @@ static int launch_stream(const AttnParams& p, int num_seqs, float* scratch, int 
   // fused modes: keep the raw logits in shared memory when [Q][padded ctx] fits next to the ring
   // (<= 32 blocks so the recording bits fit one 64-bit register, and <= 3.5 KB per warp)
   int smem_logit_tokens = 0;
-  if ((MODE == kModeFused || MODE == kModeFusedWrite) && scratch_tokens <= 32 * kB &&
-      (size_t)scratch_tokens * p.Q * 4 <= 3584)
+  constexpr size_t kPend = (MODE == kModeFusedWriteMove) ? 2 * kD * 2 : 0;  // parked-token staging per warp
+  if ((MODE == kModeFused || MODE == kModeFusedWrite || MODE == kModeFusedWriteMove) && scratch_tokens <= 32 * kB &&
+      (size_t)scratch_tokens * p.Q * 4 + kPend <= 3584)
     smem_logit_tokens = scratch_tokens;
-  const size_t smem = (size_t)kConsumers * (kNUnit * kUnitBytes + NT * 8 * 16 * 2 + 2 * kNUnit * 8 + 32 +
+  const size_t smem = (size_t)kConsumers * (kNUnit * kUnitBytes + NT * 8 * 16 * 2 + 2 * kNUnit * 8 + 32 + kPend +
                                             (size_t)smem_logit_tokens * p.Q * 4);
   const int items = num_seqs * p.num_kv_heads;
   const dim3 grid((items + kConsumers - 1) / kConsumers);
@@ -1144,7 +1209,7 @@ static int fill_params(AttnParams& p, void* out, float* metric, const void* quer
   p.record = record ? 1 : 0; p.max_partitions = 1; p.num_seqs = num_seqs;
   p.new_k = nullptr; p.new_v = nullptr; p.new_k_stride = 0; p.new_v_stride = 0;
   p.slot_mapping = nullptr; p.head_bias = nullptr;
-  p.pend_kv = nullptr; p.pend_slot = nullptr;
+  p.pend_kv = nullptr; p.pend_slot = nullptr; p.pend_dst = nullptr;
   return KVC_OK;
 }
 
@@ -1272,7 +1337,7 @@ extern "C" int kvc_paged_attention_fused_step(
 extern "C" int kvc_paged_attention_fused_step_deferred(
     void* out, float* kv_metrics, const void* query, const void* key, const void* value, void* key_cache,
     void* value_cache, const int64_t* slot_mapping, const float* kv_metric_head_bias, void* pend_kv,
-    int64_t* pend_slot, int num_seqs, int num_heads, int num_kv_heads, int head_size, float scale,
+    int64_t* pend_slot, int64_t* pend_dst, int num_seqs, int num_heads, int num_kv_heads, int head_size, float scale,
     const int* block_tables, const int* context_lens, const int* kv_position, const int* last_position,
     const int* kv_metric_buffer_len, int block_size, int max_context_len, int max_num_blocks_per_seq,
     int64_t q_stride, int64_t key_stride, int64_t value_stride, int64_t kv_block_stride,
@@ -1293,11 +1358,14 @@ extern "C" int kvc_paged_attention_fused_step_deferred(
   if (num_seqs == 0) return KVC_OK;
   p.new_k = key; p.new_v = value; p.new_k_stride = key_stride; p.new_v_stride = value_stride;
   p.slot_mapping = slot_mapping; p.head_bias = kv_metric_head_bias;
-  p.pend_kv = reinterpret_cast<uint16_t*>(pend_kv); p.pend_slot = pend_slot;
+  p.pend_kv = reinterpret_cast<uint16_t*>(pend_kv); p.pend_slot = pend_slot; p.pend_dst = pend_dst;
   const int padded = (max_context_len + kB - 1) / kB * kB;
   const size_t need = kvc_paged_attention_fused_metrics_workspace_bytes(num_seqs, num_heads, max_context_len);
   KVC_REQUIRE(workspace && workspace_bytes >= need, KVC_ERR_WORKSPACE,
               "fused attention step: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+  if (pend_dst != nullptr)
+    return dispatch_stream<kModeFusedWriteMove>(p, num_seqs, reinterpret_cast<float*>(workspace), padded, dtype,
+                                                as_stream(stream));
   return dispatch_stream<kModeFusedWrite>(p, num_seqs, reinterpret_cast<float*>(workspace), padded, dtype,
                                           as_stream(stream));
 }

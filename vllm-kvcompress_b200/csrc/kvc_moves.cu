@@ -65,7 +65,7 @@ __device__ __forceinline__ void store_v_row_partial(uint16_t* __restrict__ row, 
 // none).  A move whose source is that slot reads the compact copy; a pending token that no move
 // consumes is stored to its own slot, so the cache is canonical when the kernel completes.
 template <bool PEND>
-__global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_kernel(
+__device__ __forceinline__ void moves_run_head(
     uint16_t* __restrict__ k_cache,        // [NB, 16, 16, 8]
     uint16_t* __restrict__ v_cache,        // [NB, 128, 16]
     float* __restrict__ kv_metrics,        // [NB, 16]
@@ -73,18 +73,11 @@ __global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_ker
     const int2* __restrict__ moves,        // [max_evicted_kv] (dst, src)
     const int* __restrict__ move_count,    // [S*L*H]
     const int* __restrict__ move_offsets,  // [S*L*H]
-    int total_heads,
     const uint16_t* __restrict__ pend_kv, const int64_t* __restrict__ pend_slot, int num_seqs,
-    int num_layers, int num_kv_heads, int skip_single) {
+    int num_layers, int num_kv_heads, int g, int lane) {
   constexpr int B = 16, D = 128;
   constexpr int kBlockElems = B * D;  // 2048 two-byte elements = 4 KB
-  // one WARP per head (steady-state compression schedules ~1 run per head: a CTA per head would
-  // leave three of its four warps idle); blockIdx.y strides over the head's 32-move segments
-  const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
-  const int g = blockIdx.x * kMoveWarps + wid;
-  if (g >= total_heads) return;
   const int cnt = move_count[g];
-  if (skip_single && cnt <= 1) return;  // execute_moves_single_kernel owns heads with at most one move
   const int off = move_offsets[g];
   const int nseg = (cnt + kMovesPerSegment - 1) / kMovesPerSegment;
   const int2* __restrict__ mv = moves + off;
@@ -238,12 +231,56 @@ __global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_ker
   }
 }
 
+// one WARP per head (post-prefill compaction: few heads, thousands of moves each); blockIdx.y strides over the
+// head's 32-move segments
+template <bool PEND>
+__global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_kernel(
+    uint16_t* __restrict__ k_cache, uint16_t* __restrict__ v_cache, float* __restrict__ kv_metrics,
+    int* __restrict__ kv_position, const int2* __restrict__ moves, const int* __restrict__ move_count,
+    const int* __restrict__ move_offsets, int total_heads, const uint16_t* __restrict__ pend_kv,
+    const int64_t* __restrict__ pend_slot, int num_seqs, int num_layers, int num_kv_heads) {
+  const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int g = blockIdx.x * kMoveWarps + wid;
+  if (g >= total_heads) return;
+  moves_run_head<PEND>(k_cache, v_cache, kv_metrics, kv_position, moves, move_count, move_offsets, pend_kv,
+                       pend_slot, num_seqs, num_layers, num_kv_heads, g, lane);
+}
+
+// decode-time compaction (many heads, most with <= 1 move, which execute_moves_light_kernel owns): a warp
+// looks at 32 heads at once and runs only those with more than one move.  gridDim.y == 1.
+template <bool PEND>
+__global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_chunk_kernel(
+    uint16_t* __restrict__ k_cache, uint16_t* __restrict__ v_cache, float* __restrict__ kv_metrics,
+    int* __restrict__ kv_position, const int2* __restrict__ moves, const int* __restrict__ move_count,
+    const int* __restrict__ move_offsets, int total_heads, const uint16_t* __restrict__ pend_kv,
+    const int64_t* __restrict__ pend_slot, int num_seqs, int num_layers, int num_kv_heads) {
+  // warp w looks at heads w, w + W, w + 2W, ... (W = warps in the grid): heads with many moves cluster by
+  // sequence, a strided assignment spreads them over the warps
+  const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int W = gridDim.x * kMoveWarps;
+  const int w = blockIdx.x * kMoveWarps + wid;
+  for (int g0 = w; g0 < total_heads; g0 += W * kWarp) {
+    const int g = g0 + lane * W;
+    const int c = (g < total_heads) ? move_count[g] : 0;
+    unsigned todo = __ballot_sync(0xffffffffu, c > 1);
+    while (todo) {
+      const int l0 = __ffs(todo) - 1;
+      todo &= todo - 1;
+      moves_run_head<PEND>(k_cache, v_cache, kv_metrics, kv_position, moves, move_count, move_offsets, pend_kv,
+                           pend_slot, num_seqs, num_layers, num_kv_heads, g0 + l0 * W, lane);
+    }
+  }
+}
+
 // -----------------------------------------------------------------------------
 // Heads with at most ONE move: the steady state of continual compression (every head evicts one token
-// per step and the newest token takes its slot).  The run kernel above carries 128 registers for its
-// 16-token gather and keeps 16 warps per SM in flight, which makes a launch of 65 536 one-move heads
-// latency bound; here a warp moves one token with ~32 registers (64 warps per SM) and three dependent
-// round trips (count -> move -> source).  cnt == 0 heads only resolve their pending token (PEND).
+// per step and the newest token takes its slot).  A warp looks at 32 heads at once (coalesced counts,
+// offsets, moves, parked slots):
+//   * deferred move (pend_dst given, the head's one move takes its parked token): the lane itself moves
+//     metric and position and records the destination; the K/V is stored by the next fused attention step;
+//   * heads with K/V work (a move from the cache or resolved in place, a parked token to put back) are then
+//     handled by the whole warp one after the other: ~32 registers, no 16-token gather;
+//   * cnt > 1 heads belong to execute_moves_b16_d128_chunk_kernel.
 // FULLROW: the destination V rows are read, patched and written back as whole 32 B sectors instead
 // of 128 two-byte partial-sector stores (same DRAM traffic -- the partial stores make L2 fetch the
 // sectors -- but full-sector transactions).
@@ -251,93 +288,118 @@ __global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_ker
 constexpr int kSingleWarps = 8;
 
 template <bool PEND, bool FULLROW>
-__global__ void __launch_bounds__(kSingleWarps * kWarp) execute_moves_single_kernel(
+__global__ void __launch_bounds__(kSingleWarps * kWarp) execute_moves_light_kernel(
     uint16_t* __restrict__ k_cache, uint16_t* __restrict__ v_cache, float* __restrict__ kv_metrics,
     int* __restrict__ kv_position, const int2* __restrict__ moves, const int* __restrict__ move_count,
     const int* __restrict__ move_offsets, int total_heads, const uint16_t* __restrict__ pend_kv,
-    const int64_t* __restrict__ pend_slot, int num_seqs, int num_layers, int num_kv_heads) {
+    const int64_t* __restrict__ pend_slot, int64_t* __restrict__ pend_dst, int num_seqs, int num_layers,
+    int num_kv_heads) {
   constexpr int B = 16, D = 128;
   constexpr int kBlockElems = B * D;
   const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
-  const int g = blockIdx.x * kSingleWarps + wid;
-  if (g >= total_heads) return;
-  const int cnt = move_count[g];
-  if (cnt > 1) return;
-  int pslot = -1;
-  const uint16_t* __restrict__ pk = nullptr;
-  if (PEND) {
-    const int sq = g / (num_layers * num_kv_heads);
-    const int ly = (g / num_kv_heads) % num_layers;
-    const int64_t pidx = ((int64_t)ly * num_seqs + sq) * num_kv_heads + (g % num_kv_heads);
-    pslot = (int)pend_slot[pidx];
-    pk = pend_kv + pidx * (2 * D);
-  }
-  int dst, src;
-  if (cnt == 1) {
-    const int2 m = moves[move_offsets[g]];
-    dst = m.x;
-    src = m.y;
-  } else {
-    if (!PEND || pslot < 0) return;
-    dst = src = pslot;  // nothing moved: the parked token goes to its own slot
-  }
-  const bool from_pend = PEND && src == pslot;
-  // a parked token that the head's only move does not consume (its source is an older token)
-  const bool flush_too = PEND && pslot >= 0 && !from_pend;
-  // ---- loads ----
-  uint4 kx = make_uint4(0, 0, 0, 0);
-  uint16_t vx[4];
-  if (from_pend) {
-    if (lane < 16) kx = *reinterpret_cast<const uint4*>(pk + lane * 8);
-#pragma unroll
-    for (int r = 0; r < 4; ++r) vx[r] = pk[D + lane + 32 * r];
-  } else {
-    if (lane < 16) kx = ld_stream16(k_cache + (int64_t)(src >> 4) * kBlockElems + lane * (B * 8) + (src & 15) * 8);
-    const uint16_t* __restrict__ sp = v_cache + (int64_t)(src >> 4) * kBlockElems + (src & 15) + lane * B;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) vx[r] = sp[r * 32 * B];
-  }
-  float mt = 0.f;
-  int ps = 0;
-  if (cnt == 1) {  // metric and position of a parked token are already at its slot
-    if (lane == 16) mt = kv_metrics[src];
-    if (lane == 17) ps = kv_position[src];
-  }
-  uint16_t* __restrict__ vd = v_cache + (int64_t)(dst >> 4) * kBlockElems + lane * B;
-  const int o = dst & 15;
-  if (FULLROW) {
-    uint4 ra[4], rb[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      ra[r] = *reinterpret_cast<const uint4*>(vd + r * 32 * B);
-      rb[r] = *reinterpret_cast<const uint4*>(vd + r * 32 * B + 8);
+  const int base = (blockIdx.x * kSingleWarps + wid) * kWarp;
+  if (base >= total_heads) return;
+  // ---- the lane's own head ----
+  const int g = base + lane;
+  int my_cnt = 2, my_dst = -1, my_src = -1, my_pslot = -1;
+  int64_t my_pidx = 0;
+  if (g < total_heads) {
+    my_cnt = move_count[g];
+    if (my_cnt <= 1) {
+      if (PEND) {
+        const int sq = g / (num_layers * num_kv_heads);
+        const int ly = (g / num_kv_heads) % num_layers;
+        my_pidx = ((int64_t)ly * num_seqs + sq) * num_kv_heads + (g % num_kv_heads);
+        my_pslot = (int)pend_slot[my_pidx];
+      }
+      if (my_cnt == 1) {
+        const int2 m = moves[move_offsets[g]];
+        my_dst = m.x;
+        my_src = m.y;
+      }
     }
-    const int wi = o >> 1;
-    const uint32_t keep = (o & 1) ? 0xffffu : 0xffff0000u;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const uint32_t x = (o & 1) ? ((uint32_t)vx[r] << 16) : (uint32_t)vx[r];
-      uint32_t w[8] = {ra[r].x, ra[r].y, ra[r].z, ra[r].w, rb[r].x, rb[r].y, rb[r].z, rb[r].w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = (i == wi) ? ((w[i] & keep) | x) : w[i];
-      *reinterpret_cast<uint4*>(vd + r * 32 * B) = make_uint4(w[0], w[1], w[2], w[3]);
-      *reinterpret_cast<uint4*>(vd + r * 32 * B + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+  bool work = false;  // K/V to copy with the whole warp
+  if (my_cnt <= 1) {
+    if (PEND && pend_dst != nullptr && my_cnt == 1 && my_src == my_pslot) {
+      // deferred move: metric and position go now (the next selection reads them), the K/V stays parked and
+      // the next fused attention step stores it while it has the destination block staged
+      kv_metrics[my_dst] = kv_metrics[my_src];
+      kv_position[my_dst] = kv_position[my_src];
+      pend_dst[my_pidx] = my_dst;
+    } else {
+      work = (my_cnt == 1) || (PEND && my_pslot >= 0);
     }
-  } else {
-#pragma unroll
-    for (int r = 0; r < 4; ++r) vd[r * 32 * B + o] = vx[r];
   }
-  if (lane < 16) st_stream16(k_cache + (int64_t)(dst >> 4) * kBlockElems + lane * (B * 8) + o * 8, kx);
-  if (cnt == 1) {
-    if (lane == 16) kv_metrics[dst] = mt;
-    if (lane == 17) kv_position[dst] = ps;
-  }
-  if (flush_too) {
-    uint16_t* kd = k_cache + (int64_t)(pslot >> 4) * kBlockElems + (pslot & 15) * 8;
-    uint16_t* pd = v_cache + (int64_t)(pslot >> 4) * kBlockElems + (pslot & 15);
-    if (lane < 16) *reinterpret_cast<uint4*>(kd + lane * (B * 8)) = *reinterpret_cast<const uint4*>(pk + lane * 8);
+  unsigned todo = __ballot_sync(0xffffffffu, work);
+  while (todo) {
+    const int l0 = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int cnt = __shfl_sync(0xffffffffu, my_cnt, l0);
+    const int pslot = __shfl_sync(0xffffffffu, my_pslot, l0);
+    const int64_t pidx = __shfl_sync(0xffffffffu, my_pidx, l0);
+    int dst = __shfl_sync(0xffffffffu, my_dst, l0), src = __shfl_sync(0xffffffffu, my_src, l0);
+    const uint16_t* __restrict__ pk = PEND ? pend_kv + pidx * (2 * D) : nullptr;
+    if (cnt == 0) dst = src = pslot;  // nothing moved: the parked token goes to its own slot
+    const bool from_pend = PEND && src == pslot;
+    // a parked token that the head's only move does not consume (its source is an older token)
+    const bool flush_too = PEND && pslot >= 0 && !from_pend;
+    // ---- loads ----
+    uint4 kx = make_uint4(0, 0, 0, 0);
+    uint16_t vx[4];
+    if (from_pend) {
+      if (lane < 16) kx = *reinterpret_cast<const uint4*>(pk + lane * 8);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) pd[(lane + 32 * r) * B] = pk[D + lane + 32 * r];
+      for (int r = 0; r < 4; ++r) vx[r] = pk[D + lane + 32 * r];
+    } else {
+      if (lane < 16) kx = ld_stream16(k_cache + (int64_t)(src >> 4) * kBlockElems + lane * (B * 8) + (src & 15) * 8);
+      const uint16_t* __restrict__ sp = v_cache + (int64_t)(src >> 4) * kBlockElems + (src & 15) + lane * B;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) vx[r] = sp[r * 32 * B];
+    }
+    float mt = 0.f;
+    int ps = 0;
+    if (cnt == 1) {  // metric and position of a parked token are already at its slot
+      if (lane == 16) mt = kv_metrics[src];
+      if (lane == 17) ps = kv_position[src];
+    }
+    uint16_t* __restrict__ vd = v_cache + (int64_t)(dst >> 4) * kBlockElems + lane * B;
+    const int o = dst & 15;
+    if (FULLROW) {
+      uint4 ra[4], rb[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        ra[r] = *reinterpret_cast<const uint4*>(vd + r * 32 * B);
+        rb[r] = *reinterpret_cast<const uint4*>(vd + r * 32 * B + 8);
+      }
+      const int wi = o >> 1;
+      const uint32_t keep = (o & 1) ? 0xffffu : 0xffff0000u;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const uint32_t x = (o & 1) ? ((uint32_t)vx[r] << 16) : (uint32_t)vx[r];
+        uint32_t w[8] = {ra[r].x, ra[r].y, ra[r].z, ra[r].w, rb[r].x, rb[r].y, rb[r].z, rb[r].w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = (i == wi) ? ((w[i] & keep) | x) : w[i];
+        *reinterpret_cast<uint4*>(vd + r * 32 * B) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(vd + r * 32 * B + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) vd[r * 32 * B + o] = vx[r];
+    }
+    if (lane < 16) st_stream16(k_cache + (int64_t)(dst >> 4) * kBlockElems + lane * (B * 8) + o * 8, kx);
+    if (cnt == 1) {
+      if (lane == 16) kv_metrics[dst] = mt;
+      if (lane == 17) kv_position[dst] = ps;
+    }
+    if (flush_too) {
+      uint16_t* kd = k_cache + (int64_t)(pslot >> 4) * kBlockElems + (pslot & 15) * 8;
+      uint16_t* pd = v_cache + (int64_t)(pslot >> 4) * kBlockElems + (pslot & 15);
+      if (lane < 16) *reinterpret_cast<uint4*>(kd + lane * (B * 8)) = *reinterpret_cast<const uint4*>(pk + lane * 8);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) pd[(lane + 32 * r) * B] = pk[D + lane + 32 * r];
+    }
+    __syncwarp();
   }
 }
 
@@ -383,7 +445,7 @@ static int execute_moves_impl(
     const int* cache_moves_idx, const int* cache_moves_count, const int* evicted_kv_offsets,
     int num_seqs, int num_layers, int num_kv_heads, int64_t num_blocks, int head_size,
     int vec_size, int block_size, int dtype, int blocks_per_head, int threads_per_head,
-    const void* pend_kv, const int64_t* pend_slot, kvc_stream_t stream) {
+    const void* pend_kv, const int64_t* pend_slot, int64_t* pend_dst, kvc_stream_t stream) {
   (void)blocks_per_head;
   (void)threads_per_head;  // launch hints in the reference; results never depend on them
   (void)num_blocks;
@@ -414,45 +476,46 @@ static int execute_moves_impl(
   const bool two_byte = (dtype == KVC_F16 || dtype == KVC_BF16);
   if (two_byte && head_size == 128 && vec_size == 8 && block_size == 16 &&
       (reinterpret_cast<uintptr_t>(k_cache) & 15) == 0 && (reinterpret_cast<uintptr_t>(v_cache) & 15) == 0) {
-    const dim3 grid((total_heads + kMoveWarps - 1) / kMoveWarps, gy);
-    // many heads (decode-time compression of a whole batch): heads with <= 1 move go to the light kernel
-    const int split = total_heads >= 4096 ? 1 : 0;
+    // many heads (decode-time compression of a whole batch): a warp per 32 heads; heads with <= 1 move go to
+    // the light kernel (deferred moves live there), the others to the run kernel
+    const bool split = total_heads >= 4096 || pend_dst != nullptr;
     uint16_t* kc = reinterpret_cast<uint16_t*>(k_cache);
     uint16_t* vc = reinterpret_cast<uint16_t*>(v_cache);
     const uint16_t* pkv = reinterpret_cast<const uint16_t*>(pend_kv);
+    const bool pend = pend_slot != nullptr;
     if (split) {
       static const int fullrow = [] { const char* e = getenv("KVC_MOVES_FULLROW"); return e ? atoi(e) : 0; }();
-      const dim3 sgrid((total_heads + kSingleWarps - 1) / kSingleWarps);
+      const int chunks = (total_heads + kWarp - 1) / kWarp;
+      const dim3 sgrid((chunks + kSingleWarps - 1) / kSingleWarps);
       const int sthreads = kSingleWarps * kWarp;
-      if (pend_slot != nullptr) {
-        if (fullrow)
-          execute_moves_single_kernel<true, true><<<sgrid, sthreads, 0, st>>>(
-              kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, pkv,
-              pend_slot, num_seqs, num_layers, num_kv_heads);
-        else
-          execute_moves_single_kernel<true, false><<<sgrid, sthreads, 0, st>>>(
-              kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, pkv,
-              pend_slot, num_seqs, num_layers, num_kv_heads);
-      } else {
-        if (fullrow)
-          execute_moves_single_kernel<false, true><<<sgrid, sthreads, 0, st>>>(
-              kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, nullptr,
-              nullptr, 0, 0, 0);
-        else
-          execute_moves_single_kernel<false, false><<<sgrid, sthreads, 0, st>>>(
-              kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, nullptr,
-              nullptr, 0, 0, 0);
-      }
-      KVC_CHECK_LAUNCH("execute_moves_single_kernel");
+#define KVC_LIGHT(PEND_, FULL_)                                                                              \
+  execute_moves_light_kernel<PEND_, FULL_><<<sgrid, sthreads, 0, st>>>(                                       \
+      kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, pkv, pend_slot, \
+      pend_dst, num_seqs, num_layers, num_kv_heads)
+      if (pend) { if (fullrow) KVC_LIGHT(true, true); else KVC_LIGHT(true, false); }
+      else { if (fullrow) KVC_LIGHT(false, true); else KVC_LIGHT(false, false); }
+#undef KVC_LIGHT
+      KVC_CHECK_LAUNCH("execute_moves_light_kernel");
+      const dim3 cgrid(min((chunks + kMoveWarps - 1) / kMoveWarps, 148 * 8));
+      if (pend)
+        execute_moves_b16_d128_chunk_kernel<true><<<cgrid, kMoveWarps * kWarp, 0, st>>>(
+            kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, pkv, pend_slot,
+            num_seqs, num_layers, num_kv_heads);
+      else
+        execute_moves_b16_d128_chunk_kernel<false><<<cgrid, kMoveWarps * kWarp, 0, st>>>(
+            kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, nullptr, nullptr,
+            0, 0, 0);
+    } else {
+      const dim3 grid((total_heads + kMoveWarps - 1) / kMoveWarps, gy);
+      if (pend)
+        execute_moves_b16_d128_kernel<true><<<grid, kMoveWarps * kWarp, 0, st>>>(
+            kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, pkv, pend_slot,
+            num_seqs, num_layers, num_kv_heads);
+      else
+        execute_moves_b16_d128_kernel<false><<<grid, kMoveWarps * kWarp, 0, st>>>(
+            kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, nullptr, nullptr,
+            0, 0, 0);
     }
-    if (pend_slot != nullptr)
-      execute_moves_b16_d128_kernel<true><<<grid, kMoveWarps * kWarp, 0, st>>>(
-          kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, pkv, pend_slot,
-          num_seqs, num_layers, num_kv_heads, split);
-    else
-      execute_moves_b16_d128_kernel<false><<<grid, kMoveWarps * kWarp, 0, st>>>(
-          kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, nullptr,
-          nullptr, 0, 0, 0, split);
     KVC_CHECK_LAUNCH("execute_moves_b16_d128_kernel");
     return KVC_OK;
   }
@@ -489,19 +552,65 @@ extern "C" int kvc_execute_cache_moves(
   return execute_moves_impl(k_cache, v_cache, kv_metrics, kv_position, cache_moves_idx, cache_moves_count,
                             evicted_kv_offsets, num_seqs, num_layers, num_kv_heads, num_blocks, head_size,
                             vec_size, block_size, dtype, blocks_per_head, threads_per_head, nullptr, nullptr,
-                            stream);
+                            nullptr, stream);
 }
 
 extern "C" int kvc_execute_cache_moves_deferred(
     void* k_cache, void* v_cache, float* kv_metrics, int* kv_position,
     const int* cache_moves_idx, const int* cache_moves_count, const int* evicted_kv_offsets,
-    const void* pend_kv, const int64_t* pend_slot, int num_seqs, int num_layers, int num_kv_heads,
-    int64_t num_blocks, int head_size, int vec_size, int block_size, int dtype, kvc_stream_t stream) {
+    const void* pend_kv, const int64_t* pend_slot, int64_t* pend_dst, int num_seqs, int num_layers,
+    int num_kv_heads, int64_t num_blocks, int head_size, int vec_size, int block_size, int dtype,
+    kvc_stream_t stream) {
   KVC_REQUIRE(num_seqs == 0 || (pend_kv && pend_slot), KVC_ERR_INVALID,
               "execute_cache_moves_deferred: pend_kv / pend_slot are required");
   KVC_REQUIRE((reinterpret_cast<uintptr_t>(pend_kv) & 15) == 0, KVC_ERR_INVALID,
               "execute_cache_moves_deferred: pend_kv must be 16-byte aligned");
   return execute_moves_impl(k_cache, v_cache, kv_metrics, kv_position, cache_moves_idx, cache_moves_count,
                             evicted_kv_offsets, num_seqs, num_layers, num_kv_heads, num_blocks, head_size,
-                            vec_size, block_size, dtype, 1, 16, pend_kv, pend_slot, stream);
+                            vec_size, block_size, dtype, 1, 16, pend_kv, pend_slot, pend_dst, stream);
+}
+
+namespace kvc {
+// every parked token to the slot it belongs to: its granted destination if a deferred move is outstanding,
+// else the slot batch_append_slots gave it; both markers are cleared
+__global__ void __launch_bounds__(256) flush_deferred_kernel(uint16_t* __restrict__ k_cache,
+                                                             uint16_t* __restrict__ v_cache,
+                                                             const uint16_t* __restrict__ pend_kv,
+                                                             int64_t* __restrict__ pend_slot,
+                                                             int64_t* __restrict__ pend_dst, int total_heads) {
+  constexpr int B = 16, D = 128, kBlockElems = B * D;
+  const int lane = threadIdx.x % kWarp;
+  const int g = blockIdx.x * (blockDim.x / kWarp) + threadIdx.x / kWarp;
+  if (g >= total_heads) return;
+  const int64_t pd = pend_dst != nullptr ? pend_dst[g] : -1;
+  const int64_t ps = pend_slot[g];
+  const int64_t slot = pd >= 0 ? pd : ps;
+  __syncwarp();
+  if (lane == 0) {
+    pend_slot[g] = -1;
+    if (pend_dst != nullptr) pend_dst[g] = -1;
+  }
+  if (slot < 0) return;
+  const uint16_t* __restrict__ pk = pend_kv + (int64_t)g * (2 * D);
+  uint16_t* kd = k_cache + (slot >> 4) * kBlockElems + (slot & 15) * 8;
+  uint16_t* vd = v_cache + (slot >> 4) * kBlockElems + (slot & 15);
+  if (lane < 16) *reinterpret_cast<uint4*>(kd + lane * (B * 8)) = *reinterpret_cast<const uint4*>(pk + lane * 8);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) vd[(lane + 32 * r) * B] = pk[D + lane + 32 * r];
+}
+}  // namespace kvc
+
+extern "C" int kvc_flush_deferred(void* k_cache, void* v_cache, const void* pend_kv, int64_t* pend_slot,
+                                  int64_t* pend_dst, int64_t num_heads, int head_size, int vec_size,
+                                  int block_size, int dtype, kvc_stream_t stream) {
+  KVC_REQUIRE((dtype == KVC_F16 || dtype == KVC_BF16) && head_size == 128 && vec_size == 8 && block_size == 16,
+              KVC_ERR_UNSUPPORTED, "flush_deferred: only the production layout (2-byte cache, head size 128, "
+              "block size 16, x = 8) supports deferred appends");
+  if (num_heads <= 0) return KVC_OK;
+  KVC_REQUIRE(k_cache && v_cache && pend_kv && pend_slot, KVC_ERR_INVALID, "flush_deferred: null tensor");
+  kvc::flush_deferred_kernel<<<(unsigned)((num_heads + 7) / 8), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<uint16_t*>(k_cache), reinterpret_cast<uint16_t*>(v_cache),
+      reinterpret_cast<const uint16_t*>(pend_kv), pend_slot, pend_dst, (int)num_heads);
+  KVC_CHECK_LAUNCH("flush_deferred_kernel");
+  return KVC_OK;
 }

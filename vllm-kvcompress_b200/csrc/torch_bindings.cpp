@@ -160,7 +160,8 @@ void execute_cache_moves(torch::Tensor& k_cache, torch::Tensor& v_cache, torch::
 void execute_cache_moves_deferred(torch::Tensor& k_cache, torch::Tensor& v_cache, torch::Tensor& kv_metrics,
                                   torch::Tensor& kv_position, torch::Tensor& cache_moves_idx,
                                   torch::Tensor& cache_moves_count, torch::Tensor& evicted_kv_offsets,
-                                  torch::Tensor& pend_kv, torch::Tensor& pend_slot) {
+                                  torch::Tensor& pend_kv, torch::Tensor& pend_slot,
+                                  const c10::optional<torch::Tensor>& pend_dst) {
   TORCH_CHECK(k_cache.dim() == 4 && v_cache.dim() == 3, "k_cache [NB, D/x, B, x], v_cache [NB, D, B] expected");
   TORCH_CHECK(k_cache.is_cuda() && v_cache.is_cuda() && k_cache.is_contiguous() && v_cache.is_contiguous(),
               "k_cache / v_cache must be contiguous CUDA tensors");
@@ -175,15 +176,44 @@ void execute_cache_moves_deferred(torch::Tensor& k_cache, torch::Tensor& v_cache
   TORCH_CHECK(pend_slot.scalar_type() == at::kLong && pend_slot.is_contiguous() && pend_slot.is_cuda() &&
                   pend_slot.numel() == heads,
               "pend_slot must be contiguous int64 [num_layers, num_seqs, num_kv_heads]");
+  int64_t* pend_dst_ptr = nullptr;
+  if (pend_dst) {
+    const auto& t = pend_dst.value();
+    TORCH_CHECK(t.scalar_type() == at::kLong && t.is_contiguous() && t.is_cuda() && t.numel() == heads,
+                "pend_dst must be contiguous int64 [num_layers, num_seqs, num_kv_heads]");
+    pend_dst_ptr = t.data_ptr<int64_t>();
+  }
   const at::cuda::OptionalCUDAGuard guard(device_of(cache_moves_idx));
   check_status(kvc_execute_cache_moves_deferred(
                    k_cache.data_ptr(), v_cache.data_ptr(), kv_metrics.data_ptr<float>(),
                    i32_mut(kv_position, "kv_position"), i32(cache_moves_idx, "cache_moves_idx"),
                    i32(cache_moves_count, "cache_moves_count"), i32(evicted_kv_offsets, "evicted_kv_offsets"),
-                   pend_kv.data_ptr(), pend_slot.data_ptr<int64_t>(), cache_moves_count.size(0),
+                   pend_kv.data_ptr(), pend_slot.data_ptr<int64_t>(), pend_dst_ptr, cache_moves_count.size(0),
                    cache_moves_count.size(1), cache_moves_count.size(2), v_cache.size(0), v_cache.size(1),
                    k_cache.size(3), v_cache.size(2), cache_dtype(k_cache), cur_stream()),
                "execute_cache_moves_deferred");
+}
+
+// additive op: see include/kvc_b200.h kvc_flush_deferred
+void flush_deferred(torch::Tensor& k_cache, torch::Tensor& v_cache, torch::Tensor& pend_kv, torch::Tensor& pend_slot,
+                    const c10::optional<torch::Tensor>& pend_dst) {
+  TORCH_CHECK(k_cache.dim() == 4 && v_cache.dim() == 3 && k_cache.is_cuda() && k_cache.is_contiguous() &&
+                  v_cache.is_contiguous(), "k_cache [NB, D/x, B, x], v_cache [NB, D, B] contiguous CUDA tensors expected");
+  const int64_t heads = pend_slot.numel();
+  TORCH_CHECK(pend_kv.scalar_type() == k_cache.scalar_type() && pend_kv.is_contiguous() &&
+                  pend_kv.numel() == heads * 2 * v_cache.size(1), "pend_kv must be contiguous [heads, 2 * head_size]");
+  TORCH_CHECK(pend_slot.scalar_type() == at::kLong && pend_slot.is_contiguous(), "pend_slot must be contiguous int64");
+  int64_t* pend_dst_ptr = nullptr;
+  if (pend_dst) {
+    const auto& t = pend_dst.value();
+    TORCH_CHECK(t.scalar_type() == at::kLong && t.is_contiguous() && t.numel() == heads, "pend_dst must match pend_slot");
+    pend_dst_ptr = t.data_ptr<int64_t>();
+  }
+  const at::cuda::OptionalCUDAGuard guard(device_of(k_cache));
+  check_status(kvc_flush_deferred(k_cache.data_ptr(), v_cache.data_ptr(), pend_kv.data_ptr(),
+                                  pend_slot.data_ptr<int64_t>(), pend_dst_ptr, heads, v_cache.size(1), k_cache.size(3),
+                                  v_cache.size(2), cache_dtype(k_cache), cur_stream()),
+               "flush_deferred");
 }
 
 // additive op: see include/kvc_b200.h kvc_select_evictions
@@ -617,7 +647,8 @@ void kvcompress_paged_attention_fused_step(
 void kvcompress_paged_attention_fused_step_deferred(
     torch::Tensor& out, torch::Tensor& kv_metrics, torch::Tensor& query, torch::Tensor& key, torch::Tensor& value,
     torch::Tensor& key_cache, torch::Tensor& value_cache, torch::Tensor& slot_mapping,
-    torch::Tensor& kv_metric_head_bias, torch::Tensor& pend_kv, torch::Tensor& pend_slot, int64_t num_kv_heads,
+    torch::Tensor& kv_metric_head_bias, torch::Tensor& pend_kv, torch::Tensor& pend_slot,
+    const c10::optional<torch::Tensor>& pend_dst, int64_t num_kv_heads,
     double scale, torch::Tensor& block_tables, torch::Tensor& context_lens, torch::Tensor& kv_position,
     torch::Tensor& last_position, torch::Tensor& kv_metric_buffer_len, int64_t block_size, int64_t max_context_len,
     const c10::optional<torch::Tensor>& alibi_slopes, const std::string& kv_cache_dtype) {
@@ -635,13 +666,21 @@ void kvcompress_paged_attention_fused_step_deferred(
               "pend_kv must be contiguous [num_seqs, num_kv_heads, 2 * head_size] of the cache dtype");
   TORCH_CHECK(pend_slot.scalar_type() == at::kLong && pend_slot.is_contiguous() &&
                   pend_slot.numel() == key.size(0) * key.size(1), "pend_slot must be contiguous int64 [num_seqs, num_kv_heads]");
+  int64_t* pend_dst_ptr = nullptr;
+  if (pend_dst) {
+    const auto& t = pend_dst.value();
+    TORCH_CHECK(t.scalar_type() == at::kLong && t.is_contiguous() && t.numel() == pend_slot.numel(),
+                "pend_dst must be contiguous int64 [num_seqs, num_kv_heads]");
+    pend_dst_ptr = t.data_ptr<int64_t>();
+  }
   const at::cuda::OptionalCUDAGuard guard(device_of(query));
   const size_t ws_bytes = kvc_paged_attention_fused_metrics_workspace_bytes(c.S, c.Hq, (int)max_context_len);
   auto ws = torch::empty({(int64_t)ws_bytes}, query.options().dtype(at::kByte));
   check_status(kvc_paged_attention_fused_step_deferred(
                    out.data_ptr(), kv_metrics.data_ptr<float>(), query.data_ptr(), key.data_ptr(), value.data_ptr(),
                    key_cache.data_ptr(), value_cache.data_ptr(), slot_mapping.data_ptr<int64_t>(),
-                   kv_metric_head_bias.data_ptr<float>(), pend_kv.data_ptr(), pend_slot.data_ptr<int64_t>(), c.S, c.Hq,
+                   kv_metric_head_bias.data_ptr<float>(), pend_kv.data_ptr(), pend_slot.data_ptr<int64_t>(),
+                   pend_dst_ptr, c.S, c.Hq,
                    (int)num_kv_heads, c.D, (float)scale, i32(block_tables, "block_tables"),
                    i32(context_lens, "context_lens"), i32(kv_position, "kv_position"),
                    i32(last_position, "last_position"), i32(kv_metric_buffer_len, "kv_metric_buffer_len"),
@@ -706,7 +745,7 @@ TORCH_LIBRARY_FRAGMENT(_C, ops) {
       "kvcompress_paged_attention_fused_step_deferred("
       "    Tensor! out, Tensor! kv_metrics, Tensor query, Tensor key, Tensor value,"
       "    Tensor! key_cache, Tensor! value_cache, Tensor slot_mapping,"
-      "    Tensor kv_metric_head_bias, Tensor! pend_kv, Tensor! pend_slot,"
+      "    Tensor kv_metric_head_bias, Tensor! pend_kv, Tensor! pend_slot, Tensor? pend_dst,"
       "    int num_kv_heads, float scale,"
       "    Tensor block_tables, Tensor context_lens,"
       "    Tensor kv_position, Tensor last_position,"
@@ -784,8 +823,12 @@ TORCH_LIBRARY_FRAGMENT(_C_kvc_ops, kvc_ops) {
       "execute_cache_moves_deferred(Tensor! k_cache, Tensor! v_cache, Tensor! kv_metrics,"
       "                             Tensor! kv_position, Tensor cache_moves_idx,"
       "                             Tensor cache_moves_count, Tensor evicted_kv_offsets,"
-      "                             Tensor pend_kv, Tensor pend_slot) -> ()");
+      "                             Tensor pend_kv, Tensor pend_slot, Tensor? pend_dst) -> ()");
   kvc_ops.impl("execute_cache_moves_deferred", torch::kCUDA, &execute_cache_moves_deferred);
+  kvc_ops.def(
+      "flush_deferred(Tensor! k_cache, Tensor! v_cache, Tensor pend_kv, Tensor! pend_slot,"
+      "               Tensor? pend_dst) -> ()");
+  kvc_ops.impl("flush_deferred", torch::kCUDA, &flush_deferred);
   // additive (not in the reference op list)
   kvc_ops.def(
       "select_evictions(Tensor! evicted_logical_indices, Tensor! evicted_kv_count,"

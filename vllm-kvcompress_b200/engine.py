@@ -68,6 +68,10 @@ class HotPathConfig:
     # at its final slot, by the next step's execute_cache_moves_deferred (see include/kvc_b200.h).  Needs the
     # fused cache write.  flush_pending() makes the cache canonical at any point.
     deferred_append: bool = True
+    # deferred move (with deferred_append): when a head's only move takes the parked token, its K/V is stored by
+    # the next fused attention step (which has the destination block staged and writes whole sectors back)
+    # instead of by execute_cache_moves (partial-sector stores into a block it has to fetch for that).
+    deferred_move: bool = True
     host_copy_layers: int = 4          # step_host: layers per H2D / D2H copy
     seed: int = 0
 
@@ -135,6 +139,8 @@ class DecodeHotPath:
         if self.deferred:
             self.pend_kv = torch.zeros((L, S, H, 2 * D), dtype=cfg.dtype, device=device)
             self.pend_slot = torch.full((L, S, H), -1, dtype=torch.int64, device=device)
+            self.pend_dst = (torch.full((L, S, H), -1, dtype=torch.int64, device=device)
+                             if cfg.deferred_move else None)
         self.alloc = None
         if cfg.allocator == "device":
             self.alloc = capi.DeviceBlockAllocator(st.NB, st.block_tables, st.context_lens, st.kv_position, B)
@@ -194,7 +200,8 @@ class DecodeHotPath:
                                                      self.evicted_kv_count, offs, st.block_tables, ctx, B)
         if self.deferred:
             ops.execute_cache_moves_deferred(st.k_cache, st.v_cache, st.kv_metrics, st.kv_position,
-                                             self.cache_moves, self.moves_count, offs, self.pend_kv, self.pend_slot)
+                                             self.cache_moves, self.moves_count, offs, self.pend_kv, self.pend_slot,
+                                             self.pend_dst)
         else:
             ops.execute_cache_moves(st.k_cache, st.v_cache, st.kv_metrics, st.kv_position, self.cache_moves,
                                     self.moves_count, offs, 1, 16)
@@ -206,10 +213,7 @@ class DecodeHotPath:
         the reference's reshape_and_cache + execute_cache_moves sequence leaves."""
         if not self.deferred:
             return
-        self.moves_count.zero_()
-        ops.execute_cache_moves_deferred(self.st.k_cache, self.st.v_cache, self.st.kv_metrics, self.st.kv_position,
-                                         self.cache_moves, self.moves_count, self.offs, self.pend_kv, self.pend_slot)
-        self.pend_slot.fill_(-1)
+        ops.flush_deferred(self.st.k_cache, self.st.v_cache, self.pend_kv, self.pend_slot, self.pend_dst)
 
     # ------------------------------------------------------------------ append + forward
     def append_slots(self) -> None:
@@ -241,7 +245,8 @@ class DecodeHotPath:
         if self.deferred:
             ops.paged_attention_kvc_fused_step_deferred(o, st.kv_metrics, q, k, v, st.k_cache, st.v_cache,
                                                         self.slot_mapping[l].reshape(-1), self.head_bias[l],
-                                                        self.pend_kv[l], self.pend_slot[l], H, self.scale,
+                                                        self.pend_kv[l], self.pend_slot[l],
+                                                        None if self.pend_dst is None else self.pend_dst[l], H, self.scale,
                                                         st.block_tables[l], st.context_lens[l], st.kv_position,
                                                         last_pos, self.zeros_s, B, self.max_ctx)
             self.launches += 1
@@ -384,7 +389,8 @@ class DecodeHotPath:
                     v = qkv[l][:, (Hq + H) * D:].view(-1, H, D)
                     ops.paged_attention_kvc_fused_step_deferred(
                         o, st.kv_metrics, q, k, v, st.k_cache, st.v_cache, self.slot_mapping[l].reshape(-1),
-                        self.head_bias[l], self.pend_kv[l], self.pend_slot[l], H, self.scale, st.block_tables[l],
+                        self.head_bias[l], self.pend_kv[l], self.pend_slot[l],
+                        None if self.pend_dst is None else self.pend_dst[l], H, self.scale, st.block_tables[l],
                         st.context_lens[l], st.kv_position, last_pos, self.zeros_s, B, self.max_ctx)
                 elif cfg.fused_metrics and cfg.fused_cache_write:
                     k = qkv[l][:, Hq * D: (Hq + H) * D].view(-1, H, D)
@@ -402,16 +408,26 @@ class DecodeHotPath:
                                                st.block_tables[l], st.context_lens[l], st.kv_position, last_pos,
                                                self.zeros_s, B, self.max_ctx, None, "auto", 1.0, 1.0, True)
 
+        armed0 = self.pend_dst.clone() if getattr(self, "pend_dst", None) is not None else None
         attn_only()
         torch.cuda.synchronize()
+        if armed0 is not None:
+            self.pend_dst.copy_(armed0)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             attn_only()
         graph.replay()
         torch.cuda.synchronize()
+        if armed0 is not None:
+            self.pend_dst.copy_(armed0)
         pairs = []
+        # every replay must do the step's real work: the deferred moves recorded by the last compression are
+        # consumed (pend_dst reset) by the first launch that applies them, so they are re-armed before each replay
+        armed = self.pend_dst.clone() if getattr(self, "pend_dst", None) is not None else None
         for _ in range(steps):
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            if armed is not None:
+                self.pend_dst.copy_(armed)
             ev[0].record()
             graph.replay()
             ev[1].record()
