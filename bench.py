@@ -43,6 +43,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-deferred-append", action="store_true",
+                    help="store every new token to the cache at once (reference op sequence)")
+    ap.add_argument("--no-deferred-move", action="store_true",
+                    help="execute_cache_moves stores the parked tokens itself instead of the next attention step")
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
     ap.add_argument("--layers", type=int, default=32)
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama3-70b"],
@@ -199,6 +203,8 @@ def workload_config(args, batch):
             "global_batch": batch, "seq_len": 6000, "parallelism": "request-sharded replicas",
             "l2": "inputs larger than L2 (per-step KV read ~4.6 GB vs 126 MB L2)",
             "selection": args.selection, "allocator": getattr(args, "allocator", "device"),
+            "deferred_append": not getattr(args, "no_deferred_append", False),
+            "deferred_move": not getattr(args, "no_deferred_move", False),
             "fused_metrics": not args.unfused_metrics,
             "fused_cache_write": not getattr(args, "separate_cache_write", False),
             "launch": "one CUDA graph per step" if args.selection == "fused" else "eager"}
@@ -314,7 +320,8 @@ def main():
     cfg = HotPathConfig(num_seqs=args.batch, num_layers=args.layers, selection=args.selection,
                         fused_metrics=not args.unfused_metrics, allocator=args.allocator,
                         host_copy_layers=args.host_copy_layers, **preset,
-                        fused_cache_write=not args.separate_cache_write, seed=rank)
+                        fused_cache_write=not args.separate_cache_write, seed=rank,
+                        deferred_append=not args.no_deferred_append, deferred_move=not args.no_deferred_move)
     from vllm_kvcompress_b200 import sharding
     # the only collective on this path: one start-up broadcast (stands in for the weight broadcast
     # of the 8-replica layout); every replica then owns an independent cache for its own requests
@@ -395,7 +402,7 @@ def main():
                 "d2h_bytes_per_step": out_host.numel() * out_host.element_size()},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "paged_attention_stream_kernel (cache write + attention + metric aggregation), %d launches/step" % L,
+        "roofline": {"bound": "hbm", "kernel": "paged_attention_stream_kernel (cache write + deferred moves + attention + metric aggregation), %d launches/step" % L,
                      "achieved": attn_b / (attn_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": attn_b / (attn_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
                      "bytes_per_launch": attn_b, "ms_per_launch": attn_ms,

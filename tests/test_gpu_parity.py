@@ -893,3 +893,52 @@ def test_execute_moves_many_heads_small_counts_vs_oracle(capi, O, deferred, full
     env = dict(os.environ, KVC_MOVES_FULLROW=fullrow)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_k4_many_heads_short_lists_vs_oracle(capi, O):
+    """schedule_t1_cache_moves at decode-time shape (>= 4096 heads: 32 heads per warp, heads with at most one
+    evicted slot settled by their own lane, longer lists by the whole warp): counts and (dst, src) pairs
+    bit-exact against the C oracle, incl. evicting the last token itself (no move) and lists of 2..20."""
+    rs = np.random.RandomState(9)
+    S, L, H, B, MB = 6, 12, 64, 16, 6            # 4608 heads
+    heads = S * L * H
+    ctx = rs.randint(1, MB * B + 1, size=(L, S, H)).astype(np.int32)
+    nblk = (ctx + B - 1) // B
+    NB = int(nblk.sum()) + 5
+    perm = rs.permutation(NB).astype(np.int32)
+    bt = np.zeros((L, S, H, MB), np.int32)
+    k = 0
+    for idx in np.ndindex(L, S, H):
+        n = int(nblk[idx])
+        bt[idx][:n] = perm[k:k + n]
+        k += n
+    ctx_slh = ctx.transpose(1, 0, 2)
+    alloc = (nblk.transpose(1, 0, 2) * B).reshape(-1)
+    offs = np.concatenate([[0], np.cumsum(alloc)[:-1]]).astype(np.int32).reshape(S, L, H)
+    N = int(alloc.sum())
+    cnt = np.zeros((S, L, H), np.int32)
+    elog = np.full(N, MAX_INT, np.int32)
+    for idx in np.ndindex(S, L, H):
+        n = int(ctx_slh[idx])
+        c = int(rs.choice([0, 1, 1, 1, 1, 2, 3, 7, 20]))
+        c = min(c, n)
+        if c == 1 and rs.rand() < 0.15:
+            ev = np.array([n - 1])                # the last token itself: nothing to move
+        else:
+            ev = np.sort(rs.choice(n, size=c, replace=False))
+        cnt[idx] = c
+        elog[offs[idx]:offs[idx] + c] = ev
+    wm = np.zeros((N, 2), np.int32)
+    wc = np.zeros((S, L, H), np.int32)
+    O.schedule_cache_moves(wm, wc, elog, cnt, offs, bt, ctx, B)
+    moves = torch.zeros((N, 2), dtype=torch.int32, device="cuda")
+    mcnt = torch.full((S, L, H), -3, dtype=torch.int32, device="cuda")
+    capi.schedule_t1_cache_moves(moves, mcnt, cu(elog), cu(cnt), cu(offs), cu(bt), cu(ctx), B)
+    got_c, got_m = mcnt.cpu().numpy(), moves.cpu().numpy()
+    np.testing.assert_array_equal(got_c, wc)
+    valid = np.zeros(N, bool)
+    for o, c in zip(offs.reshape(-1), wc.reshape(-1)):
+        valid[o:o + c] = True
+    np.testing.assert_array_equal(got_m[valid], wm[valid])
+    assert (got_m[~valid] == 0).all()
+    assert int((wc == 1).sum()) > 1000 and int((wc > 1).sum()) > 500

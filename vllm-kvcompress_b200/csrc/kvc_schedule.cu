@@ -123,7 +123,7 @@ __global__ void count_block_evictions_kernel(int* __restrict__ evicted_block_cou
 // K4  schedule_t1_cache_moves: one warp per head
 // =============================================================================
 template <int B>
-__global__ void __launch_bounds__(128) schedule_moves_kernel(
+__device__ __forceinline__ void schedule_moves_head(
     int* __restrict__ cache_moves_idx,                  // [max_evicted_kv, 2]
     int* __restrict__ cache_moves_count,                // [S,L,H]
     const int* __restrict__ evicted_logical_indices,    // [max_evicted_kv]
@@ -131,13 +131,7 @@ __global__ void __launch_bounds__(128) schedule_moves_kernel(
     const int* __restrict__ evicted_kv_offsets,         // [S,L,H]
     const int* __restrict__ block_tables,               // [L,S,H,MB]
     const int* __restrict__ context_lens,               // [L,S,H]
-    int num_seqs, int num_layers, int num_kv_heads, int MB) {
-  __shared__ unsigned occ[4][kWarp];  // per-warp 1024-bit window of evicted tail positions
-  const int wid = threadIdx.x / kWarp;
-  const int lane = threadIdx.x % kWarp;
-  const int g = blockIdx.x * (blockDim.x / kWarp) + wid;  // (s, l, h) flat
-  const int total = num_seqs * num_layers * num_kv_heads;
-  if (g >= total) return;
+    int num_seqs, int num_layers, int num_kv_heads, int MB, unsigned (*occ)[kWarp], int wid, int lane, int g) {
   const int s = g / (num_layers * num_kv_heads);
   const int l = (g / num_kv_heads) % num_layers;
   const int h = g % num_kv_heads;
@@ -213,6 +207,75 @@ __global__ void __launch_bounds__(128) schedule_moves_kernel(
   }
 }
 
+
+
+// one warp per head (few heads, long eviction lists: post-prefill compression)
+template <int B>
+__global__ void __launch_bounds__(128) schedule_moves_kernel(
+    int* __restrict__ cache_moves_idx, int* __restrict__ cache_moves_count,
+    const int* __restrict__ evicted_logical_indices, const int* __restrict__ evicted_kv_count,
+    const int* __restrict__ evicted_kv_offsets, const int* __restrict__ block_tables,
+    const int* __restrict__ context_lens, int num_seqs, int num_layers, int num_kv_heads, int MB) {
+  __shared__ unsigned occ[4][kWarp];  // per-warp 1024-bit window of evicted tail positions
+  const int wid = threadIdx.x / kWarp;
+  const int lane = threadIdx.x % kWarp;
+  const int g = blockIdx.x * (blockDim.x / kWarp) + wid;  // (s, l, h) flat
+  if (g >= num_seqs * num_layers * num_kv_heads) return;
+  schedule_moves_head<B>(cache_moves_idx, cache_moves_count, evicted_logical_indices, evicted_kv_count,
+                         evicted_kv_offsets, block_tables, context_lens, num_seqs, num_layers, num_kv_heads, MB,
+                         occ, wid, lane, g);
+}
+
+// many heads with 0 or 1 evicted slot each (decode-time continual compression): a warp looks at 32 heads, every
+// lane settles its own head when c <= 1 (closed form: the one evicted index E0 takes the last token unless it
+// IS the last token), the heads with longer lists are then done by the whole warp one after the other
+template <int B>
+__global__ void __launch_bounds__(128) schedule_moves_many_kernel(
+    int* __restrict__ cache_moves_idx, int* __restrict__ cache_moves_count,
+    const int* __restrict__ evicted_logical_indices, const int* __restrict__ evicted_kv_count,
+    const int* __restrict__ evicted_kv_offsets, const int* __restrict__ block_tables,
+    const int* __restrict__ context_lens, int num_seqs, int num_layers, int num_kv_heads, int MB) {
+  __shared__ unsigned occ[4][kWarp];
+  const int wid = threadIdx.x / kWarp;
+  const int lane = threadIdx.x % kWarp;
+  const int total = num_seqs * num_layers * num_kv_heads;
+  const int base = (blockIdx.x * (blockDim.x / kWarp) + wid) * kWarp;
+  if (base >= total) return;
+  const int g = base + lane;
+  int c = 0;
+  if (g < total) {
+    c = evicted_kv_count[g];
+    if (c <= 1) {
+      int m = 0;
+      if (c == 1) {
+        const int s = g / (num_layers * num_kv_heads);
+        const int l = (g / num_kv_heads) % num_layers;
+        const int h = g % num_kv_heads;
+        const int lsh = (l * num_seqs + s) * num_kv_heads + h;
+        const int off = evicted_kv_offsets[g];
+        const int n = context_lens[lsh];
+        const int e0 = evicted_logical_indices[off];
+        if (e0 < n - 1) {  // dst = E[0] < new_n = n - 1, src = the last token
+          const int* __restrict__ bt = block_tables + (int64_t)lsh * MB;
+          const int src = n - 1;
+          reinterpret_cast<int2*>(cache_moves_idx)[(int64_t)off] =
+              make_int2(bt[e0 / B] * B + e0 % B, bt[src / B] * B + src % B);
+          m = 1;
+        }
+      }
+      cache_moves_count[g] = m;
+    }
+  }
+  unsigned todo = __ballot_sync(0xffffffffu, c > 1);
+  while (todo) {
+    const int l0 = __ffs(todo) - 1;
+    todo &= todo - 1;
+    schedule_moves_head<B>(cache_moves_idx, cache_moves_count, evicted_logical_indices, evicted_kv_count,
+                           evicted_kv_offsets, block_tables, context_lens, num_seqs, num_layers, num_kv_heads, MB,
+                           occ, wid, lane, base + l0);
+    __syncwarp();
+  }
+}
 
 // =============================================================================
 // K1  schedule_cache_evictions as a chunked stable multi-bin rank
@@ -649,13 +712,20 @@ extern "C" int kvc_schedule_t1_cache_moves(
               "schedule_t1_cache_moves: cache_moves_idx must be 8-byte aligned");
   const int total = num_seqs * num_layers * num_kv_heads;
   if (total <= 0) return KVC_OK;
-  const dim3 grid(ceil_div(total, 4)), block(128);
+  const bool many = total >= 4096;  // decode-time batches: 32 heads per warp
+  const dim3 grid(many ? ceil_div(ceil_div(total, 32), 4) : ceil_div(total, 4)), block(128);
   cudaStream_t st = as_stream(stream);
 #define KVC_LAUNCH_K4(BS)                                                              \
-  schedule_moves_kernel<BS><<<grid, block, 0, st>>>(                                   \
-      cache_moves_idx, cache_moves_count, evicted_logical_indices, evicted_kv_count,   \
-      evicted_kv_offsets, block_tables, context_lens, num_seqs, num_layers,            \
-      num_kv_heads, max_num_blocks_per_seq)
+  if (many)                                                                            \
+    schedule_moves_many_kernel<BS><<<grid, block, 0, st>>>(                            \
+        cache_moves_idx, cache_moves_count, evicted_logical_indices, evicted_kv_count, \
+        evicted_kv_offsets, block_tables, context_lens, num_seqs, num_layers,          \
+        num_kv_heads, max_num_blocks_per_seq);                                         \
+  else                                                                                 \
+    schedule_moves_kernel<BS><<<grid, block, 0, st>>>(                                 \
+        cache_moves_idx, cache_moves_count, evicted_logical_indices, evicted_kv_count, \
+        evicted_kv_offsets, block_tables, context_lens, num_seqs, num_layers,          \
+        num_kv_heads, max_num_blocks_per_seq)
   switch (block_size) {
     case 1: KVC_LAUNCH_K4(1); break;
     case 2: KVC_LAUNCH_K4(2); break;

@@ -370,71 +370,58 @@ class DecodeHotPath:
 
     # ------------------------------------------------------------------ measurement helper
     def profile_attention(self, qkv: torch.Tensor, out: torch.Tensor, steps: int = 5):
-        """Device time of the attention launches alone: the L launches of one step (current state)
-        are captured in a CUDA graph, so no host launch gap sits between the two CUDA events that
-        bracket each replay (events recorded on the launching stream).  Returns (mean ms per
-        launch, mean algorithmic bytes per launch)."""
+        """Device time of the attention launches alone, doing exactly the work they do inside a step: the
+        compression and append of one more step run first (so the parked tokens and deferred moves of that step
+        are outstanding), then the L launches are captured in a CUDA graph -- no host launch gap sits between the
+        two CUDA events that bracket each replay (events recorded on the launching stream).  The state the
+        launches consume (pend_dst / pend_kv) is re-armed before every replay, outside the events.  Returns
+        (mean ms per launch, mean algorithmic bytes per launch)."""
         cfg, st = self.cfg, self.st
         L = cfg.num_layers
         H, Q, D, B = cfg.num_kv_heads, cfg.queries_per_kv, cfg.head_size, cfg.block_size
         Hq = H * Q
+        self.compress()
+        self.append_slots()
         last_pos = self.seq_len - 1
+        nbytes = self.attention_bytes() / L
 
         def attn_only():
             for l in range(L):
-                q = qkv[l][:, : Hq * D].view(-1, Hq, D)
-                o = out[l].view(-1, Hq, D)
-                if self.deferred:
-                    k = qkv[l][:, Hq * D: (Hq + H) * D].view(-1, H, D)
-                    v = qkv[l][:, (Hq + H) * D:].view(-1, H, D)
-                    ops.paged_attention_kvc_fused_step_deferred(
-                        o, st.kv_metrics, q, k, v, st.k_cache, st.v_cache, self.slot_mapping[l].reshape(-1),
-                        self.head_bias[l], self.pend_kv[l], self.pend_slot[l],
-                        None if self.pend_dst is None else self.pend_dst[l], H, self.scale, st.block_tables[l],
-                        st.context_lens[l], st.kv_position, last_pos, self.zeros_s, B, self.max_ctx)
-                elif cfg.fused_metrics and cfg.fused_cache_write:
-                    k = qkv[l][:, Hq * D: (Hq + H) * D].view(-1, H, D)
-                    v = qkv[l][:, (Hq + H) * D:].view(-1, H, D)
-                    ops.paged_attention_kvc_fused_step(o, st.kv_metrics, q, k, v, st.k_cache, st.v_cache,
-                                                       self.slot_mapping[l].reshape(-1), self.head_bias[l], H,
-                                                       self.scale, st.block_tables[l], st.context_lens[l],
-                                                       st.kv_position, last_pos, self.zeros_s, B, self.max_ctx)
-                elif cfg.fused_metrics:
-                    ops.paged_attention_kvc_fused_metrics(o, st.kv_metrics, q, st.k_cache, st.v_cache, H,
-                                                          self.scale, st.block_tables[l], st.context_lens[l],
-                                                          st.kv_position, last_pos, self.zeros_s, B, self.max_ctx)
-                else:
-                    ops.paged_attention_kvc_v1(o, self.temp_metrics, q, st.k_cache, st.v_cache, H, self.scale,
-                                               st.block_tables[l], st.context_lens[l], st.kv_position, last_pos,
-                                               self.zeros_s, B, self.max_ctx, None, "auto", 1.0, 1.0, True)
+                self.forward_layer(l, qkv[l], out[l], last_pos)
+            self._aggregate_unfused()
 
-        armed0 = self.pend_dst.clone() if getattr(self, "pend_dst", None) is not None else None
+        armed = None
+        if self.deferred:
+            armed = [(t, t.clone()) for t in (self.pend_kv, self.pend_slot) +
+                     ((self.pend_dst,) if self.pend_dst is not None else ())]
+
+        def rearm():
+            if armed is not None:
+                for t, v in armed:
+                    t.copy_(v)
+
+        n0 = self.launches
         attn_only()
         torch.cuda.synchronize()
-        if armed0 is not None:
-            self.pend_dst.copy_(armed0)
+        rearm()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             attn_only()
+        rearm()
         graph.replay()
         torch.cuda.synchronize()
-        if armed0 is not None:
-            self.pend_dst.copy_(armed0)
         pairs = []
-        # every replay must do the step's real work: the deferred moves recorded by the last compression are
-        # consumed (pend_dst reset) by the first launch that applies them, so they are re-armed before each replay
-        armed = self.pend_dst.clone() if getattr(self, "pend_dst", None) is not None else None
         for _ in range(steps):
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            if armed is not None:
-                self.pend_dst.copy_(armed)
+            rearm()
             ev[0].record()
             graph.replay()
             ev[1].record()
             pairs.append(ev)
         torch.cuda.synchronize()
+        self.launches = n0
         ms = sum(a.elapsed_time(b) for a, b in pairs) / (len(pairs) * L)
-        return ms, self.attention_bytes() / L
+        return ms, nbytes
 
     @property
     def tokens_per_step(self) -> int:
@@ -444,4 +431,11 @@ class DecodeHotPath:
         """Algorithmic bytes of one step's attention launches: K+V of every
         context token once (2*D*2 B) + position read (4 B) + metric read-modify-write (8 B)."""
         ctx_total = int(self.st.context_lens.sum())
-        return ctx_total * (2 * self.cfg.head_size * 2 + 4 + 8)
+        n = ctx_total * (2 * self.cfg.head_size * 2 + 4 + 8)
+        if self.cfg.fused_metrics and self.cfg.fused_cache_write:
+            # the same launches also store the step's new token of every head (K6: K + V + metric) ...
+            n += self.st.context_lens.numel() * (2 * self.cfg.head_size * 2 + 4)
+            # ... and apply the deferred moves recorded by the compression (K5: 1048 B per move, SURVEY 8d)
+            if getattr(self, "pend_dst", None) is not None:
+                n += int((self.pend_dst >= 0).sum()) * 1048
+        return n
