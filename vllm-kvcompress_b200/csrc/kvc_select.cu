@@ -674,8 +674,9 @@ __global__ void __launch_bounds__(kSeqThreads, 2) select_fused_seq_kernel(Select
   int* s_r0 = s_n + LH;                                      // [LH] hanging tokens
   int* s_off = s_r0 + LH;                                    // [LH] segment offset
   unsigned* s_third = dyn + 6 * LH;                          // [LH] smallest third-smallest key of a lane (KEEP2)
-  unsigned* row = dyn + 7 * LH + w * (32 * KPL);             // per-warp compaction row
-  unsigned* s_small = dyn + 7 * LH + kSeqWarps * 32 * KPL;   // [LH][64] two smallest keys per lane (KEEP2)
+  unsigned* s_min = dyn + 7 * LH;                            // [LH] smallest candidate key of the head
+  unsigned* row = dyn + 8 * LH + w * (32 * KPL);             // per-warp compaction row
+  unsigned* s_small = dyn + 8 * LH + kSeqWarps * 32 * KPL;   // [LH][64] two smallest keys per lane (KEEP2)
   int* s_bt = reinterpret_cast<int*>(s_small + (KEEP2 ? LH * 64 : 0));  // [LH][MB] (BTS)
   const int g0 = s * LH;
   const int E = p.budgets[s];
@@ -688,17 +689,30 @@ __global__ void __launch_bounds__(kSeqThreads, 2) select_fused_seq_kernel(Select
     s_off[hd] = p.offsets[g0 + hd];
   }
   if (BTS) {
-    for (int hd = w; hd < LH; hd += kSeqWarps) {
-      const int* __restrict__ src = p.block_tables + (int64_t)(((hd / p.H) * p.S + s) * p.H + hd % p.H) * p.MB;
-      for (int b = lane; b < p.MB; b += kWarp) s_bt[hd * p.MB + b] = src[b];
+    if ((p.MB & 3) == 0) {  // rows are 16 B aligned: a thread copies a row with 16 B loads
+      const int nv = p.MB >> 2;
+      for (int i = tid; i < LH * nv; i += kSeqThreads) {
+        const int hd = i / nv, v = i - hd * nv;
+        const int4* __restrict__ src = reinterpret_cast<const int4*>(
+            p.block_tables + (int64_t)(((hd / p.H) * p.S + s) * p.H + hd % p.H) * p.MB);
+        reinterpret_cast<int4*>(s_bt + hd * p.MB)[v] = src[v];
+      }
+    } else {
+      for (int i = tid; i < LH * p.MB; i += kSeqThreads) {
+        const int hd = i / p.MB, b = i - hd * p.MB;
+        s_bt[i] = p.block_tables[(int64_t)(((hd / p.H) * p.S + s) * p.H + hd % p.H) * p.MB + b];
+      }
     }
   }
   __syncthreads();
   if (stop_after == 1) return;  // (profiling aid: KVC_SELECT_STOP_AFTER truncates the kernel after a phase)
 
   // keys of the lane's slots of head hd: k[4 j + r] <-> logical index 4 (lane + 32 j) + r.  The loads are
-  // unconditional (lanes beyond the context read block 0), so nothing separates the loads of two heads.
-  auto head_keys = [&](int hd, int n, unsigned (&k)[KPL]) {
+  // unconditional (lanes beyond the context read block 0) and separate from the key arithmetic, so the loads of
+  // the next head can be in flight while this one is processed.
+  struct Raw { float4 m[NG]; int4 q[NG]; };
+  auto issue = [&](int hd, Raw& r) {
+    const int n = s_n[hd];
     const int l = hd / p.H, h = hd % p.H;
     const int* __restrict__ bt = p.block_tables + (int64_t)((l * p.S + s) * p.H + h) * p.MB;
 #pragma unroll
@@ -708,16 +722,30 @@ __global__ void __launch_bounds__(kSeqThreads, 2) select_fused_seq_kernel(Select
       const int bi = in ? (i0 >> 4) : 0;
       const int phys = BTS ? s_bt[hd * p.MB + bi] : bt[bi];
       const int64_t slot = in ? (int64_t)phys * 16 + (i0 & 15) : 0;
-      const float4 m4 = *reinterpret_cast<const float4*>(p.kv_metrics + slot);
-      const int4 q4 = *reinterpret_cast<const int4*>(p.kv_position + slot);
-      const float m[4] = {m4.x, m4.y, m4.z, m4.w};
-      const int q[4] = {q4.x, q4.y, q4.z, q4.w};
+      r.m[j] = *reinterpret_cast<const float4*>(p.kv_metrics + slot);
+      r.q[j] = *reinterpret_cast<const int4*>(p.kv_position + slot);
+    }
+  };
+  auto build = [&](int hd, const Raw& r, unsigned (&k)[KPL]) {
+    const int n = s_n[hd];
+    const int l = hd / p.H, h = hd % p.H;
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const unsigned key = PLAIN ? slot_key_plain(m[r], q[r], max_pos) : slot_key(p, m[r], q[r], max_pos, last_pos, l, h);
-        k[4 * j + r] = (i0 + r < n) ? key : kInfKey;
+    for (int j = 0; j < NG; ++j) {
+      const int i0 = 4 * (lane + 32 * j);
+      const float m[4] = {r.m[j].x, r.m[j].y, r.m[j].z, r.m[j].w};
+      const int q[4] = {r.q[j].x, r.q[j].y, r.q[j].z, r.q[j].w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const unsigned key = PLAIN ? slot_key_plain(m[t], q[t], max_pos) : slot_key(p, m[t], q[t], max_pos, last_pos, l, h);
+        k[4 * j + t] = (i0 + t < n) ? key : kInfKey;
       }
     }
+  };
+  auto head_keys = [&](int hd, int n, unsigned (&k)[KPL]) {
+    (void)n;
+    Raw r;
+    issue(hd, r);
+    build(hd, r, k);
   };
 
   // keep keys <= T1, compact, sort on the smallest network that holds them, write the completion keys
@@ -758,54 +786,52 @@ __global__ void __launch_bounds__(kSeqThreads, 2) select_fused_seq_kernel(Select
 
   unsigned T1 = kInfKey;
   if (E > 0) {
-    // ---- A: bounds ----
-    for (int hd0 = w; hd0 < LH; hd0 += kPair * kSeqWarps) {   // two heads per iteration: their loads overlap
-      const int hd1 = hd0 + kSeqWarps;
-      const bool two = kPair == 2 && hd1 < LH;
-      unsigned ka[KPL], kb[KPL];
-      head_keys(hd0, s_n[hd0], ka);
-      if (two) head_keys(hd1, s_n[hd1], kb);
+    // ---- A: bounds ----  (one head at a time, the next head's loads already in flight)
+    Raw cur;
+    if (w < LH) issue(w, cur);
+    for (int hd = w; hd < LH; hd += kSeqWarps) {
+      Raw nxt;
+      const bool more = hd + kSeqWarps < LH;
+      if (kPair == 2 && more) issue(hd + kSeqWarps, nxt);
+      unsigned kk[KPL];
+      build(hd, cur, kk);
+      const int r0 = s_r0[hd];
+      unsigned m1 = kInfKey, m2 = kInfKey, m3 = kInfKey;
+      int idx = 0x7fffffff;
 #pragma unroll
-      for (int t = 0; t < kPair; ++t) {
-        if (t == 1 && !two) break;
-        unsigned* kk = t ? kb : ka;
-        const int hd = t ? hd1 : hd0;
-        const int r0 = s_r0[hd];
-        unsigned m1 = kInfKey, m2 = kInfKey, m3 = kInfKey;
-        int idx = 0x7fffffff;
+      for (int j = 0; j < NG; ++j)
 #pragma unroll
-        for (int j = 0; j < NG; ++j)
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const unsigned k = kk[4 * j + r];
-            if (k < m1) idx = 4 * (lane + 32 * j) + r;   // strict: the lane's first index wins ties
-            const unsigned b1 = max(m1, k);
-            m1 = min(m1, k);
-            const unsigned b2 = max(m2, b1);
-            m2 = min(m2, b1);
-            m3 = min(m3, b2);
-          }
-        unsigned gm = m1;
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) gm = min(gm, __shfl_xor_sync(0xffffffffu, gm, d));
-        int amin = (m1 == gm) ? idx : 0x7fffffff;       // smallest logical index attaining the minimum
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) amin = min(amin, __shfl_xor_sync(0xffffffffu, amin, d));
-        unsigned u = gm;                                // r0 == 1: the minimum itself
-        if (r0 != 1) {
-          unsigned sm1[1] = {m1};
-          warp_bitonic_sort<1>(sm1, lane);
-          u = (r0 >= 1 && r0 <= kWarp) ? __shfl_sync(0xffffffffu, sm1[0], (r0 - 1) & 31) : kInfKey;
+        for (int r = 0; r < 4; ++r) {
+          const unsigned k = kk[4 * j + r];
+          if (k < m1) idx = 4 * (lane + 32 * j) + r;   // strict: the lane's first index wins ties
+          const unsigned b1 = max(m1, k);
+          m1 = min(m1, k);
+          const unsigned b2 = max(m2, b1);
+          m2 = min(m2, b1);
+          m3 = min(m3, b2);
         }
-        if (KEEP2) {
-          unsigned t3 = m3;
+      unsigned gm = m1;
 #pragma unroll
-          for (int d = 16; d >= 1; d >>= 1) t3 = min(t3, __shfl_xor_sync(0xffffffffu, t3, d));
-          *reinterpret_cast<uint2*>(s_small + hd * 64 + 2 * lane) = make_uint2(m1, m2);
-          if (lane == 0) s_third[hd] = t3;
-        }
-        if (lane == 0) { s_first[hd] = u; s_argmin[hd] = amin; }
+      for (int d = 16; d >= 1; d >>= 1) gm = min(gm, __shfl_xor_sync(0xffffffffu, gm, d));
+      int amin = (m1 == gm) ? idx : 0x7fffffff;       // smallest logical index attaining the minimum
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) amin = min(amin, __shfl_xor_sync(0xffffffffu, amin, d));
+      unsigned u = gm;                                // r0 == 1: the minimum itself
+      if (r0 != 1) {
+        unsigned sm1[1] = {m1};
+        warp_bitonic_sort<1>(sm1, lane);
+        u = (r0 >= 1 && r0 <= kWarp) ? __shfl_sync(0xffffffffu, sm1[0], (r0 - 1) & 31) : kInfKey;
       }
+      if (KEEP2) {
+        unsigned t3 = m3;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) t3 = min(t3, __shfl_xor_sync(0xffffffffu, t3, d));
+        *reinterpret_cast<uint2*>(s_small + hd * 64 + 2 * lane) = make_uint2(m1, m2);
+        if (lane == 0) s_third[hd] = t3;
+      }
+      if (lane == 0) { s_first[hd] = u; s_argmin[hd] = amin; s_min[hd] = gm; }
+      if (kPair == 2) cur = nxt;
+      else if (more) issue(hd + kSeqWarps, cur);
     }
     __syncthreads();
     if (stop_after == 2) return;
@@ -822,8 +848,16 @@ __global__ void __launch_bounds__(kSeqThreads, 2) select_fused_seq_kernel(Select
       for (int q = lane; q < nblk; q += kWarp) ev[q] = kInfKey;
     } else if (KEEP2 && s_third[hd] > T1) {   // every key <= T1 is among the lanes' two smallest
       const uint2 v = *reinterpret_cast<const uint2*>(s_small + hd * 64 + 2 * lane);
-      unsigned k2[2] = {v.x, v.y};
-      prune_sort_write(k2, T1, s_r0[hd], nblk, ev);
+      const int r0 = s_r0[hd];
+      const int ncand = __popc(__ballot_sync(0xffffffffu, v.x <= T1 && v.x != kInfKey)) +
+                        __popc(__ballot_sync(0xffffffffu, v.y <= T1 && v.y != kInfKey));
+      if (r0 == 1 && ncand <= B) {
+        // at most one completion key (rank 0 = the head's smallest candidate): no sort needed
+        for (int q = lane; q < nblk; q += kWarp) ev[q] = (q == 0 && ncand >= 1) ? s_min[hd] : kInfKey;
+      } else {
+        unsigned k2[2] = {v.x, v.y};
+        prune_sort_write(k2, T1, r0, nblk, ev);
+      }
     } else {
       unsigned k[KPL];
       head_keys(hd, s_n[hd], k);
@@ -996,7 +1030,7 @@ extern "C" int kvc_select_evictions_ex(
     const bool can_fuse = warp_path && block_size == 16 && LH <= 8192;
     if (can_fuse && mode != 1 && (mode == 2 || num_seqs >= 96)) {
       const int kpl = max_slots <= 256 ? 8 : 16;
-      const size_t base_words = (size_t)7 * LH + (size_t)kSeqWarps * 32 * kpl;
+      const size_t base_words = (size_t)8 * LH + (size_t)kSeqWarps * 32 * kpl;
       const size_t bt_words = (size_t)LH * max_num_blocks_per_seq, small_words = (size_t)LH * 64;
       const size_t budget = 100 * 1024 / sizeof(unsigned);   // two CTAs per SM must still fit
       const bool keep2 = base_words + small_words <= budget;
