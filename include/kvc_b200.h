@@ -309,10 +309,11 @@ KVC_API int kvc_paged_attention_fused_step(
  *     registers).  Production layout only (2-byte cache, D=128, B=16, x=8).
  *   Deferred MOVE (pend_dst [L, S, H] int64, optional in both calls, initialised to -1): when the head's only
  *     move takes the parked token, kvc_execute_cache_moves_deferred moves metric and position only and
- *     records the destination slot in pend_dst; the next kvc_paged_attention_fused_step_deferred patches the
- *     parked K/V into its staged copy of that block (so its own attention already sees the token), writes
- *     the block's touched 32 B sectors back whole -- no read-for-ownership of 144 partially written sectors
- *     -- and resets pend_dst.  Between the two calls the cache lacks that token's K/V at the destination.
+ *     records the destination slot in pend_dst; the next kvc_paged_attention_fused_step_deferred stores the
+ *     parked K/V there in its consumer warps' prologue, holds the TMA fetch of that block back until the store
+ *     is visible (so its own attention already reads the token; the sectors L2 fetches for the partial stores
+ *     are the ones the block's bulk copy needs next) and resets pend_dst.  Between the two calls the cache
+ *     lacks that token's K/V at the destination.
  *   kvc_flush_deferred: stores every parked token where it belongs (pend_dst if set, else pend_slot) and
  *     clears both markers: afterwards the cache is canonical.  pend arrays flattened [num_heads].
  * ------------------------------------------------------------------------- */

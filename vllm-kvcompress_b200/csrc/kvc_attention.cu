@@ -453,12 +453,12 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   constexpr int kPsBytes = NT * 8 * 16 * 2;
   const int H = p.num_kv_heads, Q = p.Q;
   // per-warp smem: ring | P^T | full/empty barriers | (fused, short contexts) raw logits [Q][smem_logit_tokens]
-  constexpr int kPendBytes = kMove ? 2 * kD * 2 : 0;  // the parked token of a deferred move (K | V)
-  const int kPerWarp = kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32 + kPendBytes + smem_logit_tokens * Q * 4;
+  const int kPerWarp = kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32 + smem_logit_tokens * Q * 4;
   const int num_items = p.num_kv_heads * p.num_seqs;
   auto ring_of = [&](int w) { return smem_raw + (size_t)w * kPerWarp; };
   auto full_of = [&](int w) { return smem_u32(ring_of(w) + kNUnit * kUnitBytes + kPsBytes); };
   auto empty_of = [&](int w) { return full_of(w) + kNUnit * 8; };
+  auto patched_of = [&](int w) { return full_of(w) + 2 * kNUnit * 8; };  // deferred move stored (kMove)
 
   if (wid < kConsumers && lane == 0) {
 #pragma unroll
@@ -466,6 +466,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
       mbar_init(full_of(wid) + 8 * i, 1);
       mbar_init(empty_of(wid) + 8 * i, 1);
     }
+    if (kMove) mbar_init(patched_of(wid), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -480,6 +481,11 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     const int* __restrict__ bt = p.block_tables + (int64_t)item * p.max_num_blocks_per_seq;
     const int bt_spec0 = bt[0], bt_spec1 = (p.max_num_blocks_per_seq > 1) ? bt[1] : 0;  // speculative, with ctx
     const int ctx = p.context_lens[item];  // item == s * H + h
+    // deferred move: the consumer stores the parked token to the cache in its prologue; units of the
+    // destination block are not fetched before that store is visible (patched barrier)
+    const int64_t pdp = kMove ? p.pend_dst[item] : -1;
+    const int pd_phys = pdp >= 0 ? (int)(pdp >> 4) : -1;
+    bool patched = pd_phys < 0;
     const int nblk = (ctx + kB - 1) / kB;
     if (nblk == 0) return;
     const uint16_t* __restrict__ kc = reinterpret_cast<const uint16_t*>(p.k_cache);
@@ -517,6 +523,13 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
                        : "=r"(ok) : "r"(empty + 8 * slot), "r"((uint32_t)((round - 1) & 1)) : "memory");
           ready = ok != 0;
         }
+        if (kMove && ready && !patched && phys == pd_phys) {
+          uint32_t ok;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(patched_of(w)), "r"(0u) : "memory");
+          patched = ok != 0;
+          ready = patched;
+        }
         if (ready) {
           if (skip_last && blk == nblk - 1) {
             mbar_arrive(full + 8 * slot);
@@ -541,8 +554,6 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   const int ctx = p.context_lens[item];
   // destination of a deferred move (see below); loaded with the context length so the two latencies overlap
   const int64_t pd = kMove ? p.pend_dst[item] : -1;
-  const int bt_mine = (kMove && lane < p.max_num_blocks_per_seq)
-                          ? p.block_tables[(int64_t)item * p.max_num_blocks_per_seq + lane] : -1;
   const int nblk = (ctx + kB - 1) / kB;
   uint16_t* outp = reinterpret_cast<uint16_t*>(p.out) + ((int64_t)s * p.num_heads + h * Q) * kD;
   if (ctx <= 0) {
@@ -551,6 +562,32 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     return;
   }
   unsigned char* ring = ring_of(wid);
+  // Deferred move: the token this head parked last step was granted an evicted slot by the compression that ran
+  // since (execute_cache_moves_deferred left only its destination in pend_dst).  It is stored to the cache
+  // here, while the warp would otherwise just wait for its first units; the producer holds the destination
+  // block's units back until the store is visible, so this step's attention already reads the moved token and
+  // the sweep below is exactly the plain fused step.  The 144 partial-sector stores make L2 fetch the block's
+  // sectors -- the very sectors the bulk copy of that block needs next, so DRAM sees them once -- and only the
+  // write-back of the block is extra traffic.
+  if (kMove) {
+    if (pd >= 0) {
+      const uint16_t* __restrict__ pk = p.pend_kv + (int64_t)item * (2 * kD);
+      uint4 kx = make_uint4(0, 0, 0, 0);
+      if (lane < 16) kx = *reinterpret_cast<const uint4*>(pk + lane * 8);
+      uint16_t vx[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) vx[r] = pk[kD + lane + 32 * r];
+      const int o = (int)(pd & (kB - 1));
+      uint16_t* kd = reinterpret_cast<uint16_t*>(const_cast<void*>(p.k_cache)) + (pd >> 4) * p.kv_block_stride;
+      uint16_t* vd = reinterpret_cast<uint16_t*>(const_cast<void*>(p.v_cache)) + (pd >> 4) * p.kv_block_stride;
+      if (lane < 16) *reinterpret_cast<uint4*>(kd + lane * (kB * 8) + o * 8) = kx;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) vd[(lane + 32 * r) * kB + o] = vx[r];
+      asm volatile("fence.proxy.async;" ::: "memory");  // generic stores before the async-proxy read of the block
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(patched_of(wid));
+  }
   uint16_t* psw = reinterpret_cast<uint16_t*>(ring + kNUnit * kUnitBytes);
   const uint32_t full = full_of(wid), empty = empty_of(wid);
   const int* __restrict__ bt = p.block_tables + (int64_t)item * p.max_num_blocks_per_seq;
@@ -567,7 +604,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   const int lg_stride = smem_logits ? smem_logit_tokens : scratch_tokens;
   unsigned long long passbits = 0ull;
   if (kFusedMetrics) {
-    float* base = smem_logits ? reinterpret_cast<float*>(ring + kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32 + kPendBytes)
+    float* base = smem_logits ? reinterpret_cast<float*>(ring + kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32)
                               : scratch + (int64_t)item * Q * scratch_tokens;
     lg0 = base + (2 * c) * lg_stride;  // column q = 2c (nt = 0)
     lg1 = lg0 + lg_stride;
@@ -615,30 +652,6 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
       slope[nt][i] = (ALIBI && qc < Q) ? p.alibi_slopes[h * Q + qc] : 0.f;
     }
   }
-  // deferred move: the token this head parked last step was granted an evicted slot by the compression that
-  // ran since (execute_cache_moves_deferred left only its destination).  It is patched into the staged copy
-  // of that block -- so this step's attention already sees it -- and the block's touched sectors go back to
-  // the cache as WHOLE 32 B sectors (a lone 2-byte store per V row would make L2 fetch every sector first).
-  // The parked K/V (512 B) is staged in this warp's shared memory now and read when its block comes up.
-  int pd_blk = -1, pd_o = 0, pd_phys = 0;
-  const uint16_t* pend_sm = reinterpret_cast<const uint16_t*>(ring + kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32);
-  if (kMove) {
-    if (pd >= 0) {
-      pd_phys = (int)(pd >> 4);
-      pd_o = (int)(pd & (kB - 1));
-      int hit = (lane < nblk && bt_mine == pd_phys) ? lane + 1 : 0;
-      for (int b = lane + kWarp; b < nblk; b += kWarp)
-        if (bt[b] == pd_phys) hit = b + 1;
-#pragma unroll
-      for (int d = 16; d >= 1; d >>= 1) hit = max(hit, __shfl_xor_sync(0xffffffffu, hit, d));
-      pd_blk = hit - 1;
-      // asynchronous copy (LDGSTS): the wait sits where the parked token is first used
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(pend_sm + lane * 8)),
-                   "l"(p.pend_kv + (int64_t)item * (2 * kD) + lane * 8) : "memory");
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-  }
-
   float m_run[NT][2], l_part[NT][2];  // running max per column; per-lane PARTIAL sums (reduced at the end)
   float oacc[NT][8][4];
 #pragma unroll
@@ -677,21 +690,6 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
           *reinterpret_cast<uint4*>(const_cast<unsigned char*>(kU) + (lane & 7) * (kB * 16) + new_o * 16) = newk;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic write, slot later refilled by TMA
         __syncwarp();
-      }
-      if (kMove && kblk == pd_blk) {  // deferred move: chunks 8 hf .. 8 hf + 7 of the parked K
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncwarp();
-        unsigned char* kW = const_cast<unsigned char*>(kU);
-        if (lane < 8) *reinterpret_cast<uint4*>(kW + lane * (kB * 16) + pd_o * 16) =
-            *reinterpret_cast<const uint4*>(pend_sm + (8 * hf + lane) * 8);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane < 16) {  // the 32 B sector (two tokens) of every chunk row goes back whole
-          const int rowi = lane >> 1, off = rowi * (kB * 16) + (pd_o >> 1) * 32 + (lane & 1) * 16;
-          unsigned char* kg = reinterpret_cast<unsigned char*>(const_cast<void*>(p.k_cache)) +
-                              ((int64_t)pd_phys * p.kv_block_stride) * 2 + hf * kUnitBytes + off;
-          *reinterpret_cast<uint4*>(kg) = *reinterpret_cast<const uint4*>(kW + off);
-        }
       }
       // four k-steps per half; one conflict-free ldmatrix.x4 per step: (chunk 2j, tok 0-7), (chunk 2j, tok 8-15),
       // (chunk 2j+1, tok 0-7), (chunk 2j+1, tok 8-15) = a0..a3 of the m16n8k16 A fragment
@@ -807,18 +805,6 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
       }
-      if (kMove && b == pd_blk) {  // deferred move: rows 64 hf .. 64 hf + 63 of the parked V
-        uint16_t* vw = reinterpret_cast<uint16_t*>(const_cast<unsigned char*>(vU));
-        vw[lane * kB + pd_o] = pend_sm[kD + 64 * hf + lane];
-        vw[(lane + 32) * kB + pd_o] = pend_sm[kD + 64 * hf + 32 + lane];
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        unsigned char* vg = reinterpret_cast<unsigned char*>(const_cast<void*>(p.v_cache)) +
-                            ((int64_t)pd_phys * p.kv_block_stride) * 2 + hf * kUnitBytes;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(vg + (lane + 32 * i) * 16) = *reinterpret_cast<const uint4*>(vU + (lane + 32 * i) * 16);
-      }
       const unsigned char* vS = vU + voff;
       uint2 va[4], vb[4];
 #pragma unroll
@@ -881,7 +867,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
         }
       }
     }
-  if (kMove && pd_blk >= 0 && lane == 0) p.pend_dst[item] = -1;  // applied
+  if (kMove && pd >= 0 && lane == 0) p.pend_dst[item] = -1;  // applied (the producer read it long ago)
   if (kWrite && new_slot >= 0) {
     // reference csrc/kvcompress_cache_kernels.cu:55-88: K chunks, V elements, metric := head bias
     if (p.pend_kv != nullptr && new_o == 0) {
@@ -1122,7 +1108,7 @@ static int launch_stream(const AttnParams& p, int num_seqs, float* scratch, int 
   // fused modes: keep the raw logits in shared memory when [Q][padded ctx] fits next to the ring
   // (<= 32 blocks so the recording bits fit one 64-bit register, and <= 3.5 KB per warp)
   int smem_logit_tokens = 0;
-  constexpr size_t kPend = (MODE == kModeFusedWriteMove) ? 2 * kD * 2 : 0;  // parked-token staging per warp
+  constexpr size_t kPend = 0;
   if ((MODE == kModeFused || MODE == kModeFusedWrite || MODE == kModeFusedWriteMove) && scratch_tokens <= 32 * kB &&
       (size_t)scratch_tokens * p.Q * 4 + kPend <= 3584)
     smem_logit_tokens = scratch_tokens;
