@@ -407,7 +407,8 @@ def main():
                      "frac": attn_b / (attn_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
                      "bytes_per_launch": attn_b, "ms_per_launch": attn_ms,
                      "traffic": ncu_traffic("paged_attention_stream_kernel")
-                     if (args.model == "llama3-8b" and args.batch == 256) else None},
+                     if (args.model == "llama3-8b" and args.batch == 256 and not args.no_deferred_append
+                         and not args.no_deferred_move) else None},
     }
     if not args.no_compaction:
         try:
