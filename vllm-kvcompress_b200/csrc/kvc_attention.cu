@@ -27,6 +27,8 @@
 // same buffers as the reference.  fused = v1 + sum_q p^2 accumulated into kv_metrics.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "kvc_common.cuh"
 
 namespace kvc {
@@ -680,8 +682,10 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   };
 
   // S^T(kblk) = K Q^T: consume the two K halves of block kblk, issue two independent MMA chains
-  auto consume_k = [&](int kblk, float (&sacc)[2][NT][4]) {
-    const bool klast = (kblk == nblk - 1);
+  // KL (compile time): kblk is the item's last block (the only one the step's new token can be patched into)
+  auto consume_k = [&](auto KL, int kblk, float (&sacc)[2][NT][4]) {
+    constexpr bool klast = decltype(KL)::value;
+    (void)kblk;
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
       const unsigned char* kU = next_unit();
@@ -712,10 +716,12 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   };
 
   float sacc[2][NT][4];  // logits of the block whose softmax is next
-  consume_k(0, sacc);
-  for (int b = 0; b < nblk; ++b) {
+  // The sweep body exists in three compile-time flavours so that the steady-state loop carries none of the
+  // last-block work (new-token patches, masking of slots beyond the context, NaN scrubbing): LAST = this is the
+  // item's last block, KL = the block whose K is consumed one ahead (b + 1) is the last one.
+  auto sweep_block = [&](auto LAST_T, auto KL_T, int b) {
+    constexpr bool last = decltype(LAST_T)::value;
     const int tok0 = b * kB + g, tok1 = tok0 + 8;
-    const bool last = (b == nblk - 1);
     bool rec0 = false, rec1 = false;
     int64_t slot0 = 0, slot1 = 0;
     if (MODE == kModeV1 && p.record) {  // independent of the staged data: issued before the waits
@@ -733,7 +739,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     }
     // software pipeline: the next block's QK^T chains are in flight while this block's softmax runs
     float snext[2][NT][4];
-    if (!last) consume_k(b + 1, snext);
+    if (!last) consume_k(KL_T, b + 1, snext);
     // ---- logits + online softmax ----
     bool rescale = false;
     float alpha[NT][2];
@@ -845,7 +851,17 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
 #pragma unroll
           for (int i = 0; i < 4; ++i) sacc[hf][nt][i] = snext[hf][nt][i];
     }
+  };
+  using T_ = std::true_type;
+  using F_ = std::false_type;
+  if (nblk == 1) {
+    consume_k(T_{}, 0, sacc);
+  } else {
+    consume_k(F_{}, 0, sacc);
+    for (int b = 0; b < nblk - 2; ++b) sweep_block(F_{}, F_{}, b);
+    sweep_block(F_{}, T_{}, nblk - 2);
   }
+  sweep_block(T_{}, F_{}, nblk - 1);
 
   // ---- output: O / (L + 1e-6); lane (g,c) holds O[d = 16 dt + g (+8)][q = 2c, 2c+1] ----
   float inv[NT][2];
