@@ -43,14 +43,19 @@ __device__ __forceinline__ uint32_t pack4(uint32_t w) {  // 4 bool bytes (0/1) -
   return (w & 1u) | ((w >> 7) & 2u) | ((w >> 14) & 4u) | ((w >> 21) & 8u);
 }
 
+// pieces (512 B of mask = 2 chunks) per warp: 2 keeps the pass short -- it is a chain of dependent shuffles per
+// piece, and 96 warps of 16 pieces each took 12 us for a 786 KB mask
+constexpr int kCountPieces = 2;
+constexpr int kCountChunksPerWarp = 2 * kCountPieces;
+
 __device__ void chunk_count_warp(const AllocIndex& ix, int warp_global, int lane) {
-  // one warp = 32 chunks (8 KB of mask); piece p: lane reads 16 B at offset (p*32 + lane)*16
-  const int64_t base = (int64_t)warp_global * 32 * kChunk;
+  // piece p: lane reads 16 B at offset (p*32 + lane)*16
+  const int64_t base = (int64_t)warp_global * kCountChunksPerWarp * kChunk;
   const int64_t end = (int64_t)ix.n_chunks * kChunk;  // bitmap covers whole chunks; bits >= num_blocks are 0
   if (base >= end) return;
   uint16_t* bm16 = reinterpret_cast<uint16_t*>(ix.bitmap);
-#pragma unroll 4
-  for (int p = 0; p < 16; ++p) {
+#pragma unroll
+  for (int p = 0; p < kCountPieces; ++p) {
     const int64_t off = base + ((int64_t)p * 32 + lane) * 16;
     uint32_t bits = 0;
     if (off + 16 <= ix.num_blocks) {
@@ -253,7 +258,13 @@ __global__ void __launch_bounds__(kNeedCta) alloc_append_kernel(AppendParams p) 
     if (p.layer_index_by_block) p.layer_index_by_block[blk] = l;
     if (p.head_index_by_block) p.head_index_by_block[blk] = h;
     if (p.logical_block_num_by_block) p.logical_block_num_by_block[blk] = ctx / p.B;
-    for (int j = 0; j < p.B; ++j) p.kv_position[(int64_t)blk * p.B + j] = pos + j;
+    if (p.B == 16) {  // one 64 B row: four 16 B stores
+      int4* row = reinterpret_cast<int4*>(p.kv_position + (int64_t)blk * 16);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) row[j] = make_int4(pos + 4 * j, pos + 4 * j + 1, pos + 4 * j + 2, pos + 4 * j + 3);
+    } else {
+      for (int j = 0; j < p.B; ++j) p.kv_position[(int64_t)blk * p.B + j] = pos + j;
+    }
   } else {
     blk = bt[ctx / p.B];
     p.kv_position[(int64_t)blk * p.B + ctx % p.B] = pos;
@@ -457,7 +468,7 @@ extern "C" int kvc_alloc_append_slots(
   p.num_batch = num_batch; p.max_seqs = max_seqs; p.L = num_layers; p.H = num_kv_heads;
   p.MB = max_num_blocks_per_seq; p.B = block_size;
   cudaStream_t st = as_stream(stream);
-  const int count_ctas = (int)cdiv64(num_blocks, 8 * 32 * kChunk);
+  const int count_ctas = (int)cdiv64(num_blocks, 8 * kCountChunksPerWarp * kChunk);
   alloc_count_kernel<<<count_ctas + p.n_need_ctas, 256, 0, st>>>(p, count_ctas);
   KVC_CHECK_LAUNCH("alloc_count_kernel");
   alloc_scan_kernel<<<p.ix.n_super, kSuper, 0, st>>>(p.ix);
@@ -497,7 +508,7 @@ extern "C" int kvc_alloc_add_sequences(
   p.n = num_new; p.max_seqs = max_seqs; p.L = num_layers; p.H = num_kv_heads;
   p.MB = max_num_blocks_per_seq; p.B = block_size;
   cudaStream_t st = as_stream(stream);
-  alloc_count_only_kernel<<<(unsigned)cdiv64(num_blocks, 8 * 32 * kChunk), 256, 0, st>>>(p.ix);
+  alloc_count_only_kernel<<<(unsigned)cdiv64(num_blocks, 8 * kCountChunksPerWarp * kChunk), 256, 0, st>>>(p.ix);
   KVC_CHECK_LAUNCH("alloc_count_only_kernel");
   alloc_scan_kernel<<<p.ix.n_super, kSuper, 0, st>>>(p.ix);
   KVC_CHECK_LAUNCH("alloc_scan_kernel");
