@@ -153,3 +153,47 @@ def test_python_shim_mirrors_reference_names(built):
         t = torch.zeros(1, dtype=torch.int32)
         ops.schedule_cache_evictions(t, t, t, t, t, t, t, t, t, t, t, t, t, t, t, 16, 1, 0, True,
                                      evict_evenly_per_layer=True)
+
+
+ADDITIVE_OPS = {
+    # op -> (namespace, arguments that the Python shim passes positionally, in order)
+    "kvcompress_paged_attention_fused_step_deferred": ("_C", [
+        "out", "kv_metrics", "query", "key", "value", "key_cache", "value_cache", "slot_mapping",
+        "kv_metric_head_bias", "pend_kv", "pend_slot", "pend_dst", "num_kv_heads", "scale", "block_tables",
+        "context_lens", "kv_position", "last_position", "kv_metric_buffer_len", "block_size", "max_context_len",
+        "alibi_slopes", "kv_cache_dtype"]),
+    "execute_cache_moves_deferred": ("_C_kvc_ops", [
+        "k_cache", "v_cache", "kv_metrics", "kv_position", "cache_moves_idx", "cache_moves_count",
+        "evicted_kv_offsets", "pend_kv", "pend_slot", "pend_dst"]),
+    "flush_deferred": ("_C_kvc_ops", ["k_cache", "v_cache", "pend_kv", "pend_slot", "pend_dst"]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(ADDITIVE_OPS))
+def test_additive_deferred_ops_are_registered(built, name):
+    """The deferred append / move ops are additive (new names, the reference schemas stay untouched) and the
+    shim's positional call order matches the dispatcher's argument list."""
+    built.load_torch_ops()
+    ns, args = ADDITIVE_OPS[name]
+    schema = getattr(getattr(torch.ops, ns), name).default._schema
+    assert [a.name for a in schema.arguments] == args
+    assert len(schema.returns) == 0
+    assert (ns, name) not in REFERENCE_SCHEMAS
+
+
+def test_deferred_ops_fail_loudly_on_cpu(built):
+    built.load_torch_ops()
+    k = torch.zeros((1, 16, 16, 8), dtype=torch.float16)
+    v = torch.zeros((1, 128, 16), dtype=torch.float16)
+    pend = torch.zeros((1, 256), dtype=torch.float16)
+    slot = torch.full((1,), -1, dtype=torch.int64)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops._C_kvc_ops.flush_deferred(k, v, pend, slot, None)
+
+
+def test_select_mode_switch_round_trips(built):
+    lib = built.load_lib()
+    assert lib.kvc_get_select_mode() == 0
+    assert lib.kvc_set_select_mode(2) == 0 and lib.kvc_get_select_mode() == 2
+    assert lib.kvc_set_select_mode(7) != 0 and lib.kvc_get_select_mode() == 2   # rejected, unchanged
+    assert lib.kvc_set_select_mode(0) == 0
