@@ -830,23 +830,26 @@ def test_execute_moves_many_heads_small_counts_vs_oracle(capi, O, deferred, full
         cnt = rs.choice([0, 1, 1, 1, 2, 3, 5], size=heads).astype(np.int32)
         offs = (np.arange(heads) * blocks_per_head * B).astype(np.int32)
         moves = np.zeros((heads * blocks_per_head * B, 2), np.int32)
-        pend_slot = np.full(heads, -1, np.int64)
-        consumed = []
-        for g in range(heads):
-            # destinations in the first two blocks, sources in the last block (descending, like K4)
-            ctx_tail = rs.randint(1, B + 1)          # tokens in the last block
-            n = min(int(cnt[g]), ctx_tail)
-            cnt[g] = n
-            dst = np.sort(rs.choice(2 * B, size=n, replace=False))
-            top = ctx_tail - 1 if rs.rand() < 0.7 else rs.randint(max(n - 1, 0), ctx_tail)  # else: newest token may stay
-            src = 2 * B + (top - np.arange(n))
-            phys = lambda i: perm[g, i // B] * B + i % B
-            for k in range(n):
-                moves[offs[g] + k] = (phys(dst[k]), phys(src[k]))
-            if g % 2 == 0:
-                pend_slot[g] = phys(2 * B + ctx_tail - 1)     # the head's newest token
-                if n and top == ctx_tail - 1:
-                    consumed.append(pend_slot[g])
+        # per head (vectorised): destinations in the first two blocks, sources in the last block (descending,
+        # like K4), the newest token first in 70 % of the heads
+        ctx_tail = rs.randint(1, B + 1, size=heads)                 # tokens in the last block
+        cnt = np.minimum(cnt, ctx_tail).astype(np.int32)
+        order = np.argsort(rs.rand(heads, 2 * B), axis=1)[:, :5]    # 5 distinct destinations per head
+        order = np.where(np.arange(5)[None] < cnt[:, None], order, 10 ** 6)
+        dst = np.sort(order, axis=1)
+        lo = np.maximum(cnt - 1, 0)
+        top = np.where(rs.rand(heads) < 0.7, ctx_tail - 1, lo + (rs.rand(heads) * (ctx_tail - lo)).astype(np.int64))
+        gidx = np.arange(heads)
+        phys = lambda i: perm[gidx, i // B] * B + i % B
+        for k in range(5):
+            sel = cnt > k
+            d = np.where(sel, dst[:, k], 0)
+            sidx = np.where(sel, 2 * B + top - k, 0)
+            pd, ps_ = phys(d), phys(sidx)
+            moves[offs[sel] + k, 0] = pd[sel]
+            moves[offs[sel] + k, 1] = ps_[sel]
+        pend_slot = np.where(gidx % 2 == 0, phys(2 * B + ctx_tail - 1), -1).astype(np.int64)   # newest token
+        consumed = pend_slot[(gidx % 2 == 0) & (cnt > 0) & (top == ctx_tail - 1)]
         # oracle on the canonical cache
         wk, wv, wm, wp = kc.copy(), vc.copy(), km.copy(), kp.copy()
         O.execute_cache_moves(wk, wv, wm, wp, moves, cnt.reshape(S, L, H), offs.reshape(S, L, H))
