@@ -80,7 +80,7 @@ def test_device_allocator_is_invisible_to_results(graph):
 
 
 @pytest.mark.parametrize("shape", [dict(num_seqs=2, num_layers=2), dict(num_seqs=5, num_layers=3),
-                                   dict(num_seqs=40, num_layers=32)])
+                                   dict(num_seqs=64, num_layers=8)])
 @pytest.mark.parametrize("graph", [False, True])
 @pytest.mark.parametrize("deferred_move", [False, True])
 def test_deferred_append_is_invisible_to_results(shape, graph, deferred_move):
