@@ -80,7 +80,7 @@ def test_device_allocator_is_invisible_to_results(graph):
 
 
 @pytest.mark.parametrize("shape", [dict(num_seqs=2, num_layers=2), dict(num_seqs=5, num_layers=3),
-                                   dict(num_seqs=64, num_layers=8)])
+                                   dict(num_seqs=96, num_layers=6)])
 @pytest.mark.parametrize("graph", [False, True])
 @pytest.mark.parametrize("deferred_move", [False, True])
 def test_deferred_append_is_invisible_to_results(shape, graph, deferred_move):
@@ -88,7 +88,8 @@ def test_deferred_append_is_invisible_to_results(shape, graph, deferred_move):
     next execute_cache_moves_deferred) against the plain fused step on the same allocator: identical
     attention outputs, tables and context lengths every step, and after flush_pending() bit-identical
     K / V / metrics / positions in every live slot.  Shapes cover gridDim.y > 1 (few heads: several warps
-    share a head's move list) and the one-warp-per-head launch of the benchmark."""
+    share a head's move list) and the decode-time launches of the benchmark (>= 4096 heads: 32 heads per warp in
+    K4 / K5; >= 96 sequences: the one-CTA-per-sequence selection)."""
     from vllm_kvcompress_b200.engine import DecodeHotPath, HotPathConfig
     dev = torch.device("cuda", 0)
     kw = dict(max_cache_tokens=64, blocks_per_head=8, protected_window=16, seed=11, **shape)
