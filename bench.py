@@ -17,8 +17,13 @@ value   = batch tokens / step time, inputs resident in HBM (CUDA events, max ove
 e2e     = same step through the public API (DecodeHotPath.step_host) with the step's Q/K/V
           coming from pinned host memory and the attention output copied back, copies inside
           the timed region.
-roofline= the dominant kernel (paged attention): algorithmic bytes / its mean launch time,
-          CUDA events on the launching stream inside the timed region.
+roofline= the dominant kernel (the fused attention step: cache write + deferred move + attention + metric
+          aggregation): algorithmic bytes / its mean launch time, measured live with CUDA events on the
+          launching stream around graph replays of one step's 32 launches (their deferred work armed,
+          engine.profile_attention); traffic = DRAM bytes per launch from the committed ncu capture.
+By default new tokens that open a fresh block are parked and stored once at their final slot (deferred
+append / deferred move); --no-deferred-append / --no-deferred-move run the reference's op
+sequence (store, read back, move) instead.
 cpu_baseline = the oracle port of the same step on the host cores, on a bounded sample.
 N>1: request-sharded replicas (one independent cache per GPU, weak scaling); NCCL only for
 the start-up broadcast and the timing reduction.
