@@ -171,6 +171,7 @@ def run_reference(args, rank, world):
     from oracle.cpu_decode_step import CpuDecodeHotPath
     from vllm_kvcompress_b200.engine import HotPathConfig
     O.build()
+    O.use_all_cores()
     ns = args.cpu_sample_seqs
     cfg = HotPathConfig(num_seqs=ns, num_layers=args.layers)
     eng = CpuDecodeHotPath(cfg)
@@ -430,6 +431,7 @@ def main():
         from oracle import kvc_oracle as O
         from oracle.cpu_decode_step import CpuDecodeHotPath
         O.build()
+        O.use_all_cores()
         ns = args.cpu_sample_seqs
         ccfg = HotPathConfig(num_seqs=ns, num_layers=L)
         ceng = CpuDecodeHotPath(ccfg)

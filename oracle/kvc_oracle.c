@@ -47,6 +47,15 @@ KVC_EXPORT int kvc_oracle_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the benchmark's CPU arm sets the thread count itself */
+KVC_EXPORT void kvc_oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------
  * K2  truncate_cache_evictions_kernel
  * reference: csrc/kvcompress_eviction_kernels.cu:158-188

@@ -50,6 +50,14 @@ def num_threads() -> int:
     return int(lib().kvc_oracle_num_threads())
 
 
+def use_all_cores() -> int:
+    """Run the OpenMP loops on every core this process may use (torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which would make the CPU baseline single-threaded under --gpus N > 1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().kvc_oracle_set_num_threads(int(n))
+    return num_threads()
+
+
 def _p(a: Optional[np.ndarray]):
     if a is None:
         return ctypes.c_void_p(0)
