@@ -426,7 +426,7 @@ def main():
             line["prefill_kv_metrics"] = prefill_metrics_bench(device)
         except Exception as ex:  # pragma: no cover
             line["prefill_kv_metrics"] = {"error": repr(ex)}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # reported at N=1 only (rank 0's host cores)
         import numpy as np
         from oracle import kvc_oracle as O
         from oracle.cpu_decode_step import CpuDecodeHotPath
