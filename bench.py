@@ -54,8 +54,10 @@ def parse():
                     help="execute_cache_moves stores the parked tokens itself instead of the next attention step")
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
     ap.add_argument("--layers", type=int, default=32)
-    ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama3-70b"],
-                    help="shape preset: 8b = L32 H8 Q4 CR64 (max_cache_tokens 128); 70b = L80 H8 Q8 CR16 (368)")
+    ap.add_argument("--model", default="llama3-8b",
+                    choices=["llama3-8b", "llama3-8b-cr16", "llama3-8b-cr8", "llama3-8b-cr4", "llama3-70b"],
+                    help="shape preset: 8b = L32 H8 Q4 CR64 (max_cache_tokens 128); -crN = the CR sweep; "
+                         "70b = L80 H8 Q8 CR16 (368)")
     ap.add_argument("--selection", default="fused", choices=["fused", "chain"])
     ap.add_argument("--allocator", default="device", choices=["device", "static"],
                     help="device = blocks freed/allocated every step by the device-side allocator")
@@ -65,6 +67,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-compaction", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=16)
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the other BASELINE.json configurations (CR 16 / 8 / 4, Llama-3-70B) and the launch-mode A/B")
+    ap.add_argument("--extra-steps", type=int, default=12, help="timed steps per extra configuration")
+    ap.add_argument("--no-reference-cuda", action="store_true",
+                    help="skip the leg that times the reference's own CUDA kernels (oracle/_ref) on the same step")
     return ap.parse_args()
 
 
@@ -162,49 +169,73 @@ class ClockSampler:
                 "reasons": [nm for nm, bit in self.REASONS if self.bits & bit], "samples": len(sm)}
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the oracle port of the step on the host cores (rank 0 only)."""
-    if rank != 0:
-        return
+def cpu_step_rate(args, seconds=None, steps=None, warmup=1):
+    """The oracle port of the step on the host cores (OpenMP over heads / sequences): tokens/s on a bounded
+    sample of the batch.  Imports oracle/ only (no product library is mapped by the CPU arm)."""
     import numpy as np
     from oracle import kvc_oracle as O
-    from oracle.cpu_decode_step import CpuDecodeHotPath
-    from vllm_kvcompress_b200.engine import HotPathConfig
+    from oracle.cpu_decode_step import CpuDecodeHotPath, CpuStepConfig
     O.build()
     O.use_all_cores()
     ns = args.cpu_sample_seqs
-    cfg = HotPathConfig(num_seqs=ns, num_layers=args.layers)
+    cfg = CpuStepConfig(num_seqs=ns, num_layers=args.layers)
     eng = CpuDecodeHotPath(cfg)
     Hq, H, D = cfg.num_kv_heads * cfg.queries_per_kv, cfg.num_kv_heads, cfg.head_size
     qkv = (np.random.RandomState(0).rand(cfg.num_layers, ns, (Hq + 2 * H) * D).astype(np.float16) - 0.5).view(np.uint16)
     out = np.zeros((cfg.num_layers, ns, Hq * D), np.float32)
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         eng.step(qkv, out)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    reps = 0
+    while (steps is not None and reps < steps) or (steps is None and (reps < 3 or (time.perf_counter() - t0 < seconds
+                                                                                   and reps < 200))):
         eng.step(qkv, out)
-    dt = (time.perf_counter() - t0) / args.steps
-    val = ns / dt
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    kv_mb = ns * cfg.num_layers * H * cfg.max_cache_tokens * 2 * D * 2 / 1e6
+    return {"value": ns / dt, "unit": "tokens/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"{ns} of {args.batch} sequences per step (K+V working set {kv_mb:.0f} MB), all {args.layers} "
+                      f"layers, full cycle (selection, moves, append, cache write, attention, metric aggregation), "
+                      f"{reps} steps in {dt * reps:.1f} s"}, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the oracle port of the step on the host cores (rank 0 only).  The reference has no CPU
+    build of these ops (csrc/cpu registers none of them), so the port is the CPU arm."""
+    if rank != 0:
+        return
+    base, dt = cpu_step_rate(args, steps=args.steps, warmup=args.warmup)
+    val = base["value"]
     line = {
         "impl": "reference", "metric": "decode tokens/sec at CR=64x (Llama-3-8B shape, KV-Compress hot path)",
         "value": val, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
         "config": workload_config(args, args.batch * args.gpus),
-        "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": O.num_threads(), "kind": "port",
-                         "sample": f"{ns} of {args.batch} sequences per step, all {args.layers} layers, full cycle"},
+        "cpu_baseline": base,
         "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def workload_config(args, batch):
-    wl = ("Llama-3-8B shape (L=32, H_kv=8, Q=4, D=128, block 16), input 6000 / output 500, "
-          "CR 64x => max_cache_tokens=128, protected_window=32, continual compression every step")
-    if getattr(args, "model", "llama3-8b") == "llama3-70b":
-        wl = ("Llama-3-70B shape (L=80, H_kv=8, Q=8, D=128, block 16), input 6000 / output 500, "
-              "CR 16x => max_cache_tokens=368, protected_window=32, continual compression every step")
+# shape presets: BASELINE.json configs[1] (the headline), configs[3] (70B) and configs[4] (CR sweep); max_cache_tokens per
+# compression rate follows benchmarks/benchmark_throughput.py:391-393 at input 6000: max(128, ((6000 // CR - 1) // 16) * 16)
+PRESETS = {
+    "llama3-8b": dict(name="Llama-3-8B", layers=32, q=4, cr=64, max_cache_tokens=128, blocks_per_head=12),
+    "llama3-8b-cr16": dict(name="Llama-3-8B", layers=32, q=4, cr=16, max_cache_tokens=368, blocks_per_head=28),
+    "llama3-8b-cr8": dict(name="Llama-3-8B", layers=32, q=4, cr=8, max_cache_tokens=736, blocks_per_head=52),
+    "llama3-8b-cr4": dict(name="Llama-3-8B", layers=32, q=4, cr=4, max_cache_tokens=1488, blocks_per_head=100),
+    "llama3-70b": dict(name="Llama-3-70B", layers=80, q=8, cr=16, max_cache_tokens=368, blocks_per_head=28),
+}
+
+
+def workload_config(args, batch, model=None):
+    p = PRESETS[model or getattr(args, "model", "llama3-8b")]
+    layers = p["layers"] if model or args.layers == 32 else args.layers
+    wl = ("%s shape (L=%d, H_kv=8, Q=%d, D=128, block 16), input 6000 / output 500, CR %dx => max_cache_tokens=%d, "
+          "protected_window=32, continual compression every step"
+          % (p["name"], layers, p["q"], p["cr"], p["max_cache_tokens"]))
     return {"workload": wl,
             "global_batch": batch, "seq_len": 6000, "parallelism": "request-sharded replicas",
             "l2": "inputs larger than L2 (per-step KV read ~4.6 GB vs 126 MB L2)",
@@ -302,6 +333,57 @@ def prefill_metrics_bench(device):
             "note": "3 launches: row stats, squared-probability column sums, max-pool + aggregate_prefill"}
 
 
+def build_engine(args, model, device, rank, pdl="model"):
+    from vllm_kvcompress_b200.engine import DecodeHotPath, HotPathConfig
+    p = PRESETS[model]
+    layers = p["layers"] if (model != "llama3-8b" or args.layers == 32) else args.layers
+    cfg = HotPathConfig(num_seqs=args.batch, num_layers=layers, queries_per_kv=p["q"],
+                        max_cache_tokens=p["max_cache_tokens"], blocks_per_head=p["blocks_per_head"],
+                        selection=args.selection, fused_metrics=not args.unfused_metrics, allocator=args.allocator,
+                        host_copy_layers=args.host_copy_layers, fused_cache_write=not args.separate_cache_write,
+                        seed=rank, deferred_append=not args.no_deferred_append,
+                        deferred_move=not args.no_deferred_move, attention_pdl=pdl)
+    return DecodeHotPath(cfg, device)
+
+
+def make_inputs(cfg, device, rank):
+    H, Q, D, L, S = cfg.num_kv_heads, cfg.queries_per_kv, cfg.head_size, cfg.num_layers, cfg.num_seqs
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    qkv = (torch.rand((L, S, (H * Q + 2 * H) * D), generator=g, device=device, dtype=torch.float32) - 0.5).to(cfg.dtype)
+    out = torch.empty((L, S, H * Q * D), device=device, dtype=cfg.dtype)
+    return qkv, out
+
+
+def time_device_steps(eng, qkv, out, steps, warmup, barrier, sampler=None):
+    """`steps` steps with device-resident inputs between two CUDA events (one CUDA graph per step)."""
+    graphed = eng.capture(qkv, out)
+    run_step = eng.replay if graphed else (lambda: eng.step(qkv, out))
+    for _ in range(warmup):
+        run_step()
+    barrier()
+    if sampler is not None:
+        sampler.start()
+    n0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run_step()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / steps, (eng.launches - n0) // steps
+
+
+def attention_roofline(eng, qkv, out, steps, peak, peak_src, traffic=None):
+    ms, nbytes = eng.profile_attention(qkv, out, steps=steps)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm",
+            "kernel": "paged_attention_stream_kernel (cache write + deferred moves + attention + metric aggregation), "
+                      "%d launches/step" % eng.cfg.num_layers,
+            "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": peak_src,
+            "bytes_per_launch": nbytes, "ms_per_launch": ms, "traffic": traffic,
+            "launch_mode": "kvc_set_attention_pdl %d (layer 0) / %d (layers >= 1)" % (eng.pdl_first, eng.pdl_rest)}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -317,136 +399,147 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
-    from vllm_kvcompress_b200.engine import DecodeHotPath, HotPathConfig
-
-    preset = {}
-    if args.model == "llama3-70b":  # BASELINE.json configs[3]
-        args.layers = 80
-        preset = dict(queries_per_kv=8, max_cache_tokens=368, blocks_per_head=28)
-    cfg = HotPathConfig(num_seqs=args.batch, num_layers=args.layers, selection=args.selection,
-                        fused_metrics=not args.unfused_metrics, allocator=args.allocator,
-                        host_copy_layers=args.host_copy_layers, **preset,
-                        fused_cache_write=not args.separate_cache_write, seed=rank,
-                        deferred_append=not args.no_deferred_append, deferred_move=not args.no_deferred_move)
     from vllm_kvcompress_b200 import sharding
-    # the only collective on this path: one start-up broadcast (stands in for the weight broadcast
-    # of the 8-replica layout); every replica then owns an independent cache for its own requests
-    hdr = sharding.broadcast_config([cfg.num_seqs, cfg.num_layers, cfg.max_cache_tokens], device)
-    assert hdr == [cfg.num_seqs, cfg.num_layers, cfg.max_cache_tokens]
-    my_requests = sharding.shard_requests(cfg.num_seqs * world, world, rank)  # ids of this replica's batch
-    assert len(my_requests) == cfg.num_seqs
-    eng = DecodeHotPath(cfg, device)
-    H, Q, D, L, S = cfg.num_kv_heads, cfg.queries_per_kv, cfg.head_size, cfg.num_layers, cfg.num_seqs
-    width_in, width_out = (H * Q + 2 * H) * D, H * Q * D
-    g = torch.Generator(device=device).manual_seed(1234 + rank)
-    qkv = (torch.rand((L, S, width_in), generator=g, device=device, dtype=torch.float32) - 0.5).to(cfg.dtype)
-    out = torch.empty((L, S, width_out), device=device, dtype=cfg.dtype)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident timing ----------------
-    graphed = eng.capture(qkv, out)   # whole step as one CUDA graph (no host round trip inside)
-    run_step = eng.replay if graphed else (lambda: eng.step(qkv, out))
-    for _ in range(args.warmup):
-        run_step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = eng.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        run_step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
-    launches = (eng.launches - launches0) // args.steps
+    peak, peak_src = peaks()
+    eng = build_engine(args, args.model, device, rank)
+    cfg = eng.cfg
+    # the only collective on this path: one start-up broadcast (stands in for the weight broadcast
+    # of the 8-replica layout); every replica then owns an independent cache for its own requests
+    hdr = sharding.broadcast_config([cfg.num_seqs, cfg.num_layers, cfg.max_cache_tokens], device)
+    assert hdr == [cfg.num_seqs, cfg.num_layers, cfg.max_cache_tokens]
+    my_requests = sharding.shard_requests(cfg.num_seqs * world, world, rank)  # ids of this replica's batch
+    assert len(my_requests) == cfg.num_seqs
+    L, S = cfg.num_layers, cfg.num_seqs
+    qkv, out = make_inputs(cfg, device, rank)
 
-    # attention kernel time: same steps, events around every attention launch (separate pass so the
-    # event records do not perturb the headline number)
-    attn_ms, attn_b = eng.profile_attention(qkv, out, steps=min(args.steps, 5))
+    # ---------------- device-resident timing (headline `value`) ----------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches = time_device_steps(eng, qkv, out, args.steps, args.warmup, barrier, sampler)
+    clocks = sampler.stop() if rank == 0 else None
+    eng.check_status()
+
+    # attention kernel time: the step's L launches alone as one CUDA graph between two events (separate pass
+    # so the event records do not perturb the headline number)
+    default_cfg = (args.model == "llama3-8b" and args.batch == 256 and not args.no_deferred_append
+                   and not args.no_deferred_move)
+    roof = attention_roofline(eng, qkv, out, min(args.steps, 5), peak, peak_src,
+                              ncu_traffic("paged_attention_stream_kernel") if default_cfg else None)
+    pdl_ab = None
+    if rank == 0 and not args.no_extras and "KVC_ATTN_PDL" not in os.environ:
+        # A/B of the launch modes on the same state (a model can only use "model"; "independent" is what round 1
+        # reported: every layer's q/k/v declared independent of the previous kernel)
+        pdl_ab = {"model": roof["ms_per_launch"]}
+        keep = eng.pdl_first, eng.pdl_rest
+        for name, (a, b) in (("independent", (1, 3)), ("safe", (1, 1)), ("off", (0, 0))):
+            eng.pdl_first, eng.pdl_rest = a, b
+            pdl_ab[name] = eng.profile_attention(qkv, out, steps=min(args.steps, 5))[0]
+        eng.pdl_first, eng.pdl_rest = keep
 
     # ---------------- end to end through the public API with host buffers ----------------
-    qkv_host = torch.empty((L, S, width_in), dtype=cfg.dtype, pin_memory=True)
-    qkv_host.copy_(qkv)
-    out_host = torch.empty((L, S, width_out), dtype=cfg.dtype, pin_memory=True)
-    host_graphed = eng.capture_host(qkv_host, out_host)
-    run_host = eng.replay_host if host_graphed else (lambda: eng.step_host(qkv_host, out_host))
-    for _ in range(3):
-        run_host()
+    # two sets of pinned host buffers alternate (the pipelined API returns before a step's output has landed)
+    qkv_host = [torch.empty(qkv.shape, dtype=cfg.dtype, pin_memory=True) for _ in range(2)]
+    out_host = [torch.empty(out.shape, dtype=cfg.dtype, pin_memory=True) for _ in range(2)]
+    for t in qkv_host:
+        t.copy_(qkv)
+    for i in range(max(4, min(args.warmup, 6))):       # includes the two eager + capture steps
+        eng.submit_host(qkv_host[i & 1], out_host[i & 1])
+    eng.wait_host()
     barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        run_host()
+    for i in range(args.steps):
+        eng.submit_host(qkv_host[i & 1], out_host[i & 1])
+    eng.wait_host()
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1) / args.steps
+    eng.check_status()
+    h2d_bytes = qkv_host[0].numel() * qkv_host[0].element_size()
+    d2h_bytes = out_host[0].numel() * out_host[0].element_size()
+    del qkv_host, out_host
 
     ms, ms_e2e = sharding.max_over_ranks([ms, ms_e2e], device)
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    peak, peak_src = peaks()
     total_tokens = S * world
     line = {
         "metric": "decode tokens/sec at CR=64x (Llama-3-8B shape, KV-Compress hot path)",
         "value": total_tokens / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": dict(workload_config(args, total_tokens),
-                       attention_launch="programmatic dependent launch, kvc_set_attention_pdl mode %d"
-                                        % eng.attention_pdl),
+        "config": workload_config(args, total_tokens),
         "e2e": {"value": total_tokens / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": qkv_host.numel() * qkv_host.element_size(),
-                "d2h_bytes_per_step": out_host.numel() * out_host.element_size()},
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "api": "DecodeHotPath.submit_host / wait_host: pipelined over two staging buffers (H2D of step "
+                       "t+1 and D2H of step t-1 under the compute of step t)"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "paged_attention_stream_kernel (cache write + deferred moves + attention + metric aggregation), %d launches/step" % L,
-                     "achieved": attn_b / (attn_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": attn_b / (attn_ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-                     "bytes_per_launch": attn_b, "ms_per_launch": attn_ms,
-                     "traffic": ncu_traffic("paged_attention_stream_kernel")
-                     if (args.model == "llama3-8b" and args.batch == 256 and not args.no_deferred_append
-                         and not args.no_deferred_move) else None},
+        "roofline": roof,
+        "attention_launch": "programmatic dependent launch, layer 0 mode %d, layers >= 1 mode %d "
+                            "(include/kvc_b200.h kvc_set_attention_pdl)" % (eng.pdl_first, eng.pdl_rest),
     }
+    if pdl_ab is not None:
+        line["attention_ms_per_launch_by_pdl"] = pdl_ab
+    del eng, qkv, out
+    torch.cuda.empty_cache()
+
+    # ---------------- the other BASELINE.json configurations (decode step, same measurement) ----------------
+    if not args.no_extras and args.model == "llama3-8b":
+        extras = {}
+        for model in ("llama3-8b-cr16", "llama3-8b-cr8", "llama3-8b-cr4", "llama3-70b"):
+            try:
+                e = build_engine(args, model, device, rank)
+                q2, o2 = make_inputs(e.cfg, device, rank)
+                xsteps = max(4, min(args.steps, args.extra_steps))
+                xms, xl = time_device_steps(e, q2, o2, xsteps, 3, barrier)
+                e.check_status()
+                xroof = attention_roofline(e, q2, o2, 3, peak, peak_src)
+                xms, = sharding.max_over_ranks([xms], device)
+                extras[model] = {"value": total_tokens / (xms * 1e-3), "unit": "tokens/s", "ms_per_step": xms,
+                                 "steps": xsteps, "warmup": 3, "gpu_launches": xl, "roofline": xroof,
+                                 "config": workload_config(args, total_tokens, model)["workload"],
+                                 "cache_gb": e.st.NB * 8192 / 1e9}
+                del e, q2, o2
+            except Exception as ex:  # pragma: no cover
+                extras[model] = {"error": repr(ex)}
+            torch.cuda.empty_cache()
+        line["configs"] = extras
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if not args.no_compaction:
         try:
             line["execute_cache_moves"] = compaction_roofline(device, peak)
         except Exception as ex:  # pragma: no cover
             line["execute_cache_moves"] = {"error": repr(ex)}
-    if not args.no_compaction:
         try:
             line["prefill_kv_metrics"] = prefill_metrics_bench(device)
         except Exception as ex:  # pragma: no cover
             line["prefill_kv_metrics"] = {"error": repr(ex)}
+    if not args.no_reference_cuda and world == 1 and args.model == "llama3-8b":
+        # the fork's own CUDA kernels (unmodified .cu files rebuilt for sm_100a, oracle/_ref) driving the same
+        # step in the fork's op order: the "reference fork's own decode tokens/s on the same box" (north_star).
+        # Outside the product's timed region; reported, like cpu_baseline.
+        try:
+            from oracle import ref_ops
+            if ref_ops.available():
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_reference_kernels as brk
+                r = brk.measure(args.batch, args.layers, steps=3, warmup=1, device=device)
+                r["ratio_value_over_reference_cuda"] = line["value"] / r["value"]
+                line["reference_cuda"] = r
+            else:
+                line["reference_cuda"] = {"unavailable": "oracle/_ref/_kvc_ref.so not built"}
+        except Exception as ex:  # pragma: no cover
+            line["reference_cuda"] = {"error": repr(ex)}
     if not args.no_cpu_baseline and world == 1:   # reported at N=1 only (rank 0's host cores)
-        import numpy as np
-        from oracle import kvc_oracle as O
-        from oracle.cpu_decode_step import CpuDecodeHotPath
-        O.build()
-        O.use_all_cores()
-        ns = args.cpu_sample_seqs
-        ccfg = HotPathConfig(num_seqs=ns, num_layers=L)
-        ceng = CpuDecodeHotPath(ccfg)
-        cq = (np.random.RandomState(0).rand(L, ns, width_in).astype(np.float16) - 0.5).view(np.uint16)
-        co = np.zeros((L, ns, width_out), np.float32)
-        ceng.step(cq, co)
-        t0 = time.perf_counter()
-        reps = 0
-        while reps < 3 or (time.perf_counter() - t0 < 10 and reps < 200):
-            ceng.step(cq, co)
-            reps += 1
-        cdt = (time.perf_counter() - t0) / reps
-        line["cpu_baseline"] = {"value": ns / cdt, "unit": "tokens/s", "cores": O.num_threads(), "kind": "port",
-                                "sample": f"{ns} of {S} sequences per step, all {L} layers, full cycle, "
-                                          f"{reps} steps in {cdt * reps:.1f} s"}
+        line["cpu_baseline"] = cpu_step_rate(args, seconds=10)[0]
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

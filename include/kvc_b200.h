@@ -344,16 +344,25 @@ KVC_API int kvc_flush_deferred(
     int block_size, int dtype /* kvc_dtype */, kvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------
- * Launch mode of the streaming decode-attention kernel (process-wide; initial value from the
- * environment variable KVC_ATTN_PDL, default 1):
+ * Launch mode of the streaming decode-attention kernel (process-wide, read at every launch; initial
+ * value from the environment variable KVC_ATTN_PDL, default 1).  PDL = programmatic dependent launch
+ * (cudaLaunchAttributeProgrammaticStreamSerialization): the kernel's CTAs may become resident while the
+ * previous kernel of the stream drains.
  *   0  plain stream-ordered launches.
- *   1  programmatic dependent launch (PDL): the kernel may start occupying SMs while the previous
- *      kernel of the stream drains; its TMA producers prefetch cache blocks (written by EARLIER
- *      steps) immediately, its consumers execute griddepcontrol.wait before they read the step's
- *      query / new key / new value, which may be the previous kernel's output.  Always safe.
- *   2  as 1, but the caller guarantees that query / key / value are NOT produced by the previous
- *      kernel in the stream (e.g. every layer's q/k/v already resident, as in bench.py's step);
- *      the wait moves to the kernel's end (it only keeps grid completion ordered).
+ *   1  PDL, always safe (default; use it for the drop-in sequence kvcompress_reshape_and_cache ->
+ *      paged attention and right after any kernel that touches tables or the cache): every warp executes
+ *      griddepcontrol.wait before its first global access and only then lets the next kernel start;
+ *      what overlaps the previous kernel's tail is CTA launch, barrier setup and shared-memory carving.
+ *   2  PDL, caller declares that block tables, context lengths, slot mapping, cache blocks and parked
+ *      tokens read by this launch were NOT written by the immediately preceding kernel of the stream
+ *      (it was the model's QKV projection / rotary kernel, or the previous layer's attention, which only
+ *      touches its own layer's blocks): the TMA producers stream cache blocks at once; the consumers
+ *      execute griddepcontrol.wait before they read query / new key / new value.  The launch in front
+ *      of a run of mode-2 launches must be mode 0/1 (engine.py: layer 0 = 1, layers >= 1 = 2).
+ *   3  as 2, and query / key / value are not produced by the preceding kernel either (synthetic
+ *      benchmarks with every layer's inputs resident): the wait moves to the kernel's end.  Falls back
+ *      to 2 whenever raw logits are parked in the caller's workspace (contexts too long for shared
+ *      memory), because consecutive launches may share that workspace.  Not usable by a model.
  * ------------------------------------------------------------------------- */
 KVC_API int kvc_set_attention_pdl(int mode);
 KVC_API int kvc_get_attention_pdl(void);
@@ -425,7 +434,9 @@ KVC_API int kvc_select_evictions_ex(
  * kvc_free_and_append_slots: per head, context_lens -= max(evicted_block_count*B -
  *   (B - hanging), 0) (skipped when evicted_block_count == NULL), then if `append`:
  *   slot = block_tables[.., ctx / B] * B + ctx % B -> slot_mapping [L,S,H] (int64),
- *   kv_position[slot] = seq_len[s], ctx += 1.
+ *   kv_position[slot] = seq_len[s], ctx += 1.  A head whose block table is full (ctx / B ==
+ *   max_num_blocks_per_seq; the reference raises an index error, block.py:303-321) appends nothing:
+ *   its slot_mapping entry is -1 and *status (optional, int32 on the device) is set to 2.
  * ------------------------------------------------------------------------- */
 KVC_API int kvc_prepare_compression(
     const int* context_lens, int* hanging_token_count, int* evicted_kv_offsets,
@@ -437,7 +448,7 @@ KVC_API int kvc_free_and_append_slots(
     int* context_lens, const int* block_tables, const int* evicted_block_count,
     const int* hanging_token_count, const int* seq_len, int64_t* slot_mapping,
     int* kv_position, int num_seqs, int num_layers, int num_kv_heads,
-    int max_num_blocks_per_seq, int block_size, int append, kvc_stream_t stream);
+    int max_num_blocks_per_seq, int block_size, int append, int* status, kvc_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Additive: prefill KV-metric initialisation on the tensor cores (tcgen05 / TMEM).

@@ -21,6 +21,18 @@ from oracle import kvc_oracle as O
 MAX_INT = O.MAX_INT
 
 
+class CpuStepConfig:
+    """The shape fields CpuDecodeHotPath reads (same names as vllm_kvcompress_b200.engine.HotPathConfig, so either
+    can be passed); lets bench.py's CPU arm run without importing the product's engine module."""
+
+    def __init__(self, num_seqs=256, num_layers=32, num_kv_heads=8, queries_per_kv=4, head_size=128, block_size=16,
+                 max_cache_tokens=128, protected_window=32, prompt_len=6000, blocks_per_head=12):
+        self.num_seqs, self.num_layers, self.num_kv_heads = num_seqs, num_layers, num_kv_heads
+        self.queries_per_kv, self.head_size, self.block_size = queries_per_kv, head_size, block_size
+        self.max_cache_tokens, self.protected_window = max_cache_tokens, protected_window
+        self.prompt_len, self.blocks_per_head = prompt_len, blocks_per_head
+
+
 class CpuDecodeHotPath:
     def __init__(self, cfg, seed=0):
         """cfg: vllm_kvcompress_b200.engine.HotPathConfig (num_seqs = the CPU sample size)."""

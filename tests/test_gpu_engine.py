@@ -42,7 +42,7 @@ def test_device_allocator_is_invisible_to_results(graph):
     out_b = torch.zeros_like(out_a)
     if graph:
         tensors = lambda e: (e.st.k_cache, e.st.v_cache, e.st.kv_metrics, e.st.kv_position, e.st.context_lens,
-                             e.st.block_tables, e.seq_len) + pend(e)
+                             e.st.block_tables, e._pos2) + pend(e)
         state = lambda e: [t.clone() for t in tensors(e)]
         restore = lambda e, s: [t.copy_(v) for t, v in zip(tensors(e), s)]
         sa, sb = state(a), state(b)
@@ -110,7 +110,7 @@ def test_deferred_append_is_invisible_to_results(shape, graph, deferred_move):
     if graph:
         def tensors(e):
             t = (e.st.k_cache, e.st.v_cache, e.st.kv_metrics, e.st.kv_position, e.st.context_lens,
-                 e.st.block_tables, e.seq_len, e.alloc.free_mask, e.alloc.free_count)
+                 e.st.block_tables, e._pos2, e.alloc.free_mask, e.alloc.free_count)
             return t + pend(e)
         sa, sb = [t.clone() for t in tensors(a)], [t.clone() for t in tensors(b)]
         assert a.capture(qkv, out_a) and b.capture(qkv, out_b)

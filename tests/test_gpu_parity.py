@@ -488,6 +488,65 @@ def test_k4_k5_vs_reference_cuda(capi, ref_ops):
                            b.view(torch.int16) if b.dtype == torch.float16 else b)
 
 
+def test_k2_k3_vs_reference_cuda(capi, ref_ops):
+    """truncate_cache_evictions (K2) and count_block_evictions (K3) kernel-vs-kernel against the reference's
+    own CUDA kernels (csrc/kvcompress_eviction_kernels.cu:158-221) on identical device tensors."""
+    rng = np.random.RandomState(131)
+    for (S, L, H, B) in ((5, 4, 8, 16), (3, 32, 8, 16), (2, 2, 4, 4)):
+        nblk = rng.randint(1, 9, size=(S, L, H))
+        hanging = rng.randint(1, B + 1, size=(S, L, H)).astype(np.int32)
+        alloc = (nblk * B).reshape(-1)
+        offs = np.concatenate([[0], np.cumsum(alloc)[:-1]]).astype(np.int32).reshape(S, L, H)
+        total = int(alloc.sum()) + 333
+        cnt = np.minimum(rng.randint(0, 9 * B, size=(S, L, H)), nblk * B).astype(np.int32)
+        ekv = rng.randint(0, 1000, size=total).astype(np.int32)
+        elog = rng.randint(0, 1000, size=total).astype(np.int32)
+        r = [cu(ekv), cu(elog), cu(cnt)]
+        g = [cu(ekv), cu(elog), cu(cnt)]
+        ref_ops.truncate_cache_evictions(r[0], r[1], r[2], cu(offs), cu(hanging), B, total, MAX_INT)
+        capi.truncate_cache_evictions(g[0], g[1], g[2], cu(offs), cu(hanging), B, total, MAX_INT)
+        torch.cuda.synchronize()
+        for a, b in zip(r, g):
+            assert torch.equal(a, b)
+        logical = np.full(total, MAX_INT, np.int32)
+        for o, n in zip(offs.reshape(-1), nblk.reshape(-1)):
+            e = rng.randint(0, n + 1)
+            logical[o:o + e * B] = rng.randint(0, n * B, size=e * B)
+        rl, rc = cu(logical), torch.zeros((S, L, H), dtype=torch.int32, device="cuda")
+        gl, gc = cu(logical), torch.zeros((S, L, H), dtype=torch.int32, device="cuda")
+        ref_ops.count_block_evictions(rc, rl, cu(offs), cu(hanging), B, MAX_INT)
+        capi.count_block_evictions(gc, gl, cu(offs), cu(hanging), B, MAX_INT)
+        torch.cuda.synchronize()
+        assert torch.equal(rc, gc) and torch.equal(rl, gl)
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_k6_vs_reference_cuda(capi, ref_ops, bf16):
+    """kvcompress_reshape_and_cache (K6) kernel-vs-kernel against the reference's CUDA kernel
+    (csrc/kvcompress_cache_kernels.cu:27-89), strided key / value views of one QKV tensor as the model passes them."""
+    rng = np.random.RandomState(151)
+    T, H, D, B, x, NB = 41, 8, 128, 16, 8, 80
+    dt = torch.bfloat16 if bf16 else torch.float16
+    qkv = (torch.rand((T, (4 * H + 2 * H) * D), device="cuda") - 0.5).to(dt)
+    key = qkv[:, 4 * H * D: 5 * H * D].view(T, H, D)
+    val = qkv[:, 5 * H * D:].view(T, H, D)
+    kc = (torch.rand((NB, D // x, B, x), device="cuda") - 0.5).to(dt)
+    vc = (torch.rand((NB, D, B), device="cuda") - 0.5).to(dt)
+    m = torch.rand((NB, B), device="cuda")
+    bias = torch.rand(H, device="cuda")
+    slots = torch.from_numpy(rng.choice(NB * B, T * H, replace=False).astype(np.int64).reshape(T, H)).cuda()
+    slots[5, :] = -1
+    slots[7, 3] = -1
+    r = (kc.clone(), vc.clone(), m.clone())
+    g = (kc.clone(), vc.clone(), m.clone())
+    ref_ops.kvcompress_reshape_and_cache(key, val, r[0], r[1], r[2], slots.view(-1), bias, "auto", 1.0, 1.0)
+    capi.reshape_and_cache(key, val, g[0], g[1], g[2], slots, bias)
+    torch.cuda.synchronize()
+    assert torch.equal(r[0].view(torch.int16), g[0].view(torch.int16))
+    assert torch.equal(r[1].view(torch.int16), g[1].view(torch.int16))
+    assert torch.equal(r[2], g[2])
+
+
 @pytest.mark.parametrize("version", ["v1", "v2"])
 @pytest.mark.parametrize("cfg", [(41, 5, 32, 8, 160, False, False, 0), (42, 3, 64, 8, 200, True, False, 0),
                                  (43, 2, 8, 8, 1500, False, True, 0)])

@@ -29,7 +29,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
         a.record()
         ops.select_evictions(eng.evicted_logical, eng.evicted_kv_count, eng.evicted_block_count, st.kv_metrics,
                              st.kv_position, st.block_tables, st.context_lens, eng.hanging, eng.offs, eng.budgets,
-                             eng.seq_len - 1, eng.protected, B, MAX_INT)
+                             eng.last_pos, eng.protected, B, MAX_INT)
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) * 1e3)

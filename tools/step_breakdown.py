@@ -30,8 +30,8 @@ for it in range(steps):
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
     torch.cuda._sleep(3_000_000)
     ctx = st.context_lens
-    last_pos = eng.seq_len - 1
-    max_blocks = (cfg.max_cache_tokens * L * H + B - 1) // B
+    last_pos = eng.last_pos
+    max_blocks = eng.max_cache_blocks
     evs[0].record()
     ops.prepare_compression(ctx, eng.hanging, eng.offs, eng.budgets, B, max_blocks)
     evs[1].record()
@@ -52,7 +52,7 @@ for it in range(steps):
     eng.alloc.free_compressed(None, eng.evicted_block_count)
     evs[5].record()
     eng.alloc.append_slots(None, eng.seq_len, eng.slot_mapping)
-    eng.seq_len.add_(1)
+    eng._pos2.add_(1)
     evs[6].record()
     eng.forward(qkv, out)
     evs[7].record()

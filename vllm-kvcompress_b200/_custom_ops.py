@@ -132,6 +132,16 @@ def schedule_cache_moves(out_cache_moves_indices, out_cache_moves_count, evicted
         context_lens.contiguous(), block_size)
 
 
+def schedule_cache_moves_nofill(out_cache_moves_indices, out_cache_moves_count, evicted_logical_indices,
+                                evicted_kv_count, evicted_kv_offsets, block_tables, context_lens,
+                                block_size: int) -> None:
+    """The op itself, without the reference wrapper's zero-fill of the whole [max_kv, 2] workspace
+    (vllm/_custom_ops.py:1168; only entries [0, count) of each head segment are ever read)."""
+    torch.ops._C_kvc_ops.schedule_t1_cache_moves(
+        out_cache_moves_indices, out_cache_moves_count, evicted_logical_indices, evicted_kv_count,
+        evicted_kv_offsets, block_tables, context_lens, block_size)
+
+
 def execute_cache_moves(k_cache, v_cache, kv_metrics, kv_position, cache_moves_indices,
                         cache_moves_count, evicted_kv_offsets, blocks_per_head: int,
                         threads_per_head: int) -> None:
@@ -198,12 +208,14 @@ def prepare_compression(context_lens, out_hanging_token_count, out_evicted_kv_of
 
 
 def free_and_append_slots(context_lens, block_tables, evicted_block_count, hanging_token_count, seq_len,
-                          out_slot_mapping, kv_position, block_size: int, append: bool = True) -> None:
+                          out_slot_mapping, kv_position, block_size: int, append: bool = True,
+                          status=None) -> None:
     """ADDITIVE op: free the compressed trailing blocks (block.py:184-210) and append one token per head
-    (block_manager.py:269-294, block.py:275-321) in one launch."""
+    (block_manager.py:269-294, block.py:275-321) in one launch.  status (int32 [1], optional) is set to 2
+    when a head's block table is full (the reference raises an index error there)."""
     torch.ops._C_kvc_ops.free_and_append_slots(context_lens, block_tables, evicted_block_count,
                                                hanging_token_count, seq_len, out_slot_mapping, kv_position,
-                                               block_size, append)
+                                               block_size, append, status)
 
 
 def paged_attention_kvc_fused_step(out, kv_metrics, query, key, value, key_cache, value_cache, slot_mapping,

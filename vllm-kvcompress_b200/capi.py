@@ -256,8 +256,9 @@ def aggregate_prefill(kv_metrics, prefill_metrics, slot_mapping):
 
 
 def set_attention_pdl(mode: int) -> None:
-    """kvc_set_attention_pdl: 0 plain launches, 1 PDL with the wait before q/k/v (default), 2 PDL for
-    callers whose q/k/v do not come from the previous kernel in the stream."""
+    """kvc_set_attention_pdl (include/kvc_b200.h): 0 plain launches; 1 PDL, every warp waits at entry
+    (default, always safe); 2 PDL, tables / cache not written by the preceding kernel (wait before q/k/v);
+    3 PDL, q/k/v not produced by the preceding kernel either (wait at exit; synthetic benchmarks only)."""
     _check(native.load_lib().kvc_set_attention_pdl(int(mode)))
 
 

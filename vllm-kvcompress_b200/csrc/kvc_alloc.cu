@@ -18,7 +18,9 @@
 //      (binary search) -> n-th set bit of the chunk's 8 bitmap words; table entry, metadata, slot mapping,
 //      token position and context length are written in the same thread.
 // Out of blocks: nothing is allocated and *status is set to 1 (the reference raises ValueError on the
-// host, block_manager.py:108-110).
+// host, block_manager.py:108-110).  A head whose block table is full (context length == MB * B and one more
+// token to append: the reference would raise an index error on block_tables[..., MB]): nothing is allocated or
+// appended by that call or any later one and *status is set to 2 (sticky until the host resets it).
 #include "kvc_common.cuh"
 
 namespace kvc {
@@ -116,6 +118,7 @@ __global__ void __launch_bounds__(256) alloc_count_kernel(AppendParams p, int co
   const int g = cta * kNeedCta + threadIdx.x;
   int lsh, ctx;
   int local = (g < total) ? append_need(p, g, lsh, ctx) : 0;
+  if (local && ctx / p.B >= p.MB) *p.status = 2;  // table overflow: alloc_append_kernel bails out
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
   if (lane == 0 && local) atomicAdd(&s_tot, local);
@@ -200,6 +203,7 @@ __global__ void __launch_bounds__(kNeedCta) alloc_append_kernel(AppendParams p) 
   __shared__ int s_w[kNeedCta / 32];
   __shared__ int s_base, s_total_need;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (*p.status == 2) return;  // a block table is full (set by alloc_count_kernel): change nothing
   const int total_free = load_super_prefix(p.ix, s_super);
   if (t == 0) s_base = s_total_need = 0;
   __syncthreads();

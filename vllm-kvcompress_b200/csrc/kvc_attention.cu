@@ -443,13 +443,18 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 template <bool BF16, int NT, int MODE, bool ALIBI>
 __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kernel(AttnParams p, float* scratch,
                                                                                    int scratch_tokens,
-                                                                                   int smem_logit_tokens, int pdl_late) {
+                                                                                   int smem_logit_tokens, int pdl) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool kWrite = (MODE == kModeFusedWrite || MODE == kModeFusedWriteMove);
   constexpr bool kMove = (MODE == kModeFusedWriteMove);
-  // Programmatic dependent launch: the next kernel in the stream may start occupying SMs as this grid's
-  // CTAs retire (its producers then stream cache blocks under this grid's tail).  No-ops without the
-  // launch attribute.
+  // Programmatic dependent launch (kvc_set_attention_pdl, include/kvc_b200.h).  pdl <= 1: every warp waits for
+  // the stream's previous kernel (completion + memory flush) before its first global access, and only then
+  // lets the NEXT kernel start: nothing launched behind this grid can run before everything in front of it is
+  // visible.  pdl == 2: tables / context lengths / cache blocks / parked tokens were not written by the
+  // previous kernel (it was a projection kernel, or the previous layer's attention): the producers stream
+  // them right away and only the consumers wait, before q / new k / new v.  pdl == 3: those inputs are
+  // independent too; the wait sits at the exit.  All no-ops without the launch attribute.
+  if (pdl <= 1) asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
   constexpr int kPsBytes = NT * 8 * 16 * 2;
@@ -615,9 +620,9 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   // fused cache write (kvcompress_reshape_and_cache folded in, csrc/kvcompress_cache_kernels.cu:44-88):
   // the step's new token of this head is stored to the cache for later steps, and patched into the
   // staged copy of the last block below (the TMA read of that block may race with the store).
-  // Everything read so far (tables, context lengths, cache blocks of earlier steps) predates the stream's
-  // previous kernel; the step's q / new k / new v may be its output: wait for it here.
-  if (!pdl_late) asm volatile("griddepcontrol.wait;" ::: "memory");
+  // pdl == 2: everything read so far (tables, context lengths, cache blocks of earlier steps) predates the
+  // stream's previous kernel by the caller's declaration; the step's q / new k / new v may be its output.
+  if (pdl == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
   uint4 newk = make_uint4(0, 0, 0, 0);   // lane j < 16: chunk j of the new K
   uint16_t newv[4] = {0, 0, 0, 0};       // rows d = lane + 32 r of the new V
   int new_o = -1;                        // block offset of the new token, -1 = none
@@ -1008,7 +1013,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     }
   }
   // inputs declared independent of the previous kernel: still order this grid's completion after it
-  if (pdl_late) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (pdl == 3) asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 // -----------------------------------------------------------------------------
@@ -1073,7 +1078,7 @@ static int attention_pdl_mode() {
   if (g_pdl_mode < 0) {
     const char* v = getenv("KVC_ATTN_PDL");
     g_pdl_mode = v ? atoi(v) : 1;
-    if (g_pdl_mode < 0 || g_pdl_mode > 2) g_pdl_mode = 1;
+    if (g_pdl_mode < 0 || g_pdl_mode > 3) g_pdl_mode = 1;
   }
   return g_pdl_mode;
 }
@@ -1145,15 +1150,21 @@ static int launch_stream(const AttnParams& p, int num_seqs, float* scratch, int 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_mode > 0 ? 1 : 0;
-  const int pdl_late = pdl_mode == 2 ? 1 : 0;
+  // mode 3 lets consecutive launches overlap completely.  The fused modes park raw logits in the caller's
+  // workspace when they do not fit in shared memory, and consecutive launches may be handed the same
+  // workspace: the wait then has to come before the first logit is parked (mode 2).
+  int pdl = pdl_mode;
+  const bool global_logits = (MODE == kModeFused || MODE == kModeFusedWrite || MODE == kModeFusedWriteMove) &&
+                             smem_logit_tokens == 0;
+  if (pdl == 3 && global_logits) pdl = 2;
   if (p.alibi_slopes) {
     auto kern = paged_attention_stream_kernel<BF16, NT, MODE, true>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, p, scratch, scratch_tokens, smem_logit_tokens, pdl_late);
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, p, scratch, scratch_tokens, smem_logit_tokens, pdl);
   } else {
     auto kern = paged_attention_stream_kernel<BF16, NT, MODE, false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, p, scratch, scratch_tokens, smem_logit_tokens, pdl_late);
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, p, scratch, scratch_tokens, smem_logit_tokens, pdl);
   }
   if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "paged attention (stream) launch: %s", cudaGetErrorString(e));
   KVC_CHECK_LAUNCH("paged_attention_stream_kernel");
@@ -1176,7 +1187,7 @@ static int dispatch_stream(const AttnParams& p, int num_seqs, float* scratch, in
 
 // one warp per (seq, head) pays off when there are enough items to fill the machine
 static bool use_stream_kernel(int num_seqs, int num_kv_heads, int max_context_len) {
-  return (long long)num_seqs * num_kv_heads >= 148 * 4 || max_context_len <= 512;
+  return (long long)num_seqs * num_kv_heads >= (long long)sm_count() * 4 || max_context_len <= 512;
 }
 
 static int fill_params(AttnParams& p, void* out, float* metric, const void* query,
@@ -1373,7 +1384,7 @@ extern "C" int kvc_paged_attention_fused_step_deferred(
 }
 
 extern "C" int kvc_set_attention_pdl(int mode) {
-  KVC_REQUIRE(mode >= 0 && mode <= 2, KVC_ERR_INVALID, "attention PDL mode must be 0, 1 or 2, got %d", mode);
+  KVC_REQUIRE(mode >= 0 && mode <= 3, KVC_ERR_INVALID, "attention PDL mode must be 0, 1, 2 or 3, got %d", mode);
   g_pdl_mode = mode;
   return KVC_OK;
 }

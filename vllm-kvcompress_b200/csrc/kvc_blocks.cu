@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(256) free_and_append_kernel(int* __restrict__ 
                                                              const int* __restrict__ seq_len,        // [S]
                                                              int64_t* __restrict__ slot_mapping,     // [L,S,H]
                                                              int* __restrict__ kv_position,          // [NB,B]
-                                                             int S, int L, int H, int MB, int B, int append) {
+                                                             int S, int L, int H, int MB, int B, int append,
+                                                             int* __restrict__ status) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // flat (l, s, h)
   if (i >= L * S * H) return;
   const int l = i / (S * H), s = (i / H) % S, h = i % H;
@@ -92,7 +93,11 @@ __global__ void __launch_bounds__(256) free_and_append_kernel(int* __restrict__ 
     const int freed = max(evicted_blocks[g] * B - (B - hanging[g]), 0);  // block.py:184-210
     ctx -= freed;
   }
-  if (append) {
+  if (append && ctx / B >= MB) {
+    // block table full: the reference would raise an index error (block.py:303-321); nothing is appended
+    if (status) *status = 2;
+    slot_mapping[i] = -1;
+  } else if (append) {
     const int blk = block_tables[(int64_t)i * MB + ctx / B];
     const int64_t slot = (int64_t)blk * B + ctx % B;
     slot_mapping[i] = slot;
@@ -129,7 +134,8 @@ extern "C" int kvc_prepare_compression(const int* context_lens, int* hanging_tok
 extern "C" int kvc_free_and_append_slots(int* context_lens, const int* block_tables, const int* evicted_block_count,
                                          const int* hanging_token_count, const int* seq_len, int64_t* slot_mapping,
                                          int* kv_position, int num_seqs, int num_layers, int num_kv_heads,
-                                         int max_num_blocks_per_seq, int block_size, int append, kvc_stream_t stream) {
+                                         int max_num_blocks_per_seq, int block_size, int append, int* status,
+                                         kvc_stream_t stream) {
   KVC_REQUIRE(context_lens && block_tables, KVC_ERR_INVALID, "free_and_append_slots: null tensor");
   KVC_REQUIRE(!evicted_block_count || hanging_token_count, KVC_ERR_INVALID,
               "free_and_append_slots: hanging_token_count required with evicted_block_count");
@@ -139,7 +145,7 @@ extern "C" int kvc_free_and_append_slots(int* context_lens, const int* block_tab
   if (total <= 0) return KVC_OK;
   free_and_append_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
       context_lens, block_tables, evicted_block_count, hanging_token_count, seq_len, slot_mapping, kv_position,
-      num_seqs, num_layers, num_kv_heads, max_num_blocks_per_seq, block_size, append ? 1 : 0);
+      num_seqs, num_layers, num_kv_heads, max_num_blocks_per_seq, block_size, append ? 1 : 0, status);
   KVC_CHECK_LAUNCH("free_and_append_kernel");
   return KVC_OK;
 }

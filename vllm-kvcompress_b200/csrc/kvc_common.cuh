@@ -41,6 +41,19 @@ inline cudaStream_t as_stream(kvc_stream_t s) { return reinterpret_cast<cudaStre
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// SM count of the current device (148 on a B200), queried once per device; grids are sized in multiples of it
+inline int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 // ---- streaming loads / stores: this path has no reuse, keep L1 out of it ----
 __device__ __forceinline__ uint4 ld_stream16(const void* p) {
   uint4 r;

@@ -470,8 +470,8 @@ static int execute_moves_impl(
   if (total_heads <= 0) return KVC_OK;
   cudaStream_t st = as_stream(stream);
   const int2* mv = reinterpret_cast<const int2*>(cache_moves_idx);
-  // enough warps (one per (head, segment stride)) to fill 148 SMs several times over
-  int gy = (148 * 64 + total_heads - 1) / total_heads;
+  // enough warps (one per (head, segment stride)) to fill the SMs several times over
+  int gy = (sm_count() * 64 + total_heads - 1) / total_heads;
   gy = gy < 1 ? 1 : (gy > 256 ? 256 : gy);
   const bool two_byte = (dtype == KVC_F16 || dtype == KVC_BF16);
   if (two_byte && head_size == 128 && vec_size == 8 && block_size == 16 &&
@@ -496,7 +496,7 @@ static int execute_moves_impl(
       else { if (fullrow) KVC_LIGHT(false, true); else KVC_LIGHT(false, false); }
 #undef KVC_LIGHT
       KVC_CHECK_LAUNCH("execute_moves_light_kernel");
-      const dim3 cgrid(min((chunks + kMoveWarps - 1) / kMoveWarps, 148 * 8));
+      const dim3 cgrid(min((chunks + kMoveWarps - 1) / kMoveWarps, sm_count() * 8));
       if (pend)
         execute_moves_b16_d128_chunk_kernel<true><<<cgrid, kMoveWarps * kWarp, 0, st>>>(
             kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, pkv, pend_slot,

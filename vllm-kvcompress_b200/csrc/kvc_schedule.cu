@@ -76,7 +76,7 @@ static int launch_truncate(int* evicted_kv_indices, int* evicted_logical_indices
   truncate_counts_kernel<<<ceil_div(total_heads, 256), 256, 0, stream>>>(
       evicted_kv_count, hanging_token_count, total_heads, B);
   KVC_CHECK_LAUNCH("truncate_counts_kernel");
-  const int tail_warps = 148 * 8;  // one wave of 256-thread CTAs for the open-ended tail
+  const int tail_warps = sm_count() * 8;  // one wave of 256-thread CTAs for the open-ended tail
   const int warps = total_heads - 1 + tail_warps;
   truncate_fill_kernel<<<ceil_div(warps, 8), 256, 0, stream>>>(
       evicted_kv_indices, evicted_logical_indices, evicted_kv_count, evicted_kv_offsets,

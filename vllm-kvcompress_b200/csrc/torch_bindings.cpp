@@ -459,7 +459,8 @@ void prepare_compression(torch::Tensor& context_lens, torch::Tensor& hanging_tok
 void free_and_append_slots(torch::Tensor& context_lens, torch::Tensor& block_tables,
                            const c10::optional<torch::Tensor>& evicted_block_count,
                            const c10::optional<torch::Tensor>& hanging_token_count, torch::Tensor& seq_len,
-                           torch::Tensor& slot_mapping, torch::Tensor& kv_position, int64_t block_size, bool append) {
+                           torch::Tensor& slot_mapping, torch::Tensor& kv_position, int64_t block_size, bool append,
+                           const c10::optional<torch::Tensor>& status) {
   TORCH_CHECK(context_lens.dim() == 3 && block_tables.dim() == 4, "context_lens [L,S,H], block_tables [L,S,H,MB] expected");
   TORCH_CHECK(slot_mapping.scalar_type() == at::kLong && slot_mapping.is_contiguous(), "slot_mapping must be contiguous int64");
   const int L = context_lens.size(0), S = context_lens.size(1), H = context_lens.size(2);
@@ -469,7 +470,8 @@ void free_and_append_slots(torch::Tensor& context_lens, torch::Tensor& block_tab
                    evicted_block_count ? i32(evicted_block_count.value(), "evicted_block_count") : nullptr,
                    hanging_token_count ? i32(hanging_token_count.value(), "hanging_token_count") : nullptr,
                    i32(seq_len, "seq_len"), slot_mapping.data_ptr<int64_t>(), i32_mut(kv_position, "kv_position"), S, L, H,
-                   block_tables.size(3), (int)block_size, append ? 1 : 0, cur_stream()),
+                   block_tables.size(3), (int)block_size, append ? 1 : 0,
+                   status ? const_cast<int*>(i32(status.value(), "status")) : nullptr, cur_stream()),
                "free_and_append_slots");
 }
 
@@ -847,7 +849,7 @@ TORCH_LIBRARY_FRAGMENT(_C_kvc_ops, kvc_ops) {
   kvc_ops.def(
       "free_and_append_slots(Tensor! context_lens, Tensor block_tables, Tensor? evicted_block_count,"
       "                       Tensor? hanging_token_count, Tensor seq_len, Tensor! slot_mapping,"
-      "                       Tensor! kv_position, int block_size, bool append) -> ()");
+      "                       Tensor! kv_position, int block_size, bool append, Tensor(a!)? status=None) -> ()");
   kvc_ops.impl("free_and_append_slots", torch::kCUDA, &free_and_append_slots);
   kvc_ops.def(
       "prefill_kv_metrics(Tensor(a!)? kv_metric_out, Tensor(b!)? kv_metrics, Tensor? slot_mapping, Tensor query,"

@@ -33,6 +33,7 @@ from typing import Optional
 import torch
 
 from . import _custom_ops as ops
+from . import _custom_ops as _default_ops
 from . import capi
 from . import workload as W
 
@@ -55,10 +56,16 @@ class HotPathConfig:
     selection: str = "fused"           # "fused" (kvc_select kernels) | "chain" (torch.sort + K1 + K2)
     fused_metrics: bool = True         # attention accumulates sum_q p^2 itself
     fused_cache_write: bool = True     # ... and writes the step's new K/V (one launch per layer)
-    # the step's q/k/v of every layer are resident before the step starts (synthetic projections), i.e.
-    # never the output of the previous kernel in the stream: lets consecutive attention launches overlap
-    # (kvc_set_attention_pdl mode 2).  A model whose QKV GEMM feeds the attention kernel uses mode 1.
-    inputs_independent: bool = True
+    # Launch mode of the attention kernels (kvc_set_attention_pdl, include/kvc_b200.h):
+    #   "model" (default)  what a model can use: layer 0 follows the bookkeeping kernels that rewrite tables
+    #                      and slot mapping -> mode 1 (every warp waits at entry); layers >= 1 follow a kernel
+    #                      that touches neither this layer's blocks nor its tables -> mode 2 (cache blocks are
+    #                      streamed at once, the wait sits in front of q / new k / new v)
+    #   "independent"      layers >= 1 in mode 3: q/k/v are declared independent of the previous kernel as
+    #                      well (true for this harness, whose inputs are resident before the step; never
+    #                      for a model) -- A/B measurements only
+    #   "safe" / "off"     mode 1 / mode 0 for every layer
+    attention_pdl: str = "model"
     # "device": blocks come from / return to the device-side allocator every step (kvc_alloc_*: free the
     # compressed trailing blocks, allocate for heads crossing a block boundary, tables rewritten in place);
     # "static": every head owns a fixed slab and only context_lens moves (round-1 harness)
@@ -80,12 +87,20 @@ class DecodeHotPath:
     """One replica: owns the unified cache, per-head tables and metrics of `num_seqs` sequences
     already compressed to `max_cache_tokens` per head (state after a post-prefill compression)."""
 
-    def __init__(self, cfg: HotPathConfig, device: torch.device):
+    def __init__(self, cfg: HotPathConfig, device: torch.device, ops_module=None):
+        """ops_module: object with the vllm/_custom_ops.py function surface (default: this package's shim over
+        libkvc_b200).  Tests and the reference-kernel measurement bind the same driver to other implementations
+        of that surface (oracle/ref_ops.py: the reference's own CUDA kernels)."""
         self.cfg = cfg
         self.dev = device
-        if "KVC_ATTN_PDL" not in os.environ:   # an explicit environment setting wins (A/B runs)
-            capi.set_attention_pdl(2 if cfg.inputs_independent else 1)
-        self.attention_pdl = capi.get_attention_pdl()
+        self.ops = ops_module if ops_module is not None else ops
+        if cfg.attention_pdl not in ("model", "independent", "safe", "off"):
+            raise ValueError(f"attention_pdl: {cfg.attention_pdl!r}")
+        # an explicit environment setting wins for every layer (A/B runs)
+        env = os.environ.get("KVC_ATTN_PDL")
+        first, rest = {"model": (1, 2), "independent": (1, 3), "safe": (1, 1), "off": (0, 0)}[cfg.attention_pdl]
+        self.pdl_first, self.pdl_rest = (int(env), int(env)) if env is not None else (first, rest)
+        self.attention_pdl = self.pdl_rest
         S, L, H, B, D = cfg.num_seqs, cfg.num_layers, cfg.num_kv_heads, cfg.block_size, cfg.head_size
         self.launches = 0
         if cfg.allocator == "device":
@@ -100,20 +115,28 @@ class DecodeHotPath:
         self.st = st
         # token positions of the surviving KVs: a random subset of the prompt (what a CR=64 eviction
         # leaves), newest `protected_window` tokens always present
-        g = torch.Generator(device="cpu").manual_seed(cfg.seed + 7)
         n = cfg.max_cache_tokens
         heads = L * S * H
-        keep = torch.rand((heads, cfg.prompt_len - cfg.protected_window), generator=g).topk(
-            n - cfg.protected_window, dim=1).indices.sort(dim=1).values
-        pos = torch.cat([keep, torch.arange(cfg.prompt_len - cfg.protected_window, cfg.prompt_len)
-                         .expand(heads, -1)], dim=1).to(torch.int32)          # [heads, n]
-        bt = st.block_tables.view(heads, -1).cpu()
-        slots = (bt[:, : n // B].long()[:, :, None] * B + torch.arange(B)[None, None]).view(heads, n)
-        kv_pos = torch.full((st.NB * B,), -1, dtype=torch.int32)
-        kv_pos[slots.flatten()] = pos.flatten()
-        st.kv_position = kv_pos.view(st.NB, B).to(device)
+        g = torch.Generator(device=device).manual_seed(cfg.seed + 7)
+        bt = st.block_tables.view(heads, -1)
+        kv_pos = torch.full((st.NB * B,), -1, dtype=torch.int32, device=device)
+        recent = torch.arange(cfg.prompt_len - cfg.protected_window, cfg.prompt_len, device=device, dtype=torch.int32)
+        ar = torch.arange(B, device=device)
+        for h0 in range(0, heads, 8192):    # chunks bound the [heads, prompt_len] scratch (1.5 GB at 64 K heads)
+            h1 = min(heads, h0 + 8192)
+            keep = torch.rand((h1 - h0, cfg.prompt_len - cfg.protected_window), generator=g, device=device).topk(
+                n - cfg.protected_window, dim=1).indices.sort(dim=1).values.to(torch.int32)
+            pos = torch.cat([keep, recent.expand(h1 - h0, -1)], dim=1)                      # [chunk, n]
+            slots = (bt[h0:h1, : n // B].long()[:, :, None] * B + ar[None, None]).view(h1 - h0, n)
+            kv_pos[slots.flatten()] = pos.flatten()
+        st.kv_position = kv_pos.view(st.NB, B)
         st.kv_metrics.uniform_(0.01, 1.0, generator=torch.Generator(device=device).manual_seed(cfg.seed + 9))
-        self.seq_len = torch.full((S,), cfg.prompt_len, dtype=torch.int32, device=device)  # tokens so far
+        # [2, S]: row 0 = tokens so far (= position of the token being appended), row 1 = position of the last
+        # cached token; one add per step advances both (no other element-wise torch op runs inside a step)
+        self._pos2 = torch.empty((2, S), dtype=torch.int32, device=device)
+        self._pos2[0].fill_(cfg.prompt_len)
+        self._pos2[1].fill_(cfg.prompt_len - 1)
+        self.seq_len, self.last_pos = self._pos2[0], self._pos2[1]
         self.head_bias = torch.zeros((L, H), dtype=torch.float32, device=device)
         self.zeros_s = torch.zeros(S, dtype=torch.int32, device=device)
         self.protected = torch.full((S,), cfg.protected_window, dtype=torch.int32, device=device)
@@ -141,6 +164,7 @@ class DecodeHotPath:
             self.pend_slot = torch.full((L, S, H), -1, dtype=torch.int64, device=device)
             self.pend_dst = (torch.full((L, S, H), -1, dtype=torch.int64, device=device)
                              if cfg.deferred_move else None)
+        self.table_status = torch.zeros(1, dtype=torch.int32, device=device)
         self.alloc = None
         if cfg.allocator == "device":
             self.alloc = capi.DeviceBlockAllocator(st.NB, st.block_tables, st.context_lens, st.kv_position, B)
@@ -155,17 +179,25 @@ class DecodeHotPath:
         cfg = self.cfg
         nblk = (self.st.context_lens + cfg.block_size - 1) // cfg.block_size   # [L,S,H]
         total = nblk.sum(dim=(0, 2))
-        max_blocks = (cfg.max_cache_tokens * cfg.num_layers * cfg.num_kv_heads + cfg.block_size - 1) // cfg.block_size
-        return (total - max_blocks).clamp_(min=0).to(torch.int32)
+        return (total - self.max_cache_blocks).clamp_(min=0).to(torch.int32)
+
+    @property
+    def max_cache_blocks(self) -> int:
+        """scheduler.py:117-137: max_cache_tokens is rounded up to a block multiple per head first."""
+        cfg = self.cfg
+        B = cfg.block_size
+        per_head = (cfg.max_cache_tokens + B - 1) // B * B
+        return (per_head * cfg.num_layers * cfg.num_kv_heads + B - 1) // B
 
     def compress(self) -> None:
         """Compression cycle + append, device-side end to end (no host round trip)."""
         cfg, st = self.cfg, self.st
         B = cfg.block_size
+        ops = self.ops
         ctx = st.context_lens                                                  # [L,S,H]
-        last_pos = self.seq_len - 1
+        last_pos = self.last_pos
         if cfg.selection == "fused":
-            max_blocks = (cfg.max_cache_tokens * cfg.num_layers * cfg.num_kv_heads + B - 1) // B
+            max_blocks = self.max_cache_blocks
             ops.prepare_compression(ctx, self.hanging, self.offs, self.budgets, B, max_blocks)
             ops.select_evictions(self.evicted_logical, self.evicted_kv_count, self.evicted_block_count,
                                  st.kv_metrics, st.kv_position, st.block_tables, ctx, self.hanging, self.offs,
@@ -196,8 +228,8 @@ class DecodeHotPath:
             self.hanging.copy_(hanging)
         # the op itself, not the reference wrapper: that one zero-fills the whole [max_kv, 2] workspace
         # first (vllm/_custom_ops.py:1168, 100 MB per call here); only [0, count) per head is ever read
-        torch.ops._C_kvc_ops.schedule_t1_cache_moves(self.cache_moves, self.moves_count, logical,
-                                                     self.evicted_kv_count, offs, st.block_tables, ctx, B)
+        ops.schedule_cache_moves_nofill(self.cache_moves, self.moves_count, logical, self.evicted_kv_count, offs,
+                                        st.block_tables, ctx, B)
         if self.deferred:
             ops.execute_cache_moves_deferred(st.k_cache, st.v_cache, st.kv_metrics, st.kv_position,
                                              self.cache_moves, self.moves_count, offs, self.pend_kv, self.pend_slot,
@@ -213,7 +245,7 @@ class DecodeHotPath:
         the reference's reshape_and_cache + execute_cache_moves sequence leaves."""
         if not self.deferred:
             return
-        ops.flush_deferred(self.st.k_cache, self.st.v_cache, self.pend_kv, self.pend_slot, self.pend_dst)
+        self.ops.flush_deferred(self.st.k_cache, self.st.v_cache, self.pend_kv, self.pend_slot, self.pend_dst)
 
     # ------------------------------------------------------------------ append + forward
     def append_slots(self) -> None:
@@ -227,17 +259,31 @@ class DecodeHotPath:
             self.alloc.append_slots(None, self.seq_len, self.slot_mapping)
             self.launches += 4
         else:
-            ops.free_and_append_slots(st.context_lens, st.block_tables, self.evicted_block_count, self.hanging,
-                                      self.seq_len, self.slot_mapping, st.kv_position, cfg.block_size, True)
+            self.ops.free_and_append_slots(st.context_lens, st.block_tables, self.evicted_block_count, self.hanging,
+                                           self.seq_len, self.slot_mapping, st.kv_position, cfg.block_size, True,
+                                           self.table_status)
             self.launches += 1
-        self.seq_len.add_(1)
+        self._pos2.add_(1)
+
+    def check_status(self) -> None:
+        """Raise if the allocator ran out of blocks or a head outgrew its block table (host sync; the reference
+        raises at the failing call, block_manager.py:108-110 / an index error in block.py:303-321)."""
+        st = int(self.table_status.item())
+        if self.alloc is not None:
+            st = max(st, int(self.alloc.status.item()))
+        if st == 1:
+            raise RuntimeError("KV cache out of free blocks")
+        if st == 2:
+            raise RuntimeError("a head's block table is full (blocks_per_head too small for this workload)")
 
     def forward_layer(self, l: int, x: torch.Tensor, o: torch.Tensor, last_pos: torch.Tensor,
                       timing=None) -> None:
         """x [S, (Hq + 2H) * D], o [S, Hq * D]: cache write + decode attention of layer l."""
-        cfg, st = self.cfg, self.st
+        cfg, st, ops = self.cfg, self.st, self.ops
         H, Q, D, B = cfg.num_kv_heads, cfg.queries_per_kv, cfg.head_size, cfg.block_size
         Hq = H * Q
+        if self.ops is _default_ops:
+            capi.set_attention_pdl(self.pdl_first if l == 0 else self.pdl_rest)
         q = x[:, : Hq * D].view(-1, Hq, D)
         k = x[:, Hq * D: (Hq + H) * D].view(-1, H, D)
         v = x[:, (Hq + H) * D:].view(-1, H, D)
@@ -282,7 +328,7 @@ class DecodeHotPath:
 
     def forward(self, qkv: torch.Tensor, out: torch.Tensor) -> None:
         """qkv [L, S, (Hq + 2H) * D], out [L, S, Hq * D]."""
-        last_pos = self.seq_len - 1
+        last_pos = self.last_pos
         for l in range(self.cfg.num_layers):
             self.forward_layer(l, qkv[l], out[l], last_pos)
         self._aggregate_unfused()
@@ -338,7 +384,7 @@ class DecodeHotPath:
                 self._ev_in[gi].record(self._h2d)
         self.compress()
         self.append_slots()
-        last_pos = self.seq_len - 1
+        last_pos = self.last_pos
         for gi, (a, b) in enumerate(groups):
             main.wait_event(self._ev_in[gi])
             for l in range(a, b):
@@ -368,6 +414,68 @@ class DecodeHotPath:
         self.host_graph.replay()
         self.launches += getattr(self, "launches_per_step", 0)
 
+    # ------------------------------------------------------------------ end to end, pipelined across steps
+    def submit_host(self, qkv_host: torch.Tensor, out_host: torch.Tensor) -> None:
+        """Public end-to-end call, pipelined: enqueue one decode step whose Q/K/V live in pinned host memory
+        and whose attention output goes back to pinned host memory, and return at once.  Two device staging
+        buffers alternate, so the H2D copy of step t+1 and the D2H copy of step t-1 run under the compute of
+        step t (PCIe is full duplex; three streams): a step costs max(H2D, compute, D2H) instead of their sum.
+        out_host of step t is valid after wait_host() (or after the second following submit_host returns
+        its events); the caller must not reuse the host buffers of a step before that."""
+        cfg = self.cfg
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_pipe"):
+            qshape = (cfg.num_layers, cfg.num_seqs, (cfg.num_kv_heads * cfg.queries_per_kv + 2 * cfg.num_kv_heads)
+                      * cfg.head_size)
+            oshape = (cfg.num_layers, cfg.num_seqs, cfg.num_kv_heads * cfg.queries_per_kv * cfg.head_size)
+            assert tuple(qkv_host.shape) == qshape and tuple(out_host.shape) == oshape
+            pipe = {"h2d": torch.cuda.Stream(), "d2h": torch.cuda.Stream(), "n": 0, "graphs": [None, None],
+                    "qkv": [torch.empty(qshape, dtype=cfg.dtype, device=self.dev) for _ in range(2)],
+                    "out": [torch.empty(oshape, dtype=cfg.dtype, device=self.dev) for _ in range(2)],
+                    "in_ready": [torch.cuda.Event() for _ in range(2)],
+                    "computed": [torch.cuda.Event() for _ in range(2)],
+                    "drained": [torch.cuda.Event() for _ in range(2)]}
+            for ev in pipe["computed"] + pipe["drained"]:
+                ev.record(main)
+            self._pipe = pipe
+        pipe = self._pipe
+        i = pipe["n"] & 1
+        pipe["n"] += 1
+        h2d, d2h = pipe["h2d"], pipe["d2h"]
+        h2d.wait_event(pipe["computed"][i])          # the step two back has consumed this staging buffer
+        with torch.cuda.stream(h2d):
+            pipe["qkv"][i].copy_(qkv_host, non_blocking=True)
+            pipe["in_ready"][i].record(h2d)
+        main.wait_event(pipe["in_ready"][i])
+        main.wait_event(pipe["drained"][i])          # ... and its output has left the device
+        if cfg.selection == "fused":
+            if pipe["graphs"][i] is None:            # first use of this buffer: run eagerly once, then capture
+                n0 = self.launches
+                self.step(pipe["qkv"][i], pipe["out"][i])
+                self.launches_per_step = self.launches - n0
+                graph = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(graph):        # capture does not execute: the state stays where it is
+                    self.step(pipe["qkv"][i], pipe["out"][i])
+                self.launches = n0 + self.launches_per_step
+                pipe["graphs"][i] = graph
+            else:
+                pipe["graphs"][i].replay()
+                self.launches += getattr(self, "launches_per_step", 0)
+        else:
+            self.step(pipe["qkv"][i], pipe["out"][i])
+        pipe["computed"][i].record(main)
+        d2h.wait_event(pipe["computed"][i])
+        with torch.cuda.stream(d2h):
+            out_host.copy_(pipe["out"][i], non_blocking=True)
+            pipe["drained"][i].record(d2h)
+
+    def wait_host(self) -> None:
+        """Every submitted step is complete and its output is in host memory."""
+        if hasattr(self, "_pipe"):
+            torch.cuda.current_stream().wait_stream(self._pipe["d2h"])
+        torch.cuda.current_stream().synchronize()
+
     # ------------------------------------------------------------------ measurement helper
     def profile_attention(self, qkv: torch.Tensor, out: torch.Tensor, steps: int = 5):
         """Device time of the attention launches alone, doing exactly the work they do inside a step: the
@@ -382,7 +490,7 @@ class DecodeHotPath:
         Hq = H * Q
         self.compress()
         self.append_slots()
-        last_pos = self.seq_len - 1
+        last_pos = self.last_pos
         nbytes = self.attention_bytes() / L
 
         def attn_only():

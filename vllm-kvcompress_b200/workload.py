@@ -81,10 +81,14 @@ def make_state(S: int, L: int, H: int, B: int, D: int, ctx, dtype=torch.float16,
     if fill_cache:
         gd = torch.Generator(device=dev).manual_seed(seed + 1)
         scale = float(D) ** -0.5  # vllm/utils.py:664-720: U(-1/sqrt(D), 1/sqrt(D))
-        k_cache = (torch.rand((NB, D // x, B, x), generator=gd, device=dev, dtype=torch.float32)
-                   .mul_(2 * scale).sub_(scale).to(dtype))
-        v_cache = (torch.rand((NB, D, B), generator=gd, device=dev, dtype=torch.float32)
-                   .mul_(2 * scale).sub_(scale).to(dtype))
+        k_cache = torch.empty((NB, D // x, B, x), device=dev, dtype=dtype)
+        v_cache = torch.empty((NB, D, B), device=dev, dtype=dtype)
+        step = 1 << 18   # blocks per chunk: bounds the fp32 scratch to 2 GB at large caches
+        for cache in (k_cache, v_cache):
+            for b0 in range(0, NB, step):
+                n = min(step, NB - b0)
+                cache[b0:b0 + n] = (torch.rand((n,) + tuple(cache.shape[1:]), generator=gd, device=dev,
+                                               dtype=torch.float32).mul_(2 * scale).sub_(scale).to(dtype))
     else:
         k_cache = torch.zeros((NB, D // x, B, x), device=dev, dtype=dtype)
         v_cache = torch.zeros((NB, D, B), device=dev, dtype=dtype)
