@@ -248,62 +248,12 @@ def workload_config(args, batch, model=None):
 
 
 def compaction_roofline(device, peak):
-    """execute_cache_moves on the post-prefill shape of BASELINE.md config 5 (S=3 sequences of
-    6000 tokens, L=32, H=8), CR in {64, 16, 8, 4}: algorithmic GB/s (1048 B per move) vs HBM peak."""
-    from vllm_kvcompress_b200 import _custom_ops as ops
-    from vllm_kvcompress_b200 import workload as W
-    res = {}
-    S, L, H, B, D = 3, 32, 8, 16, 128
-    for cr, keep in ((64, 128), (16, 368), (8, 736), (4, 1488)):  # BASELINE.md config 5: max_cache_tokens per CR
-        st = W.make_state(S, L, H, B, D, 6000, dtype=torch.float16, device=device, seed=cr, slack=1.0,
-                          fill_cache=False)
-        hanging = W.hanging_token_counts(st.context_lens, B).transpose(0, 1).contiguous()
-        offs = W.evicted_kv_offsets(st.context_lens, B)
-        N = int(((st.context_lens + B - 1) // B).sum()) * B
-        nblk_total = int(((st.context_lens + B - 1) // B).sum(dim=(0, 2))[0])
-        budgets = torch.full((S,), nblk_total - keep * L * H // B, dtype=torch.int32, device=device)
-        last = torch.full((S,), 5999, dtype=torch.int32, device=device)
-        prot = torch.full((S,), 32, dtype=torch.int32, device=device)
-        logical = torch.empty(N, dtype=torch.int32, device=device)
-        cnt = torch.empty((S, L, H), dtype=torch.int32, device=device)
-        blk = torch.empty_like(cnt)
-        def timed(fn, reps=5):
-            ts = []
-            for _ in range(reps):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-                fn()
-                b.record()
-                torch.cuda.synchronize()
-                ts.append(a.elapsed_time(b))
-            return sorted(ts[1:])[len(ts[1:]) // 2]
-
-        sel_ms = timed(lambda: ops.select_evictions(logical, cnt, blk, st.kv_metrics, st.kv_position,
-                                                    st.block_tables, st.context_lens, hanging, offs, budgets,
-                                                    last, prot, B, W.MAX_INT))
-        moves = torch.empty((N, 2), dtype=torch.int32, device=device)
-        mcnt = torch.empty((S, L, H), dtype=torch.int32, device=device)
-        k4_ms = timed(lambda: torch.ops._C_kvc_ops.schedule_t1_cache_moves(moves, mcnt, logical, cnt, offs,
-                                                                           st.block_tables, st.context_lens, B))
-        nmoves = int(mcnt.sum())
-        times = []
-        for it in range(6):  # moves are idempotent on the same state (src never overwritten): re-run is valid
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            ops.execute_cache_moves(st.k_cache, st.v_cache, st.kv_metrics, st.kv_position, moves, mcnt, offs, 1, 16)
-            e1.record()
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
-        t = sorted(times[1:])[len(times[1:]) // 2]
-        gbs = nmoves * 1048 / (t * 1e-3) / 1e9
-        res[f"cr{cr}"] = {"moves": nmoves, "ms": t, "achieved_gbs": gbs, "frac": gbs / peak,
-                          "cache_gb": st.NB * 8192 / 1e9,
-                          # the schedule builders in front of it (SURVEY 8d: 12 B per candidate slot, 20 B per move)
-                          "select_evictions_ms": sel_ms, "select_gbs": N * 12 / (sel_ms * 1e-3) / 1e9,
-                          "schedule_moves_ms": k4_ms}
-        del st, moves
-        torch.cuda.empty_cache()
-    return res
+    """execute_cache_moves on the post-prefill shape of BASELINE.md config 5, CR in {64, 16, 8, 4}: algorithmic
+    GB/s (1048 B per move) vs HBM peak, the sector floor of the move list and the committed ncu traffic
+    (tools/compaction_bench.py: 5 warm-up + 20 timed repetitions, each on a re-initialised cache)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import compaction_bench
+    return compaction_bench.run(device, peak)
 
 
 def prefill_metrics_bench(device):

@@ -393,6 +393,16 @@ KVC_API int kvc_get_attention_pdl(void);
 KVC_API int kvc_set_select_mode(int mode);
 KVC_API int kvc_get_select_mode(void);
 
+/* Kernel choice of kvc_execute_cache_moves for the production layout (process-wide; initial value from the
+ * environment variable KVC_MOVES_MODE): 0 (default) = the register-gather run kernel (post-prefill shapes) and
+ * the one-move / run kernels (decode-time batches); 1 = post-prefill compaction (fewer than 4096 heads) runs the
+ * TMA-staged kernel instead: whole source V blocks and the old destination block bulk-copied into shared
+ * memory (cp.async.bulk), lane = token column copies, finished K / V blocks written back with one bulk store
+ * each.  Results are identical in both modes; on the B200 the staged kernel is bound by the bytes it can keep in
+ * flight from ~200 KB of shared memory and is the slower of the two. */
+KVC_API int kvc_set_moves_mode(int mode);
+KVC_API int kvc_get_moves_mode(void);
+
 KVC_API size_t kvc_select_evictions_workspace_bytes(int64_t max_evicted_kv, int block_size);
 
 KVC_API int kvc_select_evictions(

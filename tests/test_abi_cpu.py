@@ -197,3 +197,20 @@ def test_select_mode_switch_round_trips(built):
     assert lib.kvc_set_select_mode(2) == 0 and lib.kvc_get_select_mode() == 2
     assert lib.kvc_set_select_mode(7) != 0 and lib.kvc_get_select_mode() == 2   # rejected, unchanged
     assert lib.kvc_set_select_mode(0) == 0
+
+
+def test_moves_mode_switch_round_trips(built):
+    lib = built.load_lib()
+    assert lib.kvc_get_moves_mode() == 0
+    assert lib.kvc_set_moves_mode(1) == 0 and lib.kvc_get_moves_mode() == 1
+    assert lib.kvc_set_moves_mode(5) != 0 and lib.kvc_get_moves_mode() == 1   # rejected, unchanged
+    assert lib.kvc_set_moves_mode(0) == 0
+
+
+def test_attention_pdl_modes_round_trip(built):
+    lib = built.load_lib()
+    keep = lib.kvc_get_attention_pdl()
+    for m in (0, 1, 2, 3):
+        assert lib.kvc_set_attention_pdl(m) == 0 and lib.kvc_get_attention_pdl() == m
+    assert lib.kvc_set_attention_pdl(4) != 0 and lib.kvc_get_attention_pdl() == 3
+    assert lib.kvc_set_attention_pdl(keep) == 0

@@ -117,6 +117,14 @@ def test_k3_golden(capi, name):
     np.testing.assert_array_equal(logical.cpu().numpy(), c["out_evicted_logical_indices"])
 
 
+@pytest.fixture(params=[0, 1], ids=["register_gather", "staged_tma"])
+def moves_mode(request, capi):
+    """execute_cache_moves kernel choice for post-prefill shapes (kvc_set_moves_mode): both must be bit-exact"""
+    capi.set_moves_mode(request.param)
+    yield request.param
+    capi.set_moves_mode(0)
+
+
 def torch_cache(a):
     if a.dtype == np.uint16:
         return cu16(a, False)
@@ -128,7 +136,7 @@ def cache_bits(t, like):
 
 
 @pytest.mark.parametrize("name", sorted(MOVES))
-def test_k4_k5_golden(capi, name):
+def test_k4_k5_golden(capi, name, moves_mode):
     c = MOVES[name]
     B = int(c["B"])
     moves = torch.zeros((int(c["total_kv"]), 2), dtype=torch.int32, device="cuda")
@@ -301,7 +309,7 @@ def random_moves_state(seed, S, L, H, B, D, max_blocks, dtype=np.uint16):
 
 @pytest.mark.parametrize("cfg", [(21, 4, 4, 8, 16, 128, 30), (22, 2, 2, 4, 16, 128, 200),
                                  (23, 3, 2, 2, 4, 4, 9), (24, 2, 3, 2, 1, 2, 40)])
-def test_k4_k5_random_vs_oracle(capi, O, cfg):
+def test_k4_k5_random_vs_oracle(capi, O, cfg, moves_mode):
     seed, S, L, H, B, D, mb = cfg
     c = random_moves_state(seed, S, L, H, B, D, mb)
     N = int(c["total_kv"])
@@ -325,6 +333,54 @@ def test_k4_k5_random_vs_oracle(capi, O, cfg):
     capi.execute_cache_moves(gk, gv, gm, gp, moves, mcnt, offs)
     np.testing.assert_array_equal(cache_bits(gk, c["k_cache"]), kc)
     np.testing.assert_array_equal(cache_bits(gv, c["v_cache"]), vc)
+    np.testing.assert_array_equal(gm.cpu().numpy(), km)
+    np.testing.assert_array_equal(gp.cpu().numpy(), kp)
+
+
+@pytest.mark.parametrize("keep", [128, 368, 1488])
+def test_k5_post_prefill_compaction_vs_oracle(capi, O, keep, moves_mode):
+    """The post-prefill compaction of BASELINE config 5 in miniature: heads of 6000 tokens evicted down to `keep`
+    (CR 64 / 16 / 4), protected window 32: runs whose 16 sources come from 16 different blocks (more than the
+    staged kernel's ring holds: the refill path) as well as runs with several sources per block."""
+    rng = np.random.RandomState(400 + keep)
+    S, L, H, B, D, ctx_len = 1, 2, 6, 16, 128, 6000
+    ctx = np.full((L, S, H), ctx_len, np.int32)
+    ctx[0, 0, 1], ctx[1, 0, 2] = 5987, 5993                # ragged last blocks
+    nblk = (ctx + B - 1) // B
+    MB, NB = int(nblk.max()) + 1, int(nblk.sum()) + 5
+    phys = rng.permutation(NB)
+    bt = np.zeros((L, S, H, MB), np.int32)
+    p = 0
+    for l in range(L):
+        for h in range(H):
+            bt[l, 0, h, :nblk[l, 0, h]] = phys[p:p + nblk[l, 0, h]]
+            p += nblk[l, 0, h]
+    alloc = np.transpose(nblk, (1, 0, 2)).reshape(-1) * B
+    offs = np.concatenate([[0], np.cumsum(alloc)[:-1]]).astype(np.int32).reshape(S, L, H)
+    total = int(alloc.sum())
+    logical = np.full(total, MAX_INT, np.int32)
+    cnt = np.zeros((S, L, H), np.int32)
+    for l in range(L):
+        for h in range(H):
+            n = int(ctx[l, 0, h])
+            c = n - keep - int(rng.randint(0, 40))            # heads end up with slightly different lengths
+            cnt[0, l, h] = c
+            logical[offs[0, l, h]: offs[0, l, h] + c] = np.sort(rng.choice(n - 32, c, replace=False))
+    wm, wc = np.zeros((total, 2), np.int32), np.zeros((S, L, H), np.int32)
+    O.schedule_cache_moves(wm, wc, logical, cnt, offs, bt, ctx, B)
+    moves = torch.zeros((total, 2), dtype=torch.int32, device="cuda")
+    mcnt = torch.zeros((S, L, H), dtype=torch.int32, device="cuda")
+    capi.schedule_t1_cache_moves(moves, mcnt, cu(logical), cu(cnt), cu(offs), cu(bt), cu(ctx), B)
+    np.testing.assert_array_equal(mcnt.cpu().numpy(), wc)
+    np.testing.assert_array_equal(moves.cpu().numpy(), wm)
+    kc = rng.randint(0, 65535, size=(NB, D // 8, B, 8)).astype(np.uint16)
+    vc = rng.randint(0, 65535, size=(NB, D, B)).astype(np.uint16)
+    km, kp = rng.rand(NB, B).astype(np.float32), rng.randint(0, 10000, size=(NB, B)).astype(np.int32)
+    gk, gv, gm, gp = torch_cache(kc), torch_cache(vc), cu(km), cu(kp)
+    capi.execute_cache_moves(gk, gv, gm, gp, moves, mcnt, cu(offs))
+    O.execute_cache_moves(kc, vc, km, kp, wm, wc, offs)
+    np.testing.assert_array_equal(cache_bits(gk, kc), kc)
+    np.testing.assert_array_equal(cache_bits(gv, vc), vc)
     np.testing.assert_array_equal(gm.cpu().numpy(), km)
     np.testing.assert_array_equal(gp.cpu().numpy(), kp)
 
@@ -466,7 +522,7 @@ def test_k1_vs_reference_cuda(capi, ref_ops, cfg):
     np.testing.assert_array_equal(got[3], rem.cpu().numpy())
 
 
-def test_k4_k5_vs_reference_cuda(capi, ref_ops):
+def test_k4_k5_vs_reference_cuda(capi, ref_ops, moves_mode):
     c = random_moves_state(61, 4, 4, 8, 16, 128, 40)
     S, L, H = c["evicted_kv_count"].shape
     N, B = int(c["total_kv"]), 16

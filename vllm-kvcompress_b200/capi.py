@@ -276,6 +276,16 @@ def get_select_mode() -> int:
     return int(native.load_lib().kvc_get_select_mode())
 
 
+def set_moves_mode(mode: int) -> None:
+    """kvc_set_moves_mode: 0 = register-gather kernels (default), 1 = TMA-staged kernel for post-prefill
+    compaction (bit-identical results)."""
+    _check(native.load_lib().kvc_set_moves_mode(int(mode)))
+
+
+def get_moves_mode() -> int:
+    return int(native.load_lib().kvc_get_moves_mode())
+
+
 class DeviceBlockAllocator:
     """The allocator / block-state ops of include/kvc_b200.h (kvc_alloc_*) bound to one set of state
     tensors -- the same tensors the reference keeps in ParallelBlockAllocator, BlockState and

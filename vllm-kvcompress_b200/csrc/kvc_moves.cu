@@ -134,16 +134,32 @@ __device__ __forceinline__ void moves_run_head(
         mask |= (c1 | c2) ? (1u << o) : 0u;
       }
 
-      // ---- metric + position: lanes 0-15 metric, 16-31 position ----
+      // ---- metric + position: lanes 0-15 metric, 16-31 position; loaded here, stored after the gather so that
+      // the load's latency is not paid before the V loads are even issued (in-order issue) ----
+      int mp_src = src[0];
+      uint32_t mp_val = 0u;
       {
         const int o = lane & 15;
-        int s = src[0];
 #pragma unroll
-        for (int i = 1; i < 16; ++i) s = (o == i) ? src[i] : s;
-        if (s >= 0) {
-          const int64_t dslot = (int64_t)run_blk * B + o;
-          if (lane < 16) kv_metrics[dslot] = kv_metrics[s];   // reference :410
-          else           kv_position[dslot] = kv_position[s]; // reference :411
+        for (int i = 1; i < 16; ++i) mp_src = (o == i) ? src[i] : mp_src;
+        if (mp_src >= 0)
+          mp_val = (lane < 16) ? __float_as_uint(kv_metrics[mp_src]) : (uint32_t)kv_position[mp_src];
+      }
+
+      // ---- K: half-warp per token, lane j copies one 16 B chunk (reference :413-424).  Loads first: they are in
+      // flight together with the V loads below; the stores follow the gather ----
+      const int half = lane >> 4, j = lane & 15;
+      uint4 kv[8];
+      bool kp[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int s = half ? src[2 * i + 1] : src[2 * i];
+        kp[i] = s >= 0;
+        if (kp[i]) {
+          if (PEND && s == pslot)
+            kv[i] = *reinterpret_cast<const uint4*>(pk + j * 8);
+          else
+            kv[i] = ld_stream16(k_cache + (int64_t)(s >> 4) * kBlockElems + j * (B * 8) + (s & 15) * 8);
         }
       }
 
@@ -153,10 +169,31 @@ __device__ __forceinline__ void moves_run_head(
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int i = 0; i < 8; ++i) w[r][i] = 0u;
+      if (!PEND) {
+        // all 64 element loads of the run are issued before the first one is used: the warp pays one memory
+        // round trip per run, not one per source token (in-order issue stalls at the first use of a load)
+        uint32_t x[16][4];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+          const int s = src[o];
+          const bool ok = s >= 0;  // warp-uniform
+          const uint16_t* __restrict__ sp =
+              v_cache + (int64_t)((ok ? s : 0) >> 4) * kBlockElems + ((ok ? s : 0) & 15) + lane * B;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            x[o][r] = 0u;
+            if (ok) x[o][r] = sp[r * 32 * B];  // reference :426-431, element d = lane + 32 r
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < 16; ++o)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) w[r][o >> 1] |= (o & 1) ? (x[o][r] << 16) : x[o][r];
+      }
 #pragma unroll
       for (int o = 0; o < 16; ++o) {
         const int s = src[o];
-        if (s >= 0) {  // warp-uniform
+        if (PEND && s >= 0) {  // warp-uniform
           if (PEND && s == pslot) {
             consumed = true;
 #pragma unroll
@@ -176,27 +213,15 @@ __device__ __forceinline__ void moves_run_head(
         }
       }
 
-      // ---- K: half-warp per token, lane j copies one 16 B chunk (reference :413-424) ----
-      {
-        const int half = lane >> 4, j = lane & 15;
-        uint4 kv[8];
-        bool kp[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int s = half ? src[2 * i + 1] : src[2 * i];
-          kp[i] = s >= 0;
-          if (kp[i]) {
-            if (PEND && s == pslot)
-              kv[i] = *reinterpret_cast<const uint4*>(pk + j * 8);
-            else
-              kv[i] = ld_stream16(k_cache + (int64_t)(s >> 4) * kBlockElems + j * (B * 8) + (s & 15) * 8);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (kp[i])
-            st_stream16(k_cache + (int64_t)run_blk * kBlockElems + j * (B * 8) + (2 * i + half) * 8, kv[i]);
-        }
+      for (int i = 0; i < 8; ++i) {
+        if (kp[i])
+          st_stream16(k_cache + (int64_t)run_blk * kBlockElems + j * (B * 8) + (2 * i + half) * 8, kv[i]);
+      }
+      if (mp_src >= 0) {
+        const int64_t dslot = (int64_t)run_blk * B + (lane & 15);
+        if (lane < 16) kv_metrics[dslot] = __uint_as_float(mp_val);   // reference :410
+        else           kv_position[dslot] = (int)mp_val;              // reference :411
       }
 
       // ---- V write-back: whole rows when the run covers all 16 tokens ----
@@ -244,6 +269,230 @@ __global__ void __launch_bounds__(kMoveWarps * kWarp) execute_moves_b16_d128_ker
   if (g >= total_heads) return;
   moves_run_head<PEND>(k_cache, v_cache, kv_metrics, kv_position, moves, move_count, move_offsets, pend_kv,
                        pend_slot, num_seqs, num_layers, num_kv_heads, g, lane);
+}
+
+// -----------------------------------------------------------------------------
+// Post-prefill compaction (few heads, thousands of moves each): whole blocks STAGED BY TMA, lane = token.
+//
+// The register-gather kernel above pulls every V element of a source token with its own 2-byte global load
+// (2048 sector requests per run) behind a warp-uniform decode of ~1700 instructions per run, and is bound by
+// instruction latency at 16 warps per SM (ncu: 22 % warps active, 62 % of DRAM peak at CR 4).  Here the bytes
+// move through the async proxy and a warp executes ~300 instructions per run:
+//   * unit of work = a 32-move segment of a head's list; its runs (moves into one destination block) are
+//     processed two at a time: lane (h, o) owns token o of run h.  A moved token's source is the slot K4 gave
+//     it; an UNMOVED token of a partly overwritten block takes its old column from the destination block
+//     itself, so every lane copies one column from some staged block and the block leaves the SM complete;
+//   * source V blocks (and the old destination block of a partial run) are bulk-copied whole into a private ring
+//     (cp.async.bulk, 4 KB each, one mbarrier per slot; any one token needs all 128 sectors of its block
+//     anyway).  K4 emits dst ascending <-> src descending, so tokens that share a source block are neighbours,
+//     also across the two runs: the block is fetched once.  kPrSlots copies are issued by kPrSlots lanes in
+//     parallel per round;
+//   * the lane copies its column, 128 x (2-byte LDS -> 2-byte STS), into a 4 KB staging image of the destination
+//     V block; its sixteen 16-byte K chunks go global -> staging with cp.async (no registers);
+//   * the finished K and V images leave with ONE bulk store each (cp.async.bulk shared -> global, 4 KB):
+//     full-sector writes only, no partial-sector writes for L2 to fill.
+// Nobody writes a block concurrently with different bytes: a block has one owner head, a destination block one
+// run, sources are never destinations; the boundary block that holds both destinations and sources is rewritten
+// with identical bytes in its source columns.  Results are bit-identical to the register kernel.
+// -----------------------------------------------------------------------------
+constexpr int kPrWarps = 5;
+constexpr int kPrSlots = 6;
+constexpr int kPrBlockBytes = 4096;
+constexpr int kPrWarpBytes = (kPrSlots + 4) * kPrBlockBytes + 512;  // ring | V images | K images | tables + barriers
+
+__device__ __forceinline__ uint32_t mv_smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mv_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "MVWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra MVDONE_%=;\n\t"
+      "bra MVWAIT_%=;\n\t"
+      "MVDONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(kPrWarps * kWarp, 1) execute_moves_staged_kernel(
+    uint16_t* __restrict__ k_cache, uint16_t* __restrict__ v_cache, float* __restrict__ kv_metrics,
+    int* __restrict__ kv_position, const int2* __restrict__ moves, const int* __restrict__ move_count,
+    const int* __restrict__ move_offsets, int total_heads) {
+  constexpr int B = 16;
+  extern __shared__ __align__(128) unsigned char mv_smem[];
+  __shared__ int s_max_cnt;
+  const int wid = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  // longest move list of the call (fewer than 4096 heads on this path): bounds the unit enumeration below
+  if (threadIdx.x == 0) s_max_cnt = 0;
+  __syncthreads();
+  {
+    int m = 0;
+    for (int i = threadIdx.x; i < total_heads; i += kPrWarps * kWarp) m = max(m, move_count[i]);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if (lane == 0 && m > 0) atomicMax(&s_max_cnt, m);
+  }
+  __syncthreads();
+  const int max_segments = (s_max_cnt + kMovesPerSegment - 1) / kMovesPerSegment;
+
+  unsigned char* base_w = mv_smem + (size_t)wid * kPrWarpBytes;
+  unsigned char* ring = base_w;
+  unsigned char* vst = base_w + kPrSlots * kPrBlockBytes;        // [2][4096] destination V images
+  unsigned char* kst = vst + 2 * kPrBlockBytes;                  // [2][4096] destination K images
+  int* tsrc = reinterpret_cast<int*>(kst + 2 * kPrBlockBytes);   // [32] source slot of (half, offset)
+  int* tblk = tsrc + 32;                                         // [2]  destination block of each half (+2 pad)
+  int* blist = tblk + 4;                                         // [40] distinct blocks to stage, in order
+  const uint32_t bars = mv_smem_u32(blist + 40);                 // [kPrSlots] mbarriers
+  const uint32_t ring_u = mv_smem_u32(ring);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < kPrSlots; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + 8 * i), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t phases = 0;   // bit i: parity the next wait on slot i expects
+  const unsigned lt = lanemask_lt();
+  const unsigned le = lt | (1u << lane);
+  const int h = lane >> 4, o = lane & 15;
+  unsigned char* const k_bytes = reinterpret_cast<unsigned char*>(k_cache);
+  unsigned char* const v_bytes = reinterpret_cast<unsigned char*>(v_cache);
+
+  // persistent grid: units (segment, head) are dealt round-robin to the warps of the grid, segment-major so that
+  // concurrently running warps work on different heads (different regions of the cache)
+  const long long total_units = (long long)max_segments * total_heads;
+  const int W = gridDim.x * kPrWarps;
+  for (long long u = (long long)wid * gridDim.x + blockIdx.x; u < total_units; u += W) {
+    const int seg = (int)(u / total_heads);
+    const int g = (int)(u - (long long)seg * total_heads);
+    const int cnt = move_count[g];
+    const int base = seg * kMovesPerSegment;
+    if (base >= cnt) continue;
+    const int2* __restrict__ mv = moves + move_offsets[g];
+    // window of 48 moves: [base, base+32) in `a`, lookahead [base+32, base+48) in `la`
+    const bool a_ok = base + lane < cnt;
+    const int2 a = a_ok ? mv[base + lane] : make_int2(-1, -1);
+    const bool la_ok = (lane < 16) && (base + 32 + lane < cnt);
+    const int2 la = la_ok ? mv[base + 32 + lane] : make_int2(-1, -1);
+    const int a_blk = a_ok ? (a.x >> 4) : -1;
+    const int la_blk = la_ok ? (la.x >> 4) : -2;
+    int prev_blk = __shfl_up_sync(0xffffffffu, a_blk, 1);
+    if (lane == 0) prev_blk = (base > 0) ? (mv[base - 1].x >> 4) : -3;
+    const unsigned starts = __ballot_sync(0xffffffffu, a_ok && a_blk != prev_blk);
+    if (starts == 0) continue;  // every move here belongs to a run that started in the previous segment
+    // runs that START in this segment, numbered 0 .. nruns-1; the last one may continue into the lookahead
+    const int nruns = __popc(starts);
+    const int f0 = __ffs(starts) - 1;
+    const unsigned ok_a = __ballot_sync(0xffffffffu, a_ok);
+    int len2_last = 0;
+    if (ok_a == 0xffffffffu) {
+      const int last_blk = __shfl_sync(0xffffffffu, a_blk, 31);
+      const unsigned same_la = __ballot_sync(0xffffffffu, la_ok && la_blk == last_blk);
+      len2_last = (same_la == 0xffffffffu) ? 32 : __ffs(~same_la) - 1;  // la_ok only on lanes < 16 -> <= 16
+    }
+    const int rank_a = (a_ok && lane >= f0) ? __popc(starts & le) - 1 : -1000;
+    const int rank_la = (lane < len2_last) ? nruns - 1 : -1000;
+
+    for (int p = 0; 2 * p < nruns; ++p) {
+      // the previous pair's bulk stores have read the staging images
+      if (lane < 4) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      tsrc[lane] = -1;
+      if (lane < 2) tblk[lane] = -1;
+      __syncwarp();
+      {
+        const int ha = rank_a - 2 * p, hl = rank_la - 2 * p;
+        if (ha == 0 || ha == 1) { tsrc[ha * 16 + (a.x & 15)] = a.y; tblk[ha] = a.x >> 4; }
+        if (hl == 0 || hl == 1) { tsrc[hl * 16 + (la.x & 15)] = la.y; tblk[hl] = la.x >> 4; }
+      }
+      __syncwarp();
+      const int mysrc = tsrc[lane];
+      const int myrun = tblk[h];          // destination block of my half, -1 = no run
+      const bool moved = mysrc >= 0;
+      const unsigned mvmask = __ballot_sync(0xffffffffu, moved);
+      const bool partial = myrun >= 0 && ((mvmask >> (16 * h)) & 0xffffu) != 0xffffu;
+      const bool active = moved || partial;
+      const int sblk = moved ? (mysrc >> 4) : myrun;   // block my column comes from
+      const int so = moved ? (mysrc & 15) : o;
+      const unsigned pmask = __ballot_sync(0xffffffffu, partial);
+      const int part_a = (pmask & 0xffffu) ? 1 : 0, part_b = (pmask >> 16) ? 1 : 0;
+      const int nold = part_a + part_b;
+      // distinct source blocks in lane order (tokens of one source block are adjacent among the moved lanes)
+      const unsigned below = mvmask & lt;
+      const int pl = below ? 31 - __clz(below) : 0;
+      const int psb = __shfl_sync(0xffffffffu, sblk, pl);
+      const bool isnew = moved && (below == 0 || psb != sblk);
+      const unsigned newmask = __ballot_sync(0xffffffffu, isnew);
+      const int total_blocks = nold + __popc(newmask);
+      const int ord = moved ? nold + __popc(newmask & le) - 1 : (h == 0 ? 0 : part_a);
+      if (isnew || (partial && !moved)) blist[ord] = sblk;   // unmoved lanes of a half all write the same value
+      __syncwarp();
+
+      // ---- K: sixteen 16-byte chunks of my token, global -> destination image (async, no registers) ----
+      if (active) {
+        const unsigned char* ks = k_bytes + (int64_t)sblk * kPrBlockBytes + so * 16;
+        const uint32_t kd = mv_smem_u32(kst + h * kPrBlockBytes + o * 16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kd + j * 256), "l"(ks + j * 256) : "memory");
+      }
+      // ---- metric + position (reference :410-411) ----
+      float mt = 0.f;
+      int ps = 0;
+      if (moved) {
+        mt = kv_metrics[mysrc];
+        ps = kv_position[mysrc];
+      }
+      // ---- V: rounds of kPrSlots staged blocks ----
+      const int my_round = ord / kPrSlots, my_slot = ord - my_round * kPrSlots;
+      const int nrounds = (total_blocks + kPrSlots - 1) / kPrSlots;
+      for (int q = 0; q < nrounds; ++q) {
+        const int n = q * kPrSlots + lane;
+        if (lane < kPrSlots && n < total_blocks) {
+          const uint32_t bar = bars + 8 * lane;
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the slot
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kPrBlockBytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(ring_u + lane * kPrBlockBytes), "l"(v_bytes + (int64_t)blist[n] * kPrBlockBytes),
+                         "r"(kPrBlockBytes), "r"(bar) : "memory");
+        }
+        if (active && my_round == q) {
+          mv_mbar_wait(bars + 8 * my_slot, (phases >> my_slot) & 1u);
+          const uint16_t* sp = reinterpret_cast<const uint16_t*>(ring + my_slot * kPrBlockBytes) + so;
+          uint16_t* dp = reinterpret_cast<uint16_t*>(vst + h * kPrBlockBytes) + o;
+          // half 1 runs one row ahead of half 0: the two halves then hit disjoint shared-memory banks
+#pragma unroll 16
+          for (int r = 0; r < 128; ++r) {
+            const int row = (r + h) & 127;
+            dp[row * B] = sp[row * B];   // reference :426-431
+          }
+        }
+        const int used = min(kPrSlots, total_blocks - q * kPrSlots);
+        phases ^= (1u << used) - 1u;
+        __syncwarp();  // every lane is done with this round's slots
+      }
+      if (moved) {
+        const int64_t dslot = (int64_t)myrun * B + o;
+        kv_metrics[dslot] = mt;
+        kv_position[dslot] = ps;
+      }
+      // ---- the finished images leave as whole blocks ----
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> bulk store reads
+      __syncwarp();
+      if (lane < 4) {
+        const int hh = lane & 1, is_k = lane >> 1;
+        const int dblk = tblk[hh];
+        if (dblk >= 0) {
+          unsigned char* gdst = (is_k ? k_bytes : v_bytes) + (int64_t)dblk * kPrBlockBytes;
+          const uint32_t ssrc = mv_smem_u32((is_k ? kst : vst) + hh * kPrBlockBytes);
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                       ::"l"(gdst), "r"(ssrc), "r"(kPrBlockBytes) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+  }
+  if (lane < 4) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before the CTA retires
 }
 
 // decode-time compaction (many heads, most with <= 1 move, which execute_moves_light_kernel owns): a warp
@@ -440,6 +689,24 @@ __global__ void execute_moves_generic_kernel(T* __restrict__ k_cache, T* __restr
 
 using namespace kvc;
 
+// 0 = register-gather kernels for every shape (default: fastest on the B200),
+// 1 = TMA-staged kernel for post-prefill compaction (fewer than 4096 heads)
+static int g_moves_mode = -1;
+static int moves_mode() {
+  if (g_moves_mode < 0) {
+    const char* v = getenv("KVC_MOVES_MODE");
+    g_moves_mode = v ? atoi(v) : 0;
+    if (g_moves_mode < 0 || g_moves_mode > 1) g_moves_mode = 0;
+  }
+  return g_moves_mode;
+}
+extern "C" int kvc_set_moves_mode(int mode) {
+  KVC_REQUIRE(mode == 0 || mode == 1, KVC_ERR_INVALID, "moves mode must be 0 or 1, got %d", mode);
+  g_moves_mode = mode;
+  return KVC_OK;
+}
+extern "C" int kvc_get_moves_mode(void) { return moves_mode(); }
+
 static int execute_moves_impl(
     void* k_cache, void* v_cache, float* kv_metrics, int* kv_position,
     const int* cache_moves_idx, const int* cache_moves_count, const int* evicted_kv_offsets,
@@ -505,6 +772,18 @@ static int execute_moves_impl(
         execute_moves_b16_d128_chunk_kernel<false><<<cgrid, kMoveWarps * kWarp, 0, st>>>(
             kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads, nullptr, nullptr,
             0, 0, 0);
+    } else if (!pend && moves_mode() == 1) {
+      // post-prefill compaction: blocks staged by TMA bulk copies, one persistent CTA of kPrWarps warps per SM
+      const size_t smem = (size_t)kPrWarps * kPrWarpBytes;
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(execute_moves_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "execute_moves_staged smem attr: %s", cudaGetErrorString(e));
+        attr_set = true;
+      }
+      execute_moves_staged_kernel<<<sm_count(), kPrWarps * kWarp, smem, st>>>(
+          kc, vc, kv_metrics, kv_position, mv, cache_moves_count, evicted_kv_offsets, total_heads);
     } else {
       const dim3 grid((total_heads + kMoveWarps - 1) / kMoveWarps, gy);
       if (pend)
