@@ -23,7 +23,9 @@ EXT = os.path.join(PKG, "_C.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CU_SOURCES = ["kvc_capi.cu", "kvc_schedule.cu", "kvc_moves.cu", "kvc_cache.cu", "kvc_attention.cu", "kvc_select.cu", "kvc_blocks.cu", "kvc_prefill.cu", "kvc_alloc.cu"]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+# KVC_EXTRA_NVCC_FLAGS: extra compile flags for diagnostic builds (e.g. -DKVC_ATTN_TRACE for tools/attn_trace.py)
+EXTRA = os.environ.get("KVC_EXTRA_NVCC_FLAGS", "").split()
+NVCC_FLAGS = EXTRA + ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I" + INC, "-I" + CSRC]
 
 

@@ -80,7 +80,21 @@ struct AttnParams {
   // deferred move (optional, with pend_kv): pend_dst [S, H] >= 0 = slot where the token parked by the PREVIOUS
   // step now belongs (set by kvc_execute_cache_moves_deferred); applied while that block is staged
   int64_t* pend_dst;
+#ifdef KVC_ATTN_TRACE
+  unsigned long long* trace;  // [items][16] timestamps (tools/attn_trace.py; diagnostic builds only)
+#endif
 };
+
+#ifdef KVC_ATTN_TRACE
+__device__ __forceinline__ unsigned long long kvc_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define KVC_TR(i, v) do { if (p.trace != nullptr && lane == 0) p.trace[(size_t)item * 16 + (i)] = (unsigned long long)(v); } while (0)
+#else
+#define KVC_TR(i, v) do { } while (0)
+#endif
 
 template <bool BF16>
 __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2,
@@ -557,10 +571,24 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   const int g = lane >> 2, c = lane & 3;
   const int item = blockIdx.x * kConsumers + wid;
   if (item >= num_items) return;
+  KVC_TR(0, kvc_globaltimer());
+  KVC_TR(1, clock64());
   const int s = item / H, h = item - s * H;
+  // Everything the warp needs from tables that no kernel of this step's attention chain writes is requested at
+  // once, so that the warp pays one memory round trip here instead of one per dependent load later: context
+  // length, the first 32 block-table entries (lane b holds entry b: the sweep and the metric epilogue take them
+  // by shuffle instead of a dependent load per block), the step's slot for the new token, the recording bound.
+  const int* __restrict__ bt = p.block_tables + (int64_t)item * p.max_num_blocks_per_seq;
+  const int my_bt = (lane < p.max_num_blocks_per_seq) ? bt[lane] : 0;
   const int ctx = p.context_lens[item];
   // destination of a deferred move (see below); loaded with the context length so the two latencies overlap
   const int64_t pd = kMove ? p.pend_dst[item] : -1;
+  int64_t nslot_early = -1;
+  if (kWrite) nslot_early = p.slot_mapping[item];
+  const int max_pos = p.last_position[s] - p.kv_metric_buffer_len[s];
+  auto phys_of = [&](int b) -> int64_t {  // b is warp-uniform
+    return b < kWarp ? (int64_t)__shfl_sync(0xffffffffu, my_bt, b) : (int64_t)bt[b];
+  };
   const int nblk = (ctx + kB - 1) / kB;
   uint16_t* outp = reinterpret_cast<uint16_t*>(p.out) + ((int64_t)s * p.num_heads + h * Q) * kD;
   if (ctx <= 0) {
@@ -590,29 +618,29 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
       if (lane < 16) *reinterpret_cast<uint4*>(kd + lane * (kB * 8) + o * 8) = kx;
 #pragma unroll
       for (int r = 0; r < 4; ++r) vd[(lane + 32 * r) * kB + o] = vx[r];
-      asm volatile("fence.proxy.async;" ::: "memory");  // generic stores before the async-proxy read of the block
+      asm volatile("fence.proxy.async.global;" ::: "memory");  // generic stores before the async-proxy read of the block
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(patched_of(wid));
   }
   uint16_t* psw = reinterpret_cast<uint16_t*>(ring + kNUnit * kUnitBytes);
   const uint32_t full = full_of(wid), empty = empty_of(wid);
-  const int* __restrict__ bt = p.block_tables + (int64_t)item * p.max_num_blocks_per_seq;
-  const int max_pos = p.last_position[s] - p.kv_metric_buffer_len[s];
   // fused mode parks raw logits transposed, [q][token], in an L2-resident scratch row of this item;
   // v1 mode parks them in kv_metric_out itself
   float* lg0 = nullptr;
   float* lg1 = nullptr;
   constexpr bool kFusedMetrics = (MODE == kModeFused || kWrite);
   // short contexts: logits stay in this warp's shared memory and the recording rule is evaluated
-  // block by block during the sweep (bit 2b / 2b+1 of `passbits`), so the epilogue has no dependent
-  // global loads; long contexts park them in the global scratch row instead
+  // block by block during the sweep (a token that fails it gets -inf as its parked logit, i.e. contributes
+  // exactly 0), so the epilogue has no dependent global loads; long contexts park them in the global scratch
+  // row instead
   const bool smem_logits = kFusedMetrics && smem_logit_tokens > 0;
   const int lg_stride = smem_logits ? smem_logit_tokens : scratch_tokens;
-  unsigned long long passbits = 0ull;
+  float* lg_base = nullptr;
   if (kFusedMetrics) {
     float* base = smem_logits ? reinterpret_cast<float*>(ring + kNUnit * kUnitBytes + kPsBytes + 2 * kNUnit * 8 + 32)
                               : scratch + (int64_t)item * Q * scratch_tokens;
+    lg_base = base;
     lg0 = base + (2 * c) * lg_stride;  // column q = 2c (nt = 0)
     lg1 = lg0 + lg_stride;
   }
@@ -622,13 +650,15 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   // staged copy of the last block below (the TMA read of that block may race with the store).
   // pdl == 2: everything read so far (tables, context lengths, cache blocks of earlier steps) predates the
   // stream's previous kernel by the caller's declaration; the step's q / new k / new v may be its output.
+  KVC_TR(2, clock64());
   if (pdl == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
+  KVC_TR(3, clock64());
   uint4 newk = make_uint4(0, 0, 0, 0);   // lane j < 16: chunk j of the new K
   uint16_t newv[4] = {0, 0, 0, 0};       // rows d = lane + 32 r of the new V
   int new_o = -1;                        // block offset of the new token, -1 = none
   int64_t new_slot = -1;
   if (kWrite) {
-    const int64_t nslot = p.slot_mapping[item];
+    const int64_t nslot = nslot_early;
     if (nslot >= 0) {
       new_o = (int)(nslot & (kB - 1));
       const uint16_t* nk = reinterpret_cast<const uint16_t*>(p.new_k) + (int64_t)s * p.new_k_stride + h * kD;
@@ -730,7 +760,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     bool rec0 = false, rec1 = false;
     int64_t slot0 = 0, slot1 = 0;
     if (MODE == kModeV1 && p.record) {  // independent of the staged data: issued before the waits
-      const int64_t phys = bt[b];
+      const int64_t phys = phys_of(b);
       slot0 = phys * kB + g;
       slot1 = slot0 + 8;
       rec0 = tok0 < ctx && p.kv_position[slot0] <= max_pos;
@@ -738,7 +768,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
     }
     int pos0 = 0x7fffffff, pos1 = 0x7fffffff;
     if (smem_logits) {  // recording rule of this block's two tokens (loads overlap the math below)
-      const int64_t phys = bt[b];
+      const int64_t phys = phys_of(b);
       if (tok0 < ctx) pos0 = p.kv_position[phys * kB + g];
       if (tok1 < ctx) pos1 = p.kv_position[phys * kB + g + 8];
     }
@@ -844,9 +874,16 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
       }
     }
     __syncwarp();  // P buffer is rewritten next iteration
-    if (smem_logits) {
-      passbits |= (unsigned long long)(pos0 <= max_pos) << (2 * (b & 31));
-      passbits |= (unsigned long long)(pos1 <= max_pos) << (2 * (b & 31) + 1);
+    if (smem_logits) {  // recording rule (reference :124, :309): rarely fails (protected window, masked tail)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (nt * 8 + 2 * c + i < Q) {
+            float* lg = (i ? lg1 : lg0) + nt * 8 * lg_stride;
+            if (!(pos0 <= max_pos)) lg[tok0] = -INFINITY;
+            if (!(pos1 <= max_pos)) lg[tok1] = -INFINITY;
+          }
     }
     if (!last) {
 #pragma unroll
@@ -859,14 +896,17 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   };
   using T_ = std::true_type;
   using F_ = std::false_type;
+  KVC_TR(4, clock64());
   if (nblk == 1) {
     consume_k(T_{}, 0, sacc);
   } else {
     consume_k(F_{}, 0, sacc);
+    KVC_TR(5, clock64());
     for (int b = 0; b < nblk - 2; ++b) sweep_block(F_{}, F_{}, b);
     sweep_block(F_{}, T_{}, nblk - 2);
   }
   sweep_block(T_{}, F_{}, nblk - 1);
+  KVC_TR(6, clock64());
 
   // ---- output: O / (L + 1e-6); lane (g,c) holds O[d = 16 dt + g (+8)][q = 2c, 2c+1] ----
   float inv[NT][2];
@@ -888,6 +928,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
         }
       }
     }
+  KVC_TR(8, clock64());
   if (kMove && pd >= 0 && lane == 0) p.pend_dst[item] = -1;  // applied (the producer read it long ago)
   if (kWrite && new_slot >= 0) {
     // reference csrc/kvcompress_cache_kernels.cu:55-88: K chunks, V elements, metric := head bias
@@ -912,34 +953,42 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   } else if (kWrite && p.pend_slot != nullptr && lane == 0) {
     p.pend_slot[item] = -1;
   }
+  KVC_TR(9, clock64());
   if (smem_logits) {
-    // metrics[slot] += sum_q p^2 from the warp's own shared-memory logits; every lane finalises the two
-    // tokens x two columns it produced, the column sum runs over the 4 lanes of a token (c = 0..3)
+    // metrics[slot] += sum_q p^2 from the warp's own shared-memory logits, token-major: a lane finalises four
+    // consecutive tokens of all Q columns (16-byte shared-memory reads) and issues ONE 16-byte fire-and-forget
+    // reduction for them (every slot belongs to exactly one warp; red.global.add.v4.f32, sm_90+).  Tokens
+    // that fail the recording rule or lie beyond the context hold -inf logits: they add exactly 0.
     __syncwarp();
-    for (int b = 0; b < nblk; ++b) {
-      const int tok0 = b * kB + g, tok1 = tok0 + 8;
-      float a0 = 0.f, a1 = 0.f;
+    float* mi = reinterpret_cast<float*>(psw);  // the P buffer is free now: [NT*8][2] = (M, 1 / (sum + 1e-6))
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          if (nt * 8 + 2 * c + i < Q) {
-            const float* lg = (i ? lg1 : lg0) + nt * 8 * lg_stride;
-            const float p0 = __expf(lg[tok0] - m_run[nt][i]) * inv[nt][i];
-            const float p1 = __expf(lg[tok1] - m_run[nt][i]) * inv[nt][i];
-            a0 += p0 * p0;
-            a1 += p1 * p1;
-          }
+      for (int i = 0; i < 2; ++i)
+        if (g == 0) {
+          mi[(nt * 8 + 2 * c + i) * 2] = m_run[nt][i];
+          mi[(nt * 8 + 2 * c + i) * 2 + 1] = inv[nt][i];
         }
-      a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
-      a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-      if (c == 0) {
-        const int64_t phys = bt[b];
-        // every slot belongs to exactly one warp: a fire-and-forget reduction, no read-back
-        if ((passbits >> (2 * (b & 31))) & 1ull) atomicAdd(&p.metric[phys * kB + g], a0);
-        if ((passbits >> (2 * (b & 31) + 1)) & 1ull) atomicAdd(&p.metric[phys * kB + g + 8], a1);
+    __syncwarp();
+    const int ntok = nblk * kB;  // <= 32 blocks in this mode
+    for (int t0 = 0; t0 < ntok; t0 += 4 * kWarp) {
+      const int t4 = t0 + 4 * lane;
+      const bool valid = t4 < ntok;
+      const int64_t phys = __shfl_sync(0xffffffffu, my_bt, valid ? (t4 >> 4) : 0);
+      if (valid) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        bool any = false;
+        for (int q = 0; q < Q; ++q) {
+          const float4 l = *reinterpret_cast<const float4*>(lg_base + q * lg_stride + t4);
+          const float M = mi[2 * q], iv = mi[2 * q + 1];
+          const float p0 = __expf(l.x - M) * iv, p1 = __expf(l.y - M) * iv;
+          const float p2 = __expf(l.z - M) * iv, p3 = __expf(l.w - M) * iv;
+          a0 += p0 * p0; a1 += p1 * p1; a2 += p2 * p2; a3 += p3 * p3;
+          any |= (l.x != -INFINITY) | (l.y != -INFINITY) | (l.z != -INFINITY) | (l.w != -INFINITY);
+        }
+        if (any)
+          asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                       ::"l"(p.metric + phys * kB + (t4 & (kB - 1))), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
       }
     }
   } else if (kFusedMetrics || (MODE == kModeV1 && p.record)) {
@@ -1012,8 +1061,18 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
       }
     }
   }
+  KVC_TR(10, clock64());
   // inputs declared independent of the previous kernel: still order this grid's completion after it
   if (pdl == 3) asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef KVC_ATTN_TRACE
+  if (p.trace != nullptr && lane == 0) {
+    p.trace[(size_t)item * 16 + 7] = kvc_globaltimer();
+    // pack the exit clock with the SM id: clocks of different SMs are not comparable
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.trace[(size_t)item * 16 + 6] = (p.trace[(size_t)item * 16 + 6] & 0xffffffffffffull) | ((unsigned long long)smid << 48);
+  }
+#endif
 }
 
 // -----------------------------------------------------------------------------
@@ -1073,6 +1132,9 @@ __global__ void __launch_bounds__(kAttnThreads) paged_attention_reduce_kernel(At
   }
 }
 
+#ifdef KVC_ATTN_TRACE
+static unsigned long long* g_attn_trace = nullptr;
+#endif
 static int g_pdl_mode = -1;  // -1 = not set yet: KVC_ATTN_PDL from the environment, else 1
 static int attention_pdl_mode() {
   if (g_pdl_mode < 0) {
@@ -1223,6 +1285,9 @@ static int fill_params(AttnParams& p, void* out, float* metric, const void* quer
   p.new_k = nullptr; p.new_v = nullptr; p.new_k_stride = 0; p.new_v_stride = 0;
   p.slot_mapping = nullptr; p.head_bias = nullptr;
   p.pend_kv = nullptr; p.pend_slot = nullptr; p.pend_dst = nullptr;
+#ifdef KVC_ATTN_TRACE
+  p.trace = g_attn_trace;
+#endif
   return KVC_OK;
 }
 
@@ -1382,6 +1447,14 @@ extern "C" int kvc_paged_attention_fused_step_deferred(
   return dispatch_stream<kModeFusedWrite>(p, num_seqs, reinterpret_cast<float*>(workspace), padded, dtype,
                                           as_stream(stream));
 }
+
+#ifdef KVC_ATTN_TRACE
+// diagnostic builds only (tools/attn_trace.py): timestamps of every consumer warp of the NEXT launches
+extern "C" __attribute__((visibility("default"))) int kvc_debug_set_attention_trace(unsigned long long* buf) {
+  kvc::g_attn_trace = buf;
+  return 0;
+}
+#endif
 
 extern "C" int kvc_set_attention_pdl(int mode) {
   KVC_REQUIRE(mode >= 0 && mode <= 3, KVC_ERR_INVALID, "attention PDL mode must be 0, 1, 2 or 3, got %d", mode);
