@@ -697,6 +697,260 @@ def gen_block_manager():
     return cases
 
 
+def _strip_annotations(tree):
+    """remove decorators and annotations so a reference class can be compiled without its imports"""
+    for node in ast.walk(tree):
+        if isinstance(node, (ast.FunctionDef, ast.AsyncFunctionDef)):
+            node.decorator_list = []
+            node.returns = None
+            for a in node.args.args + node.args.kwonlyargs + node.args.posonlyargs:
+                a.annotation = None
+            if node.args.vararg:
+                node.args.vararg.annotation = None
+            if node.args.kwarg:
+                node.args.kwarg.annotation = None
+    return tree
+
+
+def chain_key(s_idx, l, h, pos, L, H, maxpos=1 << 12):
+    """unique id of a live KV: (sequence slot, layer, head, token position)"""
+    return ((np.asarray(s_idx, np.int64) * L + l) * H + h) * maxpos + pos
+
+
+def chain_noise(key, t):
+    """deterministic float32 in [2^-24, 0.5): the synthetic attention mass a KV receives at step t (bijective in
+    `key` for a fixed t, so no two KVs of a call tie); shared with tests/test_scheduler_chain.py"""
+    k = (np.asarray(key, np.int64) * 2654435761 + (t + 1) * 40503) % (1 << 23)
+    return ((k + 1).astype(np.float32) / np.float32(1 << 24)).astype(np.float32)
+
+
+def gen_scheduler_chain():
+    """Scheduler-chain golden: the reference's OWN CompressionScheduler (vllm/kvcompress/scheduler.py:44-575, policy
+    _schedule_seq_evictions :100-181, batch choice + orchestration _schedule_compression :184-560, interval logic
+    :565-575) driving its own BlockSpaceManagerKVC / BlockState / ParallelBlockAllocator
+    (block_manager.py, block.py) and CompressionMetrics.schedule_evictions / insert_metadata / remove_metadata
+    (metrics.py), all executed on CPU tensors from where they lie, over a multi-step scenario with four sequences
+    that use different policies (max_cache_tokens incl. a non-multiple of the block size, target_compression_rate,
+    compress_once, different protected windows), a max_kv_per_compression cap that forces the
+    iterations-since-compression ordering to matter, and compression_interval = 2.  The CUDA ops the scheduler
+    calls are supplied by the reference's Python twins (ref_schedule_t1_cache_moves, ref_execute_cache_moves) and,
+    for count_block_evictions, by the C oracle (see gen_selection_v2).  Recorded per step: the chosen sequences,
+    their block budgets, eviction / freed-block counts, the move lists, and the block state afterwards.
+    Because the calls are multi-sequence, the outputs include the reference's `evicted_infs` offset behaviour
+    (metrics.py:718): tests reproduce it through _custom_ops.reference_v2_budgets."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from oracle import kvc_oracle as O
+    ops = _load_reference_custom_ops()
+
+    class _Bench:
+        def wrap(self, *a, **k):
+            return lambda f: f
+        def start_range(self, *a, **k):
+            pass
+        end_range = start_range
+
+    class _Ckpt:
+        do_checkpoint = False
+        def checkpoint(self, *a, **k):
+            pass
+
+    from typing import Any, List, Tuple, Dict, NamedTuple, Union
+    import math
+    from dataclasses import dataclass
+    base_ns = {"torch": torch, "np": np, "math": math, "Any": Any, "List": List, "Tuple": Tuple, "Dict": Dict,
+               "Optional": Optional, "NamedTuple": NamedTuple, "Union": Union, "Device": object,
+               "CHECKPOINTER": _Ckpt(), "BENCHMARKER": _Bench(), "dataclass": dataclass, "MAX_INT": MAX_INT}
+    saved = torch.cuda.memory_allocated
+    torch.cuda.memory_allocated = lambda *a, **k: 0
+    # ---- block.py (whole file) ----
+    src = open(os.path.join(REF, "vllm", "kvcompress", "block.py")).read().replace('"cuda:0"', '"cpu"')
+    tree = ast.parse(src)
+    body = [n for n in tree.body if not isinstance(n, (ast.Import, ast.ImportFrom))]
+    ns = dict(base_ns)
+    exec(compile(ast.Module(body=body, type_ignores=[]), "block.py", "exec"), ns)
+    BlockState = ns["BlockState"]
+    # ---- block_manager.py: allocator + the manager class (base class and annotations dropped) ----
+    msrc = open(os.path.join(REF, "vllm", "kvcompress", "block_manager.py")).read().replace('"cuda:0"', '"cpu"')
+    mtree = _strip_annotations(ast.parse(msrc))
+    classes = {n.name: n for n in mtree.body if isinstance(n, ast.ClassDef)}
+    mns = dict(ns, tqdm=lambda it, **k: it, FreedBlockCounts=dict, BlockAllocatorBase=object, BlockSpaceManager=object,
+               ABC=object, abstractmethod=lambda f: f)
+    exec(compile(ast.Module(body=[classes["BlockTableView"], classes["ParallelBlockAllocator"],
+                                  classes["BlockSpaceManagerKVC"]], type_ignores=[]), "block_manager.py", "exec"), mns)
+    Allocator, Manager = mns["ParallelBlockAllocator"], mns["BlockSpaceManagerKVC"]
+    # ---- metrics.py: the methods the scheduler path touches, bound to a stub ----
+    def count_block_evictions(evicted_block_count, evicted_logical_indices, evicted_kv_offsets,
+                              hanging_token_count, block_size, null_value, evicted_blocks_per_seq=None):
+        cnt = np.zeros(tuple(evicted_block_count.shape), np.int32)
+        logical = evicted_logical_indices.numpy()
+        assert logical.dtype == np.int32 and logical.flags["C_CONTIGUOUS"]
+        O.count_block_evictions(cnt, logical, evicted_kv_offsets.numpy(), hanging_token_count.numpy(),
+                                block_size, null_value)
+        evicted_block_count.copy_(torch.from_numpy(cnt))
+
+    mtree2 = ast.parse(open(os.path.join(REF, "vllm", "kvcompress", "metrics.py")).read())
+    hb_cls = [n for n in mtree2.body if isinstance(n, ast.ClassDef) and n.name == "KVHeadBias"][0]
+    hns = {"torch": torch, "dataclass": dataclass}
+    exec(compile(ast.Module(body=[hb_cls], type_ignores=[]), "metrics.py", "exec"), hns)
+    KVHeadBias = hns["KVHeadBias"]
+    schedule_evictions, insert_metadata, remove_metadata = _load_reference_functions(
+        os.path.join(REF, "vllm", "kvcompress", "metrics.py"),
+        ["schedule_evictions", "insert_metadata", "remove_metadata"], class_name="CompressionMetrics",
+        extra_ns={"count_block_evictions": count_block_evictions, "MAX_INT": MAX_INT, "CHECKPOINTER": _Ckpt(),
+                  "BENCHMARKER": _Bench(), "np": np, "BlockMetadata": ns["BlockMetadata"]})
+    # ---- scheduler.py (whole file minus imports) ----
+    def schedule_cache_moves(out_idx, out_cnt, logical, kv_count, offsets, block_tables, context_lens, block_size):
+        out_idx.fill_(0)                                           # vllm/_custom_ops.py:1168
+        quiet(ops.ref_schedule_t1_cache_moves, out_idx, out_cnt, logical.contiguous(), kv_count.contiguous(),
+              offsets.contiguous(), block_tables.contiguous(), context_lens.contiguous(), block_size)
+
+    ssrc = open(os.path.join(REF, "vllm", "kvcompress", "scheduler.py")).read()
+    stree = _strip_annotations(ast.parse(ssrc))
+    sbody = [n for n in stree.body if not isinstance(n, (ast.Import, ast.ImportFrom))]
+    sns = dict(base_ns, schedule_cache_moves=schedule_cache_moves, schedule_cache_evictions=None,
+               FreedBlockCounts=dict, deepcopy=None)
+    exec(compile(ast.Module(body=sbody, type_ignores=[]), "scheduler.py", "exec"), sns)
+    Scheduler = sns["CompressionScheduler"]
+
+    # ---- scenario ----
+    L, H, B, MS, MB, NB, D, x = 2, 4, 16, 6, 24, 1400, 4, 2
+    STEPS = 24
+    cfg = types.SimpleNamespace(control_layers=None, max_kv_per_compression=5200, num_layers=L, num_kv_heads=H,
+                                even_layer_evict=False, compression_interval=2, new_token_limit=-1)
+    seq_specs = [   # seq_id, prompt_len, target_compression_rate, max_cache_tokens, protected_window, compress_once
+        (0, 200, 1.0, 64, 16, False),
+        (1, 150, 0.5, -1, 32, False),
+        (2, 90, 1.0, 50, 16, True),
+        (3, 260, 1.0, 128, 32, False),
+    ]
+    bs = BlockState(B, L, H, MS, MB, 0, False)
+    bs.block_tables.fill_(-1)
+    km = types.SimpleNamespace(
+        seq_index_by_block=torch.full((NB,), -1, dtype=torch.int), logical_block_num_by_block=torch.zeros(NB, dtype=torch.int),
+        layer_index_by_block=torch.zeros(NB, dtype=torch.int), head_index_by_block=torch.zeros(NB, dtype=torch.int),
+        token_positions=torch.full((NB, B), -1, dtype=torch.int), metrics=torch.zeros((NB, B), dtype=torch.float32),
+        block_size=B, num_layers=L, num_kv_heads=H, device="cpu", use_average=False,
+        kv_metric_head_bias=KVHeadBias(torch.zeros((L, H, 1)), torch.tensor([0], dtype=torch.int32)),
+        kv_metric_bias_weight=0.0, num_sinks=0)
+    km.insert_metadata = lambda md: insert_metadata(km, md)
+    km.remove_metadata = lambda blocks: remove_metadata(km, blocks)
+    km.schedule_evictions = lambda *a, **k: schedule_evictions(km, *a, **k)
+    km.checkpoint = lambda: None
+    mgr = object.__new__(Manager)
+    mgr.block_size, mgr.num_layers, mgr.num_kv_heads, mgr.device = B, L, H, "cpu"
+    mgr.gpu_allocator = Allocator(NB, "cpu")
+    mgr.block_state, mgr.kv_metrics = bs, km
+    mgr.free_batch_slots, mgr.batch_slot_mapping = set(range(MS)), {}
+    mgr.checkpoint = lambda: None
+    sched = Scheduler(cfg, mgr, km)
+
+    class _Seq:
+        pass
+
+    seqs, params = [], []
+    for sid, n, rate, mct, prot, once in seq_specs:
+        quiet(mgr._add_sequence, sid, n)
+        ln = [n]
+        seq = _Seq()                      # hashable: scheduler.py:220 uses the object itself as a dict key
+        seq.seq_id, seq.compressed, seq._len = sid, False, ln
+        seq.data = types.SimpleNamespace(get_len=lambda ln=ln: ln[0])
+        seqs.append(seq)
+        params.append(types.SimpleNamespace(target_compression_rate=rate, max_cache_tokens=mct,
+                                            protected_window_size=prot, compress_once=once))
+    k_cache = torch.zeros((NB, D // x, B, x), dtype=torch.float16)
+    v_cache = torch.zeros((NB, D, B), dtype=torch.float16)
+
+    def live_slots():
+        """(slot ids, keys) of every live KV, through the block tables"""
+        out_s, out_k = [], []
+        for seq in seqs:
+            s_idx = mgr.batch_slot_mapping[seq.seq_id]
+            for l in range(L):
+                for h in range(H):
+                    n = int(bs.context_lens[l, s_idx, h])
+                    idx = np.arange(n)
+                    slots = bs.block_tables[l, s_idx, h, idx // B].numpy().astype(np.int64) * B + idx % B
+                    pos = km.token_positions.view(-1).numpy()[slots]
+                    out_s.append(slots)
+                    out_k.append(chain_key(s_idx, l, h, pos, L, H))
+        return np.concatenate(out_s), np.concatenate(out_k)
+
+    def write_payload(slots, keys):
+        """K / V payload of a KV = its key, so that physical moves are checkable (fp16-exact small ints)"""
+        kf, vf = k_cache.view(-1).numpy(), v_cache.numpy()
+        blk, off = slots // B, slots % B
+        for j in range(D // x):
+            for e in range(x):
+                k_cache.numpy()[blk, j, off, e] = ((keys >> (3 * (j * x + e))) & 7).astype(np.float16)
+        for d in range(D):
+            vf[blk, d, off] = ((keys >> (3 * d + 1)) & 7).astype(np.float16)
+
+    slots, keys = live_slots()
+    km.metrics.view(-1).numpy()[slots] = 0.5 + chain_noise(keys, -1)      # prefill metrics: distinct values
+    write_payload(slots, keys)
+
+    steps = []
+    init = dict(block_tables=bs.block_tables.numpy().copy(), context_lens=bs.context_lens.numpy().copy(),
+                free_mask=mgr.gpu_allocator.free_mask.numpy().copy(), metrics=km.metrics.numpy().copy(),
+                token_positions=km.token_positions.numpy().copy(), k_cache=k_cache.numpy().copy(),
+                v_cache=v_cache.numpy().copy(),
+                seq_index_by_block=km.seq_index_by_block.numpy().copy(),
+                layer_index_by_block=km.layer_index_by_block.numpy().copy(),
+                head_index_by_block=km.head_index_by_block.numpy().copy(),
+                logical_block_num_by_block=km.logical_block_num_by_block.numpy().copy())
+    for t in range(STEPS):
+        out = quiet(sched.schedule_compression, seqs, params)
+        rec = dict(compressed=0)
+        if out is not None:
+            ids = sorted(out.freed_block_count.keys(), key=lambda sid: mgr.batch_slot_mapping[sid])
+            mv = out.cache_moves
+            cnt = mv.count.numpy().copy()
+            offs = mv.offsets.numpy().copy()
+            quiet(ops.ref_execute_cache_moves, k_cache.view(torch.int16), v_cache.view(torch.int16), km.metrics,
+                  km.token_positions, mv.index, mv.count, mv.offsets, 1, 1)
+            flat = [mv.index.numpy()[o:o + c] for o, c in zip(offs.reshape(-1), cnt.reshape(-1))]
+            rec = dict(compressed=1, seq_ids=np.array(ids, np.int32),
+                       slot_indices=np.array([mgr.batch_slot_mapping[i] for i in ids], np.int32),
+                       freed_block_count=np.stack([out.freed_block_count[i].numpy() for i in ids]).astype(np.int32),
+                       moves_count=cnt.astype(np.int32), moves_offsets=offs.astype(np.int32),
+                       moves=(np.concatenate(flat) if flat else np.zeros((0, 2))).astype(np.int32))
+        # one decode token per sequence (block_manager.py:269-294), then the step's synthetic attention mass
+        for seq in seqs:
+            seq._len[0] += 1
+        quiet(mgr._append_to_sequence_batch, seqs)
+        slots, keys = live_slots()
+        newest = np.zeros(slots.shape[0], bool)
+        p = 0
+        for seq in seqs:
+            s_idx = mgr.batch_slot_mapping[seq.seq_id]
+            for l in range(L):
+                for h in range(H):
+                    n = int(bs.context_lens[l, s_idx, h])
+                    newest[p + n - 1] = True
+                    p += n
+        km.metrics.view(-1).numpy()[slots[newest]] = 0.0            # kvcompress_reshape_and_cache: metric := head bias
+        write_payload(slots[newest], keys[newest])
+        km.metrics.view(-1).numpy()[slots] += chain_noise(keys, t)   # aggregate_decode
+        rec.update(block_tables=bs.block_tables.numpy().copy(), context_lens=bs.context_lens.numpy().copy(),
+                   free_mask=mgr.gpu_allocator.free_mask.numpy().copy(), metrics=km.metrics.numpy().copy(),
+                   token_positions=km.token_positions.numpy().copy(), k_cache=k_cache.numpy().copy(),
+                   v_cache=v_cache.numpy().copy(), seq_lens=np.array([s._len[0] for s in seqs], np.int32))
+        steps.append(rec)
+    torch.cuda.memory_allocated = saved
+    flat = dict(L=L, H=H, B=B, MS=MS, MB=MB, NB=NB, D=D, x=x, num_steps=STEPS,
+                max_kv_per_compression=cfg.max_kv_per_compression, compression_interval=cfg.compression_interval,
+                seq_specs=np.array([[a, b, int(c * 1000), d, e, int(f)] for a, b, c, d, e, f in seq_specs], np.int32))
+    for k, v in init.items():
+        flat[f"init_{k}"] = v
+    ncomp = 0
+    for i, st in enumerate(steps):
+        ncomp += st["compressed"]
+        for k, v in st.items():
+            flat[f"s{i:03d}_{k}"] = np.asarray(v)
+    assert ncomp >= 6, ncomp
+    return {"chain": flat}
+
+
 def save(name, cases):
     flat = {}
     for cname, d in cases.items():
@@ -709,7 +963,8 @@ def save(name, cases):
 
 def main():
     """python tests/golden/make_golden.py [name ...] -- regenerate all, or only the named files
-    (evictions count_blocks moves attention cache_write selection_v2 block_manager prefill_metrics)."""
+    (evictions count_blocks moves attention cache_write selection_v2 block_manager prefill_metrics
+    scheduler_chain)."""
     want = set(sys.argv[1:])
     on = lambda n: not want or n in want
     ops = _load_reference_custom_ops() if (not want or want & {"evictions", "count_blocks", "moves"}) else None
@@ -729,6 +984,8 @@ def main():
         save("block_manager.npz", gen_block_manager())
     if on("prefill_metrics"):
         save("prefill_metrics.npz", gen_prefill_metrics())
+    if on("scheduler_chain"):
+        save("scheduler_chain.npz", gen_scheduler_chain())
 
 
 if __name__ == "__main__":
