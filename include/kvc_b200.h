@@ -403,7 +403,12 @@ KVC_API int kvc_get_select_mode(void);
 KVC_API int kvc_set_moves_mode(int mode);
 KVC_API int kvc_get_moves_mode(void);
 
+/* Workspace of kvc_select_evictions[_ex]: _workspace_bytes_ex is exact for a call's shape (contexts of more
+ * than 512 slots per head take the sort-free radix path, which stores one 4-byte key per slot and 4 x 256 sums
+ * per sequence); _workspace_bytes is a shape-agnostic upper bound (up to 1024 sequences per call). */
 KVC_API size_t kvc_select_evictions_workspace_bytes(int64_t max_evicted_kv, int block_size);
+KVC_API size_t kvc_select_evictions_workspace_bytes_ex(int64_t max_evicted_kv, int block_size, int num_seqs,
+                                                       int max_num_blocks_per_seq);
 
 KVC_API int kvc_select_evictions(
     int* evicted_logical_indices, int* evicted_kv_count, int* evicted_block_count,

@@ -717,6 +717,42 @@ def test_select_evictions_equals_reference_chain(capi, O, cfg, select_mode):
 SELV2 = load_cases("selection_v2.npz")
 
 
+@pytest.mark.parametrize("quantize", [0, 8, 3])
+@pytest.mark.parametrize("cfg", [(91, 3, 2, 4, 16, 120, 32), (92, 2, 3, 2, 16, 400, 16), (93, 4, 1, 3, 4, 300, 5)])
+def test_select_evictions_long_context_radix_equals_sort(capi, cfg, quantize):
+    """Long contexts: the sort-free radix path (default) against the CTA-per-head sort path (select mode 1) on the
+    same inputs, bit for bit, over budgets of 0 / small / typical / more than exists, with metrics quantised to a
+    handful of values so that the tie rules (completion keys by (key, head, block), slots by (key, logical
+    index)) decide almost every grant."""
+    from vllm_kvcompress_b200 import workload as W
+    seed, S, L, H, B, max_blocks, prot = cfg
+    st, ctx, last, protected, _ = selection_case(seed, S, L, H, B, max_blocks, prot, 0.5)
+    if quantize:
+        st.kv_metrics = (st.kv_metrics * quantize).floor() / quantize
+    hanging = W.hanging_token_counts(ctx, B).transpose(0, 1).contiguous()
+    offs = W.evicted_kv_offsets(ctx, B)
+    nblk = (ctx + B - 1) // B
+    N = int(nblk.sum()) * B
+    total = nblk.sum(dim=(0, 2))
+    for frac in (0.0, 0.02, 0.6, 0.97, 1.5):
+        budgets = (total.float() * frac).to(torch.int32)
+        budgets[0] = int(total[0] * (1.0 - frac)) if frac <= 1 else budgets[0]   # sequences with different budgets
+        outs = []
+        for mode in (1, 0):
+            capi.set_select_mode(mode)
+            logical = torch.full((N,), -5, dtype=torch.int32, device="cuda")
+            kvc = torch.full((S, L, H), -5, dtype=torch.int32, device="cuda")
+            blk = torch.full((S, L, H), -5, dtype=torch.int32, device="cuda")
+            capi.select_evictions(logical, kvc, blk, cu(st.kv_metrics), cu(st.kv_position), cu(st.block_tables),
+                                  cu(ctx), cu(hanging), cu(offs), cu(budgets), cu(last), cu(protected), B, MAX_INT)
+            torch.cuda.synchronize()
+            outs.append((logical.cpu(), kvc.cpu(), blk.cpu()))
+        capi.set_select_mode(0)
+        for a, b in zip(*outs):
+            assert torch.equal(a, b), (cfg, quantize, frac)
+        assert int(outs[0][2].sum()) == int(torch.minimum(budgets, outs[0][2].sum(dim=(1, 2))).sum())
+
+
 @pytest.mark.parametrize("name", sorted(SELV2))
 def test_select_evictions_v2_golden(capi, name, select_mode):
     """bit-exact against CompressionMetrics.schedule_evictions (metrics.py:441-847) run on CPU,

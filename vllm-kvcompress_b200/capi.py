@@ -200,10 +200,11 @@ def select_evictions(evicted_logical_indices, evicted_kv_count, evicted_block_co
                      null_eviction_index, head_bias=None, position_bins=None, bias_weight=0.0,
                      use_average=False, num_sinks=0):
     lib = native.load_lib()
-    lib.kvc_select_evictions_workspace_bytes.restype = ctypes.c_size_t
+    lib.kvc_select_evictions_workspace_bytes_ex.restype = ctypes.c_size_t
     S, L, H = evicted_kv_count.shape
     max_kv = evicted_logical_indices.numel()
-    nbytes = lib.kvc_select_evictions_workspace_bytes(ctypes.c_int64(max_kv), block_size)
+    nbytes = lib.kvc_select_evictions_workspace_bytes_ex(ctypes.c_int64(max_kv), block_size, S,
+                                                         block_tables.shape[-1])
     ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=evicted_kv_count.device)
     assert kv_metrics.dtype == torch.float32 and kv_metrics.is_contiguous()
     ints = [kv_position, block_tables, context_lens, hanging_token_count, evicted_kv_offsets,

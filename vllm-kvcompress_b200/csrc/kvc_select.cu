@@ -472,6 +472,340 @@ __global__ void __launch_bounds__(128) select_emit_cta_kernel(SelectParams p) {
   for (int i = cnt + t; i < nblk * p.B; i += 128) out[i] = p.null_index;
 }
 
+// =====================================================================================================
+// Long contexts (post-prefill compression: a few sequences, thousands of slots per head) WITHOUT a sort.
+// Only the number of blocks a head completes matters: with R = #candidate keys of the head <= x, the head has
+// f(R) = (R >= r0 ? (R - r0) / B + 1 : 0) completion keys <= x (its k-th block completes at sorted rank
+// r0 - 1 + k B).  The per-sequence threshold K = the E-th smallest completion key is therefore the smallest x with
+// F(x) = sum over the sequence's heads of f(R_head(x)) >= E, found by a 4 x 8-bit radix descent in which every
+// head only HISTOGRAMS its keys: O(n) reads per pass instead of an O(n log^2 n) bitonic sort of 8192 keys per head.
+//   radix_pass<0>   CTA per head: keys from metrics / positions through the block table (the one DRAM pass),
+//                   written to the workspace (4 B per slot, L2 resident: 18 MB at 3 x 6000-token prompts);
+//                   digit histogram -> inclusive scan -> f(base + cum[d]) added into Fsum[pass][seq][d]
+//   radix_pass<1-3> the same on the stored keys; the digit chosen by the previous pass is re-derived by every CTA
+//                   from Fsum (1 KB) -- no host step, no extra launch
+//   radix_count     per head: #keys < K and #keys == K  -> grants (ties at K in head order, as the sort path)
+//   radix_grant     CTA per sequence: exclusive scan of the tie counts over the heads
+//   radix_emit      CTA per head: the head's cnt-th smallest key by a radix select over its keys in shared memory,
+//                   then the ordered emission of select_emit_cta_kernel
+// Same keys, same tie rules (completion keys by (key, head, block), slots by (key, logical index)): results are
+// bit-identical to the sort path (tests run both).
+// =====================================================================================================
+struct RadixWs {
+  unsigned* keys;   // [N] orderable key per slot of every head segment (offsets[g] + i)
+  int* fsum;        // [4][S][256]
+};
+
+__device__ __forceinline__ int completions(int R, int r0, int B) { return (r0 >= 1 && R >= r0) ? (R - r0) / B + 1 : 0; }
+
+// smallest digit d with F[d] >= E in fsum row (256 ints), or 256 if none; every thread of a 256-thread CTA calls it
+__device__ __forceinline__ int pick_digit(const int* __restrict__ row, int E, int* s_tmp) {
+  const int t = threadIdx.x;
+  if (t == 0) *s_tmp = 256;
+  __syncthreads();
+  if (row[t] >= E) atomicMin(s_tmp, t);
+  __syncthreads();
+  const int d = *s_tmp;
+  __syncthreads();
+  return d;
+}
+
+// state after `PASS` digits: prefix (high bits decided so far) or "all" when even the largest key does not reach E
+__device__ __forceinline__ bool radix_state(const RadixWs& w, int S, int s, int E, int npass, unsigned& prefix,
+                                            int* s_tmp) {
+  prefix = 0;
+  for (int q = 0; q < npass; ++q) {
+    const int d = pick_digit(w.fsum + ((size_t)q * S + s) * 256, E, s_tmp);
+    if (d >= 256) return false;  // fewer than E finite completion keys (can only happen at q == 0)
+    prefix |= (unsigned)d << (24 - 8 * q);
+  }
+  return true;
+}
+
+__device__ __forceinline__ void hist_add(int* hist, unsigned digit) { atomicAdd(&hist[digit], 1); }
+
+// 256-thread CTA: the bin b with cum[b-1] < need <= cum[b] (inclusive prefix sums of hist) and need - cum[b-1];
+// parallel replacement of a serial walk over the bins.  Returns through shared memory.
+__device__ __forceinline__ void pick_bin(const int* hist, int need, int* s_w, unsigned* s_bin, int* s_need) {
+  const int t = threadIdx.x, lane = t % kWarp, wid = t / kWarp;
+  int v = hist[t];
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += u;
+  }
+  if (lane == 31) s_w[wid] = v;
+  if (t == 0) { *s_bin = 255u; *s_need = 1; }
+  __syncthreads();
+  for (int q = 0; q < wid; ++q) v += s_w[q];
+  const int before = v - hist[t];
+  if (before < need && need <= v) { *s_bin = (unsigned)t; *s_need = need - before; }
+  __syncthreads();
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256) select_radix_pass_kernel(SelectParams p, RadixWs w) {
+  __shared__ int hist[256];
+  __shared__ int s_w[8];
+  __shared__ int s_tmp, s_base;
+  const int t = threadIdx.x, lane = t % kWarp, wid = t / kWarp;
+  const int g = blockIdx.x;
+  const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
+  const int E = p.budgets[s];
+  if (E <= 0) return;  // CTA-uniform
+  const int lsh = (l * p.S + s) * p.H + h;
+  const int n = p.context_lens[lsh];
+  const int off = p.offsets[g];
+  const int r0 = p.hanging[g];
+  unsigned prefix = 0;
+  if (PASS > 0 && !radix_state(w, p.S, s, E, PASS, prefix, &s_tmp)) return;
+  constexpr int shift = 24 - 8 * PASS;
+  const unsigned hi_mask = PASS == 0 ? 0u : ~((1u << (shift + 8)) - 1u);
+  hist[t] = 0;
+  if (t == 0) s_base = 0;
+  __syncthreads();
+  unsigned* __restrict__ keys = w.keys + off;
+  int base = 0;  // keys below the prefix range
+  if (PASS == 0) {
+    const int last_pos = p.last_position[s];
+    const int max_pos = last_pos - p.protected_window[s];
+    const int* __restrict__ bt = p.block_tables + (int64_t)lsh * p.MB;
+    // four independent table -> metric / position chains per thread: the gather is bound by the bytes in flight
+    for (int i0 = t; i0 < n; i0 += 4 * 256) {
+      int blk[4];
+      float mm[4];
+      int qq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        blk[u] = (i < n) ? bt[i / p.B] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        const int64_t slot = (int64_t)blk[u] * p.B + i % p.B;
+        mm[u] = (i < n) ? p.kv_metrics[slot] : 0.f;
+        qq[u] = (i < n) ? p.kv_position[slot] : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 256;
+        if (i < n) {
+          const unsigned k = slot_key(p, mm[u], qq[u], max_pos, last_pos, l, h);
+          keys[i] = k;
+          if (k != kInfKey) hist_add(hist, k >> 24);
+        }
+      }
+    }
+  } else {
+    auto one = [&](unsigned k) {
+      if (k == kInfKey) return;
+      if ((k & hi_mask) == prefix) hist_add(hist, (k >> shift) & 255u);
+      else if (k < prefix) ++base;
+    };
+    if ((off & 3) == 0) {  // 16-byte key loads (segments start at multiples of the block size)
+      const uint4* __restrict__ k4 = reinterpret_cast<const uint4*>(keys);
+      const int n4 = n >> 2;
+      for (int i = t; i < n4; i += 256) {
+        const uint4 v = k4[i];
+        one(v.x); one(v.y); one(v.z); one(v.w);
+      }
+      for (int i = (n4 << 2) + t; i < n; i += 256) one(keys[i]);
+    } else {
+      for (int i = t; i < n; i += 256) one(keys[i]);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) base += __shfl_xor_sync(0xffffffffu, base, d);
+    if (lane == 0 && base) atomicAdd(&s_base, base);
+  }
+  __syncthreads();
+  // inclusive scan of the 256 bins
+  int v = hist[t];
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += u;
+  }
+  if (lane == 31) s_w[wid] = v;
+  __syncthreads();
+  for (int q = 0; q < wid; ++q) v += s_w[q];
+  const int c = completions(s_base + v, r0, p.B);
+  if (c) atomicAdd(w.fsum + ((size_t)PASS * p.S + s) * 256 + t, c);
+}
+
+// per head: blocks completed by keys < K (-> evicted_block_count) and the extra ones completed by keys == K
+// (-> evicted_kv_count), K = inf: every finite key
+__global__ void __launch_bounds__(256) select_radix_count_kernel(SelectParams p, RadixWs w) {
+  __shared__ int s_tmp, s_less, s_eq;
+  const int t = threadIdx.x, lane = t % kWarp;
+  const int g = blockIdx.x;
+  const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
+  const int E = p.budgets[s];
+  if (E <= 0) {
+    if (t == 0) { p.evicted_block_count[g] = 0; p.evicted_kv_count[g] = 0; }
+    return;
+  }
+  unsigned K = 0;
+  const bool found = radix_state(w, p.S, s, E, 4, K, &s_tmp);
+  const int n = p.context_lens[(l * p.S + s) * p.H + h];
+  const unsigned* __restrict__ keys = w.keys + p.offsets[g];
+  if (t == 0) s_less = s_eq = 0;
+  __syncthreads();
+  int less = 0, eq = 0;
+  auto one = [&](unsigned k) {
+    if (k == kInfKey) return;
+    if (!found || k < K) ++less;
+    else if (k == K) ++eq;
+  };
+  if ((p.offsets[g] & 3) == 0) {
+    const uint4* __restrict__ k4 = reinterpret_cast<const uint4*>(keys);
+    const int n4 = n >> 2;
+    for (int i = t; i < n4; i += 256) {
+      const uint4 v = k4[i];
+      one(v.x); one(v.y); one(v.z); one(v.w);
+    }
+    for (int i = (n4 << 2) + t; i < n; i += 256) one(keys[i]);
+  } else {
+    for (int i = t; i < n; i += 256) one(keys[i]);
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    less += __shfl_xor_sync(0xffffffffu, less, d);
+    eq += __shfl_xor_sync(0xffffffffu, eq, d);
+  }
+  if (lane == 0) {
+    if (less) atomicAdd(&s_less, less);
+    if (eq) atomicAdd(&s_eq, eq);
+  }
+  __syncthreads();
+  if (t == 0) {
+    const int r0 = p.hanging[g];
+    const int c_less = completions(s_less, r0, p.B);
+    p.evicted_block_count[g] = c_less;
+    p.evicted_kv_count[g] = completions(s_less + s_eq, r0, p.B) - c_less;  // completion keys == K
+  }
+}
+
+// one CTA per sequence: grants at K go to the heads in order (same rule as select_threshold_kernel)
+__global__ void __launch_bounds__(256) select_radix_grant_kernel(SelectParams p) {
+  __shared__ int s_scan[256];
+  __shared__ int s_carry, s_lesssum;
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const int LH = p.L * p.H;
+  const int g0 = s * LH;
+  const int E = p.budgets[s];
+  if (E <= 0) return;  // counts already zeroed
+  if (tid == 0) s_carry = s_lesssum = 0;
+  __syncthreads();
+  int local = 0;
+  for (int hd = tid; hd < LH; hd += 256) local += p.evicted_block_count[g0 + hd];
+  if (local) atomicAdd(&s_lesssum, local);
+  __syncthreads();
+  const int need = E - s_lesssum;  // grants left for completion keys == K (<= 0: K was inf, no ties exist)
+  for (int h0 = 0; h0 < LH; h0 += 256) {
+    const int hd = h0 + tid;
+    const int eq = (hd < LH) ? p.evicted_kv_count[g0 + hd] : 0;
+    s_scan[tid] = eq;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {
+      const int v = (tid >= d) ? s_scan[tid - d] : 0;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    const int eq_before = s_carry + s_scan[tid] - eq;
+    if (hd < LH) {
+      const int g = g0 + hd;
+      const int k = p.evicted_block_count[g] + max(0, min(eq, need - eq_before));
+      p.evicted_block_count[g] = k;
+      p.evicted_kv_count[g] = (k > 0) ? (k - 1) * p.B + p.hanging[g] : 0;  // metrics.py:788-792
+    }
+    __syncthreads();
+    if (tid == 255) s_carry += s_scan[255];
+    __syncthreads();
+  }
+}
+
+// CTA per head: T = the head's cnt-th smallest key (radix select over the keys staged in shared memory), then
+// the ordered emission of select_emit_cta_kernel
+__global__ void __launch_bounds__(256) select_radix_emit_kernel(SelectParams p, RadixWs w) {
+  extern __shared__ __align__(16) unsigned skeys[];
+  __shared__ int hist[256];
+  __shared__ int s_less, s_w[8], s_w2[8];
+  __shared__ unsigned s_prefix;
+  __shared__ int s_need;
+  const int t = threadIdx.x, lane = t % kWarp, wid = t / kWarp;
+  const int g = blockIdx.x;
+  const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
+  const int n = p.context_lens[(l * p.S + s) * p.H + h];
+  const int nblk = (n + p.B - 1) / p.B;
+  const int off = p.offsets[g];
+  const int cnt = p.evicted_kv_count[g];
+  int* __restrict__ out = p.evicted_logical_indices + off;
+  if (cnt > 0) {  // CTA-uniform
+    const unsigned* __restrict__ keys = w.keys + off;
+    if ((off & 3) == 0) {
+      const uint4* __restrict__ k4 = reinterpret_cast<const uint4*>(keys);
+      const int n4 = n >> 2;
+      for (int i = t; i < n4; i += 256) reinterpret_cast<uint4*>(skeys)[i] = k4[i];
+      for (int i = (n4 << 2) + t; i < n; i += 256) skeys[i] = keys[i];
+    } else {
+      for (int i = t; i < n; i += 256) skeys[i] = keys[i];
+    }
+    __syncthreads();
+    unsigned prefix = 0, mask = 0;
+    int need = cnt;  // rank (1-based) among the keys that match the prefix
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      hist[t] = 0;
+      __syncthreads();
+      for (int i = t; i < n; i += 256) {
+        const unsigned k = skeys[i];
+        if ((k & mask) == prefix) hist_add(hist, (k >> shift) & 255u);
+      }
+      __syncthreads();
+      pick_bin(hist, need, s_w, &s_prefix, &s_need);
+      prefix |= s_prefix << shift;
+      need = s_need;
+      mask |= 255u << shift;
+      __syncthreads();
+    }
+    const unsigned T = prefix;  // cnt-th smallest key; `need` of the keys == T are evicted, in logical order
+    const int allowed = need;
+    int eq_base = 0, written = 0;
+    for (int i0 = 0; i0 < n; i0 += 256) {
+      const int i = i0 + t;
+      const unsigned k = (i < n) ? skeys[i] : kInfKey;
+      const bool less = (i < n) && k < T, eq = (i < n) && (k == T);
+      const unsigned em = __ballot_sync(0xffffffffu, eq);
+      if (lane == 0) s_w[wid] = __popc(em);
+      __syncthreads();
+      int eq_before = eq_base + __popc(em & lanemask_lt());
+      int eq_tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q < wid) eq_before += s_w[q];
+        eq_tot += s_w[q];
+      }
+      const bool ev = less || (eq && eq_before < allowed);
+      const unsigned vm = __ballot_sync(0xffffffffu, ev);
+      if (lane == 0) s_w2[wid] = __popc(vm);
+      __syncthreads();
+      int pos = written + __popc(vm & lanemask_lt());
+      int tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q < wid) pos += s_w2[q];
+        tot += s_w2[q];
+      }
+      if (ev) out[pos] = i;
+      written += tot;
+      eq_base += eq_tot;
+      __syncthreads();
+    }
+  }
+  for (int i = cnt + t; i < nblk * p.B; i += 256) out[i] = p.null_index;
+}
+
 // one CTA per sequence
 __global__ void __launch_bounds__(256) select_threshold_kernel(SelectParams p) {
   __shared__ int hist[256];
@@ -961,9 +1295,19 @@ extern "C" int kvc_set_select_mode(int mode) {
 }
 extern "C" int kvc_get_select_mode(void) { return g_select_mode; }
 
-extern "C" size_t kvc_select_evictions_workspace_bytes(int64_t max_evicted_kv, int block_size) {
+// exact workspace of a call: completion keys (sort paths); for long contexts (more than 512 slots per head: the
+// radix path) additionally one orderable key per slot and 4 x 256 threshold sums per sequence
+extern "C" size_t kvc_select_evictions_workspace_bytes_ex(int64_t max_evicted_kv, int block_size, int num_seqs,
+                                                          int max_num_blocks_per_seq) {
   if (max_evicted_kv <= 0 || block_size <= 0) return 0;
-  return ((size_t)max_evicted_kv / block_size + 1) * sizeof(unsigned) + 512;  // completion keys
+  size_t n = ((size_t)max_evicted_kv / block_size + 1) * sizeof(unsigned) + 512;
+  if ((int64_t)max_num_blocks_per_seq * block_size > 512)
+    n += ((size_t)max_evicted_kv + 64) * sizeof(unsigned) + 256 + (size_t)(num_seqs > 0 ? num_seqs : 0) * 4 * 256 * sizeof(int);
+  return n;
+}
+// shape-agnostic upper bound (any context length, up to 1024 sequences per call)
+extern "C" size_t kvc_select_evictions_workspace_bytes(int64_t max_evicted_kv, int block_size) {
+  return kvc_select_evictions_workspace_bytes_ex(max_evicted_kv, block_size, 1024, 1 << 20);
 }
 
 extern "C" int kvc_select_evictions(
@@ -999,7 +1343,8 @@ extern "C" int kvc_select_evictions_ex(
   KVC_REQUIRE(num_seqs >= 0 && num_layers > 0 && num_kv_heads > 0 && max_num_blocks_per_seq > 0,
               KVC_ERR_INVALID, "select_evictions: bad sizes");
   if (num_seqs == 0) return KVC_OK;
-  const size_t need = kvc_select_evictions_workspace_bytes(max_evicted_kv, block_size);
+  const size_t need = kvc_select_evictions_workspace_bytes_ex(max_evicted_kv, block_size, num_seqs,
+                                                              max_num_blocks_per_seq);
   KVC_REQUIRE(workspace && workspace_bytes >= need, KVC_ERR_WORKSPACE,
               "select_evictions: workspace of %zu bytes required, got %zu", need, workspace_bytes);
   SelectParams p;
@@ -1083,6 +1428,29 @@ extern "C" int kvc_select_evictions_ex(
       else KERNEL<1, 16><<<wgrid, 128, 0, st>>>(p);                              \
     }                                                                            \
   } while (0)
+  if (!warp_path && g_select_mode != 1 && max_slots * sizeof(unsigned) <= 200 * 1024) {
+    // long contexts: radix descent on histograms, no sort (mode 1 keeps the sort path for A/B and tests)
+    RadixWs rw;
+    uintptr_t kp = (w + ((size_t)max_evicted_kv / block_size + 1) * sizeof(unsigned) + 255) & ~uintptr_t(255);
+    rw.keys = reinterpret_cast<unsigned*>(kp);
+    rw.fsum = reinterpret_cast<int*>((kp + ((size_t)max_evicted_kv + 64) * sizeof(unsigned) + 255) & ~uintptr_t(255));
+    cudaError_t e = cudaMemsetAsync(rw.fsum, 0, (size_t)num_seqs * 4 * 256 * sizeof(int), st);
+    if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "select_evictions memset: %s", cudaGetErrorString(e));
+    select_radix_pass_kernel<0><<<total, 256, 0, st>>>(p, rw);
+    select_radix_pass_kernel<1><<<total, 256, 0, st>>>(p, rw);
+    select_radix_pass_kernel<2><<<total, 256, 0, st>>>(p, rw);
+    select_radix_pass_kernel<3><<<total, 256, 0, st>>>(p, rw);
+    select_radix_count_kernel<<<total, 256, 0, st>>>(p, rw);
+    select_radix_grant_kernel<<<num_seqs, 256, 0, st>>>(p);
+    const size_t smem = (size_t)max_slots * sizeof(unsigned);
+    if (smem > 40 * 1024) {
+      e = cudaFuncSetAttribute(select_radix_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "select_radix_emit smem attr: %s", cudaGetErrorString(e));
+    }
+    select_radix_emit_kernel<<<total, 256, smem, st>>>(p, rw);
+    KVC_CHECK_LAUNCH("select_radix kernels");
+    return KVC_OK;
+  }
   if (warp_path) {
     KVC_SEL_WARP(select_sort_kernel);
     KVC_CHECK_LAUNCH("select_sort_kernel");

@@ -246,7 +246,8 @@ void select_evictions(torch::Tensor& evicted_logical_indices, torch::Tensor& evi
               "kv_metrics must be a contiguous float32 CUDA tensor");
   const at::cuda::OptionalCUDAGuard guard(device_of(evicted_logical_indices));
   const int64_t max_kv = evicted_logical_indices.numel();
-  const size_t ws_bytes = kvc_select_evictions_workspace_bytes(max_kv, (int)block_size);
+  const size_t ws_bytes = kvc_select_evictions_workspace_bytes_ex(max_kv, (int)block_size, (int)evicted_kv_count.size(0),
+                                                                  (int)block_tables.size(3));
   auto ws = torch::empty({(int64_t)ws_bytes}, evicted_logical_indices.options().dtype(at::kByte));
   check_status(kvc_select_evictions_ex(
                    i32_mut(evicted_logical_indices, "evicted_logical_indices"),
