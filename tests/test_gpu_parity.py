@@ -451,6 +451,8 @@ def attn_case(seed, S, Hq, H, max_ctx, bf16, alibi, buf, min_ctx=1):
     (44, 2, 24, 2, 700, False, False, 50),    # Q=12 (two n-tiles)
     (45, 4, 4, 4, 17, True, False, 0),        # tiny ragged contexts
     (46, 3, 32, 8, 400, False, False, 5),     # streaming kernel, logits beyond the smem cap (fused: global scratch)
+    (47, 3, 32, 8, 2100, False, False, 0),    # long contexts: 5 partitions of 4 MMA tiles (v2: tcgen05 partition kernel)
+    (48, 2, 64, 8, 1300, True, True, 16),     # Llama-3-70B group, bf16, alibi, metric buffer, long contexts
 ])
 def test_attention_random_vs_oracle(capi, O, cfg, version):
     c = attn_case(*cfg)
@@ -605,7 +607,9 @@ def test_k6_vs_reference_cuda(capi, ref_ops, bf16):
 
 @pytest.mark.parametrize("version", ["v1", "v2"])
 @pytest.mark.parametrize("cfg", [(41, 5, 32, 8, 160, False, False, 0), (42, 3, 64, 8, 200, True, False, 0),
-                                 (43, 2, 8, 8, 1500, False, True, 0)])
+                                 (43, 2, 8, 8, 1500, False, True, 0), (47, 3, 32, 8, 2100, False, False, 0),
+                                 (48, 2, 64, 8, 1300, True, False, 0)])   # buffer 0: the reference's v2 reduce writes
+                                 # unrecorded garbage into buffered slots (:563-569), see DESIGN.md section 4
 def test_attention_vs_reference_cuda(capi, ref_ops, cfg, version):
     c = attn_case(*cfg)
     S, Hq, H, D, B = (int(c[k]) for k in ("S", "Hq", "H", "D", "B"))

@@ -1076,6 +1076,293 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
 }
 
 // -----------------------------------------------------------------------------
+// v2 partition kernel on the 5th-generation tensor cores (tcgen05 + TMEM) for LONG per-head contexts
+// (uncompressed or lightly compressed caches: thousands of tokens per head, few (sequence, head) items).
+// grid (num_kv_heads, num_seqs, partitions), 128 threads; a CTA owns one 512-token partition of one
+// (sequence, kv head) and serves all Q query heads of the GQA group (K / V read once):
+//   S^T[128 tok x 16 q] = Ktile[128 tok x 128 d] . Q^T      8 x tcgen05.mma (M=128, N=16, K=16) per 128-token tile,
+//                                                          fp32 accumulators in TMEM (16 columns per tile)
+//   softmax over the partition: one thread = one token row per tile (tcgen05.ld.32x32b.x16), column
+//                               max / sum by warp shuffles + a 4-warp merge in shared memory
+//   O^T[128 d x 16 q] += Vtile^T[128 d x 128 tok] . P^T     8 x tcgen05.mma per tile, accumulated over the tiles
+// Operands are staged global -> registers -> shared memory in the canonical no-swizzle K-major core-matrix
+// layout (8 rows x 16 B; the convention tools/tcgen05_probe.cu and kvc_prefill.cu verified on the B200):
+//   K tile   A operand, row = token:  the cache block layout [16 j][16 t][8] is already core-matrix shaped, a
+//            (block, j) pair is a contiguous 256 B run on both sides           LBO 2048 B, SBO 128 B
+//   V tile   A operand, row = d:      a 16 B piece = 8 tokens of one row d                same LBO / SBO
+//   Q, P     B operands, 16 rows (query heads):                                LBO  256 B, SBO 128 B
+// K and V tiles share two 32 KB buffers (all QK^T products of the partition are in TMEM before the first V tile
+// is staged); tokens beyond the context are masked to -inf in S and zeroed in V (reference :370-379).
+// Outputs are the reference's v2 buffers (exp_sums, max_logits, tmp_out, raw logits parked in kv_metric_out);
+// paged_attention_reduce_kernel below finishes.  Arithmetic: fp16/bf16 operands, fp32 accumulate, probabilities
+// rounded to the cache type before PV like the reference (:356-357).
+// -----------------------------------------------------------------------------
+constexpr int kTcTile = 128;                      // tokens per MMA tile (8 cache blocks)
+constexpr int kTcTileBytes = kTcTile * kD * 2;    // 32 KB
+constexpr int kTcNQ = 16;                         // UMMA N: query heads padded to 16
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;  // sm_100 descriptor version
+  return d;
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(128) paged_attention_tc_kernel(AttnParams p) {
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  unsigned char* sBuf = tc_smem;                                   // [2][32 KB] K tiles, then V tiles
+  unsigned char* sQ = tc_smem + 2 * kTcTileBytes;                  // 4 KB
+  unsigned char* sP = sQ + kTcNQ * kD * 2;                         // [4][4 KB]
+  float* red = reinterpret_cast<float*>(sP + 4 * kTcNQ * kTcTile * 2);  // [4 warps][16]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + 4 * kTcNQ);   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int h = blockIdx.x, s = blockIdx.y, part = blockIdx.z;
+  const int H = p.num_kv_heads, Q = p.Q;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int seq_head = s * H + h;
+  const int ctx = p.context_lens[seq_head];
+  const int nblk = (ctx + kB - 1) / kB;
+  const int blk_begin = part * (kPartition / kB);
+  if (blk_begin >= nblk) return;  // reference :139-142 (CTA-uniform, before any allocation)
+  const int blk_end = min(nblk, blk_begin + kPartition / kB);
+  const int tok_begin = blk_begin * kB;
+  const int ntiles = (blk_end - blk_begin + 7) / 8;
+  const int* __restrict__ bt = p.block_tables + (int64_t)seq_head * p.max_num_blocks_per_seq;
+  const int max_pos = p.last_position[s] - p.kv_metric_buffer_len[s];
+  const unsigned char* __restrict__ kc = reinterpret_cast<const unsigned char*>(p.k_cache);
+  const unsigned char* __restrict__ vc = reinterpret_cast<const unsigned char*>(p.v_cache);
+  const int64_t block_bytes = p.kv_block_stride * 2;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // ---- Q as the B operand: row n = query head, 16 chunks of 8 d ----
+  for (int i = tid; i < kTcNQ * 16; i += 128) {
+    const int n = i >> 4, c = i & 15;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (n < Q)
+      v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.q) + (int64_t)s * p.q_stride +
+                                          (int64_t)(h * Q + n) * kD + c * 8);
+    *reinterpret_cast<uint4*>(sQ + c * 256 + n * 16) = v;
+  }
+  // K tile t: smem (j, tok) = j * 2048 + tok * 16  <-  block (tok / 16): j * 256 + (tok % 16) * 16
+  auto stage_k = [&](int t, int buf) {
+    unsigned char* dst = sBuf + buf * kTcTileBytes;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int idx = it * 128 + tid;          // 2048 pieces of 16 B
+      const int run = idx >> 4, piece = idx & 15;  // run = (block in tile) * 16 + j
+      const int bi = run >> 4, j = run & 15;
+      const int b = blk_begin + t * 8 + bi;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (b < blk_end) v = ld_stream16(kc + (int64_t)bt[b] * block_bytes + j * 256 + piece * 16);
+      *reinterpret_cast<uint4*>(dst + j * 2048 + bi * 256 + piece * 16) = v;
+    }
+  };
+  // V tile t: smem (tok / 8, d) = (tok / 8) * 2048 + d * 16  <-  block: d * 32 + (tok % 16 / 8) * 16; tokens >= ctx zeroed
+  auto stage_v = [&](int t, int buf) {
+    unsigned char* dst = sBuf + buf * kTcTileBytes;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int idx = it * 128 + tid;
+      const int bi = idx >> 8, rem = idx & 255;   // 256 pieces per block: (d, half)
+      const int d = rem >> 1, half = rem & 1;
+      const int b = blk_begin + t * 8 + bi;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (b < blk_end) {
+        v = ld_stream16(vc + (int64_t)bt[b] * block_bytes + d * 32 + half * 16);
+        const int valid = ctx - (b * kB + half * 8);   // tokens of this piece inside the context
+        if (valid < 8) {
+          uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t lo = (2 * e < valid) ? 0xffffu : 0u, hi = (2 * e + 1 < valid) ? 0xffff0000u : 0u;
+            w[e] &= lo | hi;
+          }
+          v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      *reinterpret_cast<uint4*>(dst + (bi * 2 + half) * 2048 + d * 16) = v;
+    }
+  };
+  auto publish = [&]() {  // generic-proxy shared-memory writes -> tensor core, CTA-wide
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  };
+  stage_k(0, 0);
+  publish();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t kFmt = BF16 ? 1u : 0u;
+  // instruction descriptor: D = f32, A = B = f16 / bf16, both K-major, N = 16, M = 128
+  constexpr uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(kTcNQ >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+  auto mma = [&](uint32_t d_col, uint32_t a_base, uint32_t b_base, bool first_clears, int bar) {  // one thread
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint64_t ad = tc_desc(a_base + ks * 4096, 2048, 128);
+      const uint64_t bd = tc_desc(b_base + ks * 512, 256, 128);
+      const uint32_t acc = (ks > 0 || !first_clears) ? 1u : 0u;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem + d_col), "l"(ad), "l"(bd),
+          "r"(idesc), "r"(acc)
+          : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                     smem_u32(&bars[bar]))
+                 : "memory");
+  };
+  uint32_t phases = 0u;
+  auto wait_bar = [&](int b) {
+    mbar_wait(smem_u32(&bars[b]), (phases >> b) & 1u);
+    phases ^= 1u << b;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  };
+
+  // ---- S^T tiles: all QK^T products of the partition go to TMEM columns [16 t, 16 t + 16) ----
+  for (int t = 0; t < ntiles; ++t) {
+    if (tid == 0) mma(t * kTcNQ, smem_u32(sBuf + (t & 1) * kTcTileBytes), smem_u32(sQ), true, t & 1);
+    if (t + 1 < ntiles) {
+      if (t >= 1) wait_bar((t + 1) & 1);   // the MMAs of tile t-1 have read that buffer
+      stage_k(t + 1, (t + 1) & 1);
+      publish();
+    }
+  }
+  // every commit covers all earlier MMAs of the issuing thread: drain both barriers that are still pending
+  if (ntiles >= 2) wait_bar(ntiles & 1);
+  wait_bar((ntiles - 1) & 1);
+  // K buffers are free: start on the first two V tiles while the softmax runs on registers
+  stage_v(0, 0);
+  if (ntiles > 1) stage_v(1, 1);
+
+  // ---- softmax over the partition: thread = token row (tile t: token tok_begin + 128 t + tid) ----
+  float sreg[4][kTcNQ];
+  float mloc[kTcNQ];
+#pragma unroll
+  for (int q = 0; q < kTcNQ; ++q) mloc[q] = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (t < ntiles) {
+      uint32_t r[16];
+      tc_ld16(tmem + ((uint32_t)(warp * 32) << 16) + t * kTcNQ, r);
+      const int tok = tok_begin + t * kTcTile + tid;
+      const bool live = tok < ctx;
+      int64_t slot = 0;
+      bool rec = false;
+      if (live && p.record) {
+        slot = (int64_t)bt[tok >> 4] * kB + (tok & 15);
+        rec = p.kv_position[slot] <= max_pos;   // reference :309
+      }
+#pragma unroll
+      for (int q = 0; q < kTcNQ; ++q) {
+        float v = __uint_as_float(r[q]) * p.scale;
+        if (p.alibi_slopes != nullptr && q < Q) v += p.alibi_slopes[h * Q + q] * (float)(tok - ctx + 1);  // :253
+        v = live ? v : -INFINITY;
+        sreg[t][q] = v;
+        mloc[q] = fmaxf(mloc[q], v);
+        if (rec && q < Q) p.metric[slot * Q + q] = v;   // raw logit, finalised by the reduce kernel
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kTcNQ; ++q) sreg[t][q] = -INFINITY;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kTcNQ; ++q) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) mloc[q] = fmaxf(mloc[q], __shfl_xor_sync(0xffffffffu, mloc[q], d));
+    if (lane == 0) red[warp * kTcNQ + q] = mloc[q];
+  }
+  __syncthreads();
+  float mx[kTcNQ], lsum[kTcNQ];
+#pragma unroll
+  for (int q = 0; q < kTcNQ; ++q) {
+    mx[q] = fmaxf(fmaxf(red[q], red[kTcNQ + q]), fmaxf(red[2 * kTcNQ + q], red[3 * kTcNQ + q]));
+    lsum[q] = 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (t < ntiles) {
+      const int r_ = tid;  // token row inside the tile
+#pragma unroll
+      for (int q = 0; q < kTcNQ; ++q) {
+        const float pe = __expf(sreg[t][q] - mx[q]);   // the partition holds >= 1 live token: mx finite
+        lsum[q] += pe;
+        *reinterpret_cast<uint16_t*>(sP + t * (kTcNQ * kTcTile * 2) + (r_ >> 3) * 256 + q * 16 + (r_ & 7) * 2) =
+            to_bits16<BF16>(pe);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kTcNQ; ++q) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) lsum[q] += __shfl_xor_sync(0xffffffffu, lsum[q], d);
+    if (lane == 0) red[warp * kTcNQ + q] = lsum[q];
+  }
+  publish();   // P tiles + V tiles 0 / 1 visible to the tensor core; red[] visible to every thread
+  float inv[kTcNQ];
+#pragma unroll
+  for (int q = 0; q < kTcNQ; ++q) {
+    const float L = red[q] + red[kTcNQ + q] + red[2 * kTcNQ + q] + red[3 * kTcNQ + q];
+    inv[q] = __fdividef(1.f, L + 1e-6f);  // reference :298
+    if (tid == q && q < Q) {               // reference :316-326
+      const int64_t idx = ((int64_t)s * p.num_heads + h * Q + q) * p.max_partitions + part;
+      p.max_logits[idx] = mx[q];
+      p.exp_sums[idx] = L;
+    }
+  }
+
+  // ---- O^T += V^T P^T over the tiles (TMEM columns [64, 80)) ----
+  constexpr uint32_t kOCol = 4 * kTcNQ;
+  for (int t = 0; t < ntiles; ++t) {
+    if (tid == 0)
+      mma(kOCol, smem_u32(sBuf + (t & 1) * kTcTileBytes), smem_u32(sP + t * (kTcNQ * kTcTile * 2)), t == 0, t & 1);
+    if (t + 2 < ntiles) {
+      wait_bar(t & 1);          // the MMAs of tile t have read that buffer
+      stage_v(t + 2, t & 1);
+      publish();
+    }
+  }
+  if (ntiles >= 2 && ((ntiles - 2) + 2 >= ntiles)) wait_bar(ntiles & 1);   // tile ntiles-2 was not waited for above
+  wait_bar((ntiles - 1) & 1);
+
+  // ---- partial output: thread = head dim d ----
+  {
+    uint32_t r[16];
+    tc_ld16(tmem + ((uint32_t)(warp * 32) << 16) + kOCol, r);
+    uint16_t* to = reinterpret_cast<uint16_t*>(p.tmp_out);
+#pragma unroll
+    for (int q = 0; q < kTcNQ; ++q)
+      if (q < Q)
+        to[(((int64_t)s * p.num_heads + h * Q + q) * p.max_partitions + part) * kD + tid] =
+            to_bits16<BF16>(__uint_as_float(r[q]) * inv[q]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
+// -----------------------------------------------------------------------------
 // v2 reduce.  grid (num_kv_heads, num_seqs), 128 threads.  reference :525-652.
 // -----------------------------------------------------------------------------
 template <bool BF16>
@@ -1338,8 +1625,27 @@ extern "C" int kvc_paged_attention_v2(
   p.exp_sums = exp_sums; p.max_logits = max_logits; p.tmp_out = tmp_out;
   p.max_partitions = (max_context_len + kPartition - 1) / kPartition;  // reference :914
   cudaStream_t st = as_stream(stream);
-  rc = dispatch_attention<kModeV2>(p, num_seqs, p.max_partitions, 0, dtype, st);
-  if (rc != KVC_OK) return rc;
+  // partitions on the tcgen05 tensor cores (default); KVC_ATTN_V2_TC=0 keeps the mma.sync partition kernel
+  static const int use_tc = [] { const char* e = getenv("KVC_ATTN_V2_TC"); return e ? atoi(e) : 1; }();
+  if (use_tc && p.Q <= kTcNQ) {
+    const size_t tc_smem_bytes = 2 * kTcTileBytes + kTcNQ * kD * 2 + 4 * kTcNQ * kTcTile * 2 + 4 * kTcNQ * 4 + 64;
+    cudaError_t e;
+    const dim3 grid(num_kv_heads, num_seqs, p.max_partitions);
+    if (dtype == KVC_F16) {
+      e = cudaFuncSetAttribute(paged_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)tc_smem_bytes);
+      if (e == cudaSuccess) paged_attention_tc_kernel<false><<<grid, 128, tc_smem_bytes, st>>>(p);
+    } else {
+      e = cudaFuncSetAttribute(paged_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)tc_smem_bytes);
+      if (e == cudaSuccess) paged_attention_tc_kernel<true><<<grid, 128, tc_smem_bytes, st>>>(p);
+    }
+    if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "paged attention (tcgen05) smem attr: %s", cudaGetErrorString(e));
+    KVC_CHECK_LAUNCH("paged_attention_tc_kernel");
+  } else {
+    rc = dispatch_attention<kModeV2>(p, num_seqs, p.max_partitions, 0, dtype, st);
+    if (rc != KVC_OK) return rc;
+  }
   const size_t smem = sizeof(float) * (size_t)p.max_partitions;
   if (dtype == KVC_F16)
     paged_attention_reduce_kernel<false><<<dim3(num_kv_heads, num_seqs), kAttnThreads, smem, st>>>(p);
