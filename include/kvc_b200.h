@@ -367,6 +367,14 @@ KVC_API int kvc_flush_deferred(
 KVC_API int kvc_set_attention_pdl(int mode);
 KVC_API int kvc_get_attention_pdl(void);
 
+/* Partition kernel of kvc_paged_attention_v2 (long per-head contexts; process-wide, initial value from the
+ * environment variable KVC_ATTN_V2_MODE): 1 = mma.sync fragments loaded straight from the paged blocks;
+ * 2 = tcgen05 / TMEM: 128-token UMMA tiles (S^T = K Q^T, O^T = V^T P^T, fp32 accumulators in tensor memory),
+ * operands staged in the canonical K-major core-matrix layout; 0 (default) = the faster of the two on the B200.
+ * Same buffers and results (within the fp16 tolerance) in every mode. */
+KVC_API int kvc_set_attention_v2_mode(int mode);
+KVC_API int kvc_get_attention_v2_mode(void);
+
 /* ---------------------------------------------------------------------------
  * Additive: fused eviction selection straight from the paged metrics.
  * replaces CompressionMetrics.schedule_evictions (vllm/kvcompress/metrics.py:441-847:

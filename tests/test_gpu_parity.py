@@ -156,6 +156,14 @@ def test_k4_k5_golden(capi, name, moves_mode):
     np.testing.assert_array_equal(kp.cpu().numpy(), c["out_kv_position"])
 
 
+@pytest.fixture(params=[1, 2], ids=["v2_mma_sync", "v2_tcgen05"])
+def v2_mode(request, capi):
+    """partition kernel of paged attention v2 (kvc_set_attention_v2_mode); irrelevant for v1 / fused"""
+    capi.set_attention_v2_mode(request.param)
+    yield request.param
+    capi.set_attention_v2_mode(0)
+
+
 def run_attention(capi, c, version, record=True):
     S, Hq, H, D, B = (int(c[k]) for k in ("S", "Hq", "H", "D", "B"))
     Q = Hq // H
@@ -191,7 +199,9 @@ def run_attention(capi, c, version, record=True):
 
 @pytest.mark.parametrize("version", ["v1", "v2"])
 @pytest.mark.parametrize("name", sorted(ATTN))
-def test_attention_golden(capi, name, version):
+def test_attention_golden(capi, name, version, v2_mode):
+    if version != "v2" and v2_mode != 1:
+        pytest.skip("v2 partition-kernel sweep")
     c = ATTN[name]
     out, metric = run_attention(capi, c, version)
     # reference tolerance: tests/kernels/test_kvcompress_attention.py:356-357
@@ -454,7 +464,9 @@ def attn_case(seed, S, Hq, H, max_ctx, bf16, alibi, buf, min_ctx=1):
     (47, 3, 32, 8, 2100, False, False, 0),    # long contexts: 5 partitions of 4 MMA tiles (v2: tcgen05 partition kernel)
     (48, 2, 64, 8, 1300, True, True, 16),     # Llama-3-70B group, bf16, alibi, metric buffer, long contexts
 ])
-def test_attention_random_vs_oracle(capi, O, cfg, version):
+def test_attention_random_vs_oracle(capi, O, cfg, version, v2_mode):
+    if version != "v2" and v2_mode != 1:
+        pytest.skip("v2 partition-kernel sweep")
     c = attn_case(*cfg)
     S, Hq, H, D, B = (int(c[k]) for k in ("S", "Hq", "H", "D", "B"))
     Q = Hq // H
@@ -610,7 +622,9 @@ def test_k6_vs_reference_cuda(capi, ref_ops, bf16):
                                  (43, 2, 8, 8, 1500, False, True, 0), (47, 3, 32, 8, 2100, False, False, 0),
                                  (48, 2, 64, 8, 1300, True, False, 0)])   # buffer 0: the reference's v2 reduce writes
                                  # unrecorded garbage into buffered slots (:563-569), see DESIGN.md section 4
-def test_attention_vs_reference_cuda(capi, ref_ops, cfg, version):
+def test_attention_vs_reference_cuda(capi, ref_ops, cfg, version, v2_mode):
+    if version != "v2" and v2_mode != 1:
+        pytest.skip("v2 partition-kernel sweep")
     c = attn_case(*cfg)
     S, Hq, H, D, B = (int(c[k]) for k in ("S", "Hq", "H", "D", "B"))
     Q = Hq // H

@@ -267,6 +267,15 @@ def get_attention_pdl() -> int:
     return int(native.load_lib().kvc_get_attention_pdl())
 
 
+def set_attention_v2_mode(mode: int) -> None:
+    """kvc_set_attention_v2_mode: partition kernel of paged attention v2: 0 auto, 1 mma.sync, 2 tcgen05 / TMEM."""
+    _check(native.load_lib().kvc_set_attention_v2_mode(int(mode)))
+
+
+def get_attention_v2_mode() -> int:
+    return int(native.load_lib().kvc_get_attention_v2_mode())
+
+
 def set_select_mode(mode: int) -> None:
     """kvc_set_select_mode: 0 = choose by shape (default), 1 = rank / threshold / emit launches,
     2 = one CTA per sequence with the pruned sort whenever block size and context lengths allow."""

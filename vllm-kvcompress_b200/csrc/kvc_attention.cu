@@ -1162,44 +1162,62 @@ __global__ void __launch_bounds__(128) paged_attention_tc_kernel(AttnParams p) {
                                           (int64_t)(h * Q + n) * kD + c * 8);
     *reinterpret_cast<uint4*>(sQ + c * 256 + n * 16) = v;
   }
-  // K tile t: smem (j, tok) = j * 2048 + tok * 16  <-  block (tok / 16): j * 256 + (tok % 16) * 16
-  auto stage_k = [&](int t, int buf) {
-    unsigned char* dst = sBuf + buf * kTcTileBytes;
+  // Tiles stream through two 32 KB buffers in the order K(0) .. K(n-1), V(0) .. V(n-1); stream index i lives in
+  // buffer i & 1.  Staging is asynchronous (cp.async, 16 B per copy, no registers): the copies of tile i+1 are in
+  // flight while tile i is multiplied, and the first V tiles stream in under the softmax.
+  //   K tile: smem (j, tok) = j * 2048 + tok * 16        <-  block (tok / 16): j * 256 + (tok % 16) * 16
+  //   V tile: smem (tok / 8, d) = (tok / 8) * 2048 + d * 16  <-  block: d * 32 + (tok % 16 / 8) * 16
+  auto issue_tile = [&](int i) {
+    unsigned char* dst = sBuf + (i & 1) * kTcTileBytes;
+    const bool is_v = i >= ntiles;
+    const int t = is_v ? i - ntiles : i;
 #pragma unroll 4
     for (int it = 0; it < 16; ++it) {
       const int idx = it * 128 + tid;          // 2048 pieces of 16 B
-      const int run = idx >> 4, piece = idx & 15;  // run = (block in tile) * 16 + j
-      const int bi = run >> 4, j = run & 15;
-      const int b = blk_begin + t * 8 + bi;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (b < blk_end) v = ld_stream16(kc + (int64_t)bt[b] * block_bytes + j * 256 + piece * 16);
-      *reinterpret_cast<uint4*>(dst + j * 2048 + bi * 256 + piece * 16) = v;
-    }
-  };
-  // V tile t: smem (tok / 8, d) = (tok / 8) * 2048 + d * 16  <-  block: d * 32 + (tok % 16 / 8) * 16; tokens >= ctx zeroed
-  auto stage_v = [&](int t, int buf) {
-    unsigned char* dst = sBuf + buf * kTcTileBytes;
-#pragma unroll 4
-    for (int it = 0; it < 16; ++it) {
-      const int idx = it * 128 + tid;
-      const int bi = idx >> 8, rem = idx & 255;   // 256 pieces per block: (d, half)
-      const int d = rem >> 1, half = rem & 1;
-      const int b = blk_begin + t * 8 + bi;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (b < blk_end) {
-        v = ld_stream16(vc + (int64_t)bt[b] * block_bytes + d * 32 + half * 16);
-        const int valid = ctx - (b * kB + half * 8);   // tokens of this piece inside the context
-        if (valid < 8) {
-          uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint32_t lo = (2 * e < valid) ? 0xffffu : 0u, hi = (2 * e + 1 < valid) ? 0xffff0000u : 0u;
-            w[e] &= lo | hi;
-          }
-          v = make_uint4(w[0], w[1], w[2], w[3]);
-        }
+      int bi, src_off, dst_off;
+      if (!is_v) {
+        const int run = idx >> 4, piece = idx & 15;  // run = (block in tile) * 16 + j
+        bi = run >> 4;
+        const int j = run & 15;
+        src_off = j * 256 + piece * 16;
+        dst_off = j * 2048 + bi * 256 + piece * 16;
+      } else {
+        bi = idx >> 8;
+        const int rem = idx & 255, d = rem >> 1, half = rem & 1;   // 256 pieces per block: (d, half)
+        src_off = d * 32 + half * 16;
+        dst_off = (bi * 2 + half) * 2048 + d * 16;
       }
-      *reinterpret_cast<uint4*>(dst + (bi * 2 + half) * 2048 + d * 16) = v;
+      const int b = blk_begin + t * 8 + bi;
+      if (b < blk_end) {
+        const unsigned char* src = (is_v ? vc : kc) + (int64_t)bt[b] * block_bytes + src_off;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + dst_off)), "l"(src) : "memory");
+      } else {
+        *reinterpret_cast<uint4*>(dst + dst_off) = make_uint4(0, 0, 0, 0);   // beyond the context: zero operand
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // tokens >= ctx of the context's last block are zeroed in the staged V tile (reference :370-379: 0 * NaN)
+  auto fix_v_tail = [&](int i) {
+    const int t = i - ntiles;
+    const int b_last = nblk - 1;   // the only block that can hold tokens beyond the context
+    const int bi = b_last - (blk_begin + t * 8);
+    if ((ctx & (kB - 1)) == 0 || bi < 0 || bi >= 8) return;
+    unsigned char* dst = sBuf + (i & 1) * kTcTileBytes;
+    for (int rem = tid; rem < 256; rem += 128) {
+      const int d = rem >> 1, half = rem & 1;
+      const int valid = ctx - (b_last * kB + half * 8);
+      if (valid < 8) {
+        uint4* ptr = reinterpret_cast<uint4*>(dst + (bi * 2 + half) * 2048 + d * 16);
+        uint4 v = *ptr;
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t lo = (2 * e < valid) ? 0xffffu : 0u, hi = (2 * e + 1 < valid) ? 0xffff0000u : 0u;
+          w[e] &= lo | hi;
+        }
+        *ptr = make_uint4(w[0], w[1], w[2], w[3]);
+      }
     }
   };
   auto publish = [&]() {  // generic-proxy shared-memory writes -> tensor core, CTA-wide
@@ -1208,8 +1226,10 @@ __global__ void __launch_bounds__(128) paged_attention_tc_kernel(AttnParams p) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
-  stage_k(0, 0);
-  publish();
+  const int nstream = 2 * ntiles;
+  issue_tile(0);
+  issue_tile(1);   // nstream >= 2
+  publish();       // Q tile, TMEM slot
   const uint32_t tmem = *tmem_slot;
   constexpr uint32_t kFmt = BF16 ? 1u : 0u;
   // instruction descriptor: D = f32, A = B = f16 / bf16, both K-major, N = 16, M = 128
@@ -1231,120 +1251,120 @@ __global__ void __launch_bounds__(128) paged_attention_tc_kernel(AttnParams p) {
                      smem_u32(&bars[bar]))
                  : "memory");
   };
-  uint32_t phases = 0u;
+  uint32_t phases = 0u, pending = 0u;   // per barrier: parity of the next wait; a commit not yet waited for
   auto wait_bar = [&](int b) {
+    if (!((pending >> b) & 1u)) return;
     mbar_wait(smem_u32(&bars[b]), (phases >> b) & 1u);
     phases ^= 1u << b;
+    pending &= ~(1u << b);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
-
-  // ---- S^T tiles: all QK^T products of the partition go to TMEM columns [16 t, 16 t + 16) ----
-  for (int t = 0; t < ntiles; ++t) {
-    if (tid == 0) mma(t * kTcNQ, smem_u32(sBuf + (t & 1) * kTcTileBytes), smem_u32(sQ), true, t & 1);
-    if (t + 1 < ntiles) {
-      if (t >= 1) wait_bar((t + 1) & 1);   // the MMAs of tile t-1 have read that buffer
-      stage_k(t + 1, (t + 1) & 1);
-      publish();
-    }
-  }
-  // every commit covers all earlier MMAs of the issuing thread: drain both barriers that are still pending
-  if (ntiles >= 2) wait_bar(ntiles & 1);
-  wait_bar((ntiles - 1) & 1);
-  // K buffers are free: start on the first two V tiles while the softmax runs on registers
-  stage_v(0, 0);
-  if (ntiles > 1) stage_v(1, 1);
-
-  // ---- softmax over the partition: thread = token row (tile t: token tok_begin + 128 t + tid) ----
-  float sreg[4][kTcNQ];
-  float mloc[kTcNQ];
-#pragma unroll
-  for (int q = 0; q < kTcNQ; ++q) mloc[q] = -INFINITY;
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    if (t < ntiles) {
-      uint32_t r[16];
-      tc_ld16(tmem + ((uint32_t)(warp * 32) << 16) + t * kTcNQ, r);
-      const int tok = tok_begin + t * kTcTile + tid;
-      const bool live = tok < ctx;
-      int64_t slot = 0;
-      bool rec = false;
-      if (live && p.record) {
-        slot = (int64_t)bt[tok >> 4] * kB + (tok & 15);
-        rec = p.kv_position[slot] <= max_pos;   // reference :309
-      }
-#pragma unroll
-      for (int q = 0; q < kTcNQ; ++q) {
-        float v = __uint_as_float(r[q]) * p.scale;
-        if (p.alibi_slopes != nullptr && q < Q) v += p.alibi_slopes[h * Q + q] * (float)(tok - ctx + 1);  // :253
-        v = live ? v : -INFINITY;
-        sreg[t][q] = v;
-        mloc[q] = fmaxf(mloc[q], v);
-        if (rec && q < Q) p.metric[slot * Q + q] = v;   // raw logit, finalised by the reduce kernel
-      }
-    } else {
-#pragma unroll
-      for (int q = 0; q < kTcNQ; ++q) sreg[t][q] = -INFINITY;
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < kTcNQ; ++q) {
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) mloc[q] = fmaxf(mloc[q], __shfl_xor_sync(0xffffffffu, mloc[q], d));
-    if (lane == 0) red[warp * kTcNQ + q] = mloc[q];
-  }
-  __syncthreads();
-  float mx[kTcNQ], lsum[kTcNQ];
-#pragma unroll
-  for (int q = 0; q < kTcNQ; ++q) {
-    mx[q] = fmaxf(fmaxf(red[q], red[kTcNQ + q]), fmaxf(red[2 * kTcNQ + q], red[3 * kTcNQ + q]));
-    lsum[q] = 0.f;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    if (t < ntiles) {
-      const int r_ = tid;  // token row inside the tile
-#pragma unroll
-      for (int q = 0; q < kTcNQ; ++q) {
-        const float pe = __expf(sreg[t][q] - mx[q]);   // the partition holds >= 1 live token: mx finite
-        lsum[q] += pe;
-        *reinterpret_cast<uint16_t*>(sP + t * (kTcNQ * kTcTile * 2) + (r_ >> 3) * 256 + q * 16 + (r_ & 7) * 2) =
-            to_bits16<BF16>(pe);
-      }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < kTcNQ; ++q) {
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) lsum[q] += __shfl_xor_sync(0xffffffffu, lsum[q], d);
-    if (lane == 0) red[warp * kTcNQ + q] = lsum[q];
-  }
-  publish();   // P tiles + V tiles 0 / 1 visible to the tensor core; red[] visible to every thread
-  float inv[kTcNQ];
-#pragma unroll
-  for (int q = 0; q < kTcNQ; ++q) {
-    const float L = red[q] + red[kTcNQ + q] + red[2 * kTcNQ + q] + red[3 * kTcNQ + q];
-    inv[q] = __fdividef(1.f, L + 1e-6f);  // reference :298
-    if (tid == q && q < Q) {               // reference :316-326
-      const int64_t idx = ((int64_t)s * p.num_heads + h * Q + q) * p.max_partitions + part;
-      p.max_logits[idx] = mx[q];
-      p.exp_sums[idx] = L;
-    }
-  }
-
-  // ---- O^T += V^T P^T over the tiles (TMEM columns [64, 80)) ----
   constexpr uint32_t kOCol = 4 * kTcNQ;
-  for (int t = 0; t < ntiles; ++t) {
-    if (tid == 0)
-      mma(kOCol, smem_u32(sBuf + (t & 1) * kTcTileBytes), smem_u32(sP + t * (kTcNQ * kTcTile * 2)), t == 0, t & 1);
-    if (t + 2 < ntiles) {
-      wait_bar(t & 1);          // the MMAs of tile t have read that buffer
-      stage_v(t + 2, t & 1);
-      publish();
+  float mx[kTcNQ], inv[kTcNQ];
+
+  for (int i = 0; i < nstream; ++i) {
+    if (i == ntiles) {
+      // every QK^T product of the partition is needed now; the first V tiles keep streaming in meanwhile
+      wait_bar(0);
+      wait_bar(1);
+      // ---- softmax over the partition: thread = token row (tile t: token tok_begin + 128 t + tid) ----
+      float sreg[4][kTcNQ];
+      float mloc[kTcNQ];
+#pragma unroll
+      for (int q = 0; q < kTcNQ; ++q) mloc[q] = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (t < ntiles) {
+          uint32_t r[16];
+          tc_ld16(tmem + ((uint32_t)(warp * 32) << 16) + t * kTcNQ, r);
+          const int tok = tok_begin + t * kTcTile + tid;
+          const bool live = tok < ctx;
+          int64_t slot = 0;
+          bool rec = false;
+          if (live && p.record) {
+            slot = (int64_t)bt[tok >> 4] * kB + (tok & 15);
+            rec = p.kv_position[slot] <= max_pos;   // reference :309
+          }
+#pragma unroll
+          for (int q = 0; q < kTcNQ; ++q) {
+            float v = __uint_as_float(r[q]) * p.scale;
+            if (p.alibi_slopes != nullptr && q < Q) v += p.alibi_slopes[h * Q + q] * (float)(tok - ctx + 1);  // :253
+            v = live ? v : -INFINITY;
+            sreg[t][q] = v;
+            mloc[q] = fmaxf(mloc[q], v);
+            if (rec && q < Q) p.metric[slot * Q + q] = v;   // raw logit, finalised by the reduce kernel
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < kTcNQ; ++q) sreg[t][q] = -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kTcNQ; ++q) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) mloc[q] = fmaxf(mloc[q], __shfl_xor_sync(0xffffffffu, mloc[q], d));
+        if (lane == 0) red[warp * kTcNQ + q] = mloc[q];
+      }
+      __syncthreads();
+      float lsum[kTcNQ];
+#pragma unroll
+      for (int q = 0; q < kTcNQ; ++q) {
+        mx[q] = fmaxf(fmaxf(red[q], red[kTcNQ + q]), fmaxf(red[2 * kTcNQ + q], red[3 * kTcNQ + q]));
+        lsum[q] = 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (t < ntiles) {
+          const int r_ = tid;  // token row inside the tile
+#pragma unroll
+          for (int q = 0; q < kTcNQ; ++q) {
+            const float pe = __expf(sreg[t][q] - mx[q]);   // the partition holds >= 1 live token: mx finite
+            lsum[q] += pe;
+            *reinterpret_cast<uint16_t*>(sP + t * (kTcNQ * kTcTile * 2) + (r_ >> 3) * 256 + q * 16 + (r_ & 7) * 2) =
+                to_bits16<BF16>(pe);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < kTcNQ; ++q) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) lsum[q] += __shfl_xor_sync(0xffffffffu, lsum[q], d);
+        if (lane == 0) red[warp * kTcNQ + q] = lsum[q];
+      }
+      __syncthreads();   // red[] visible; the P tiles are published together with the first V tile below
+#pragma unroll
+      for (int q = 0; q < kTcNQ; ++q) {
+        const float L = red[q] + red[kTcNQ + q] + red[2 * kTcNQ + q] + red[3 * kTcNQ + q];
+        inv[q] = __fdividef(1.f, L + 1e-6f);  // reference :298
+        if (tid == q && q < Q) {               // reference :316-326
+          const int64_t idx = ((int64_t)s * p.num_heads + h * Q + q) * p.max_partitions + part;
+          p.max_logits[idx] = mx[q];
+          p.exp_sums[idx] = L;
+        }
+      }
+    }
+    // tile i has landed (this thread's copies; the CTA-wide publish below makes all of them visible)
+    if (i + 1 < nstream) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (i >= ntiles) {
+      __syncthreads();   // every thread's pieces of the V tile are in shared memory before the tail is patched
+      fix_v_tail(i);
+    }
+    publish();
+    if (tid == 0) {
+      const uint32_t a_base = smem_u32(sBuf + (i & 1) * kTcTileBytes);
+      if (i < ntiles) mma(i * kTcNQ, a_base, smem_u32(sQ), true, i & 1);                      // S^T(i) = K Q^T
+      else mma(kOCol, a_base, smem_u32(sP + (i - ntiles) * (kTcNQ * kTcTile * 2)), i == ntiles, i & 1);  // O^T += V^T P^T
+    }
+    pending |= 1u << (i & 1);
+    if (i + 2 < nstream) {
+      wait_bar(i & 1);       // the MMAs of tile i have read the buffer
+      issue_tile(i + 2);
     }
   }
-  if (ntiles >= 2 && ((ntiles - 2) + 2 >= ntiles)) wait_bar(ntiles & 1);   // tile ntiles-2 was not waited for above
-  wait_bar((ntiles - 1) & 1);
+  wait_bar(0);
+  wait_bar(1);
 
   // ---- partial output: thread = head dim d ----
   {
@@ -1422,6 +1442,17 @@ __global__ void __launch_bounds__(kAttnThreads) paged_attention_reduce_kernel(At
 #ifdef KVC_ATTN_TRACE
 static unsigned long long* g_attn_trace = nullptr;
 #endif
+// partition kernel of paged attention v2: 1 = mma.sync fragments straight from global memory, 2 = tcgen05 / TMEM
+// tiles (paged_attention_tc_kernel); 0 = the faster of the two on the B200 (currently 1)
+static int g_v2_mode = -1;
+static int attention_v2_mode() {
+  if (g_v2_mode < 0) {
+    const char* v = getenv("KVC_ATTN_V2_MODE");
+    g_v2_mode = v ? atoi(v) : 0;
+    if (g_v2_mode < 0 || g_v2_mode > 2) g_v2_mode = 0;
+  }
+  return g_v2_mode == 0 ? 1 : g_v2_mode;
+}
 static int g_pdl_mode = -1;  // -1 = not set yet: KVC_ATTN_PDL from the environment, else 1
 static int attention_pdl_mode() {
   if (g_pdl_mode < 0) {
@@ -1625,8 +1656,8 @@ extern "C" int kvc_paged_attention_v2(
   p.exp_sums = exp_sums; p.max_logits = max_logits; p.tmp_out = tmp_out;
   p.max_partitions = (max_context_len + kPartition - 1) / kPartition;  // reference :914
   cudaStream_t st = as_stream(stream);
-  // partitions on the tcgen05 tensor cores (default); KVC_ATTN_V2_TC=0 keeps the mma.sync partition kernel
-  static const int use_tc = [] { const char* e = getenv("KVC_ATTN_V2_TC"); return e ? atoi(e) : 1; }();
+  // partition kernel: tcgen05 / TMEM tiles or mma.sync fragments (kvc_set_attention_v2_mode)
+  const bool use_tc = attention_v2_mode() == 2;
   if (use_tc && p.Q <= kTcNQ) {
     const size_t tc_smem_bytes = 2 * kTcTileBytes + kTcNQ * kD * 2 + 4 * kTcNQ * kTcTile * 2 + 4 * kTcNQ * 4 + 64;
     cudaError_t e;
@@ -1768,3 +1799,10 @@ extern "C" int kvc_set_attention_pdl(int mode) {
   return KVC_OK;
 }
 extern "C" int kvc_get_attention_pdl(void) { return attention_pdl_mode(); }
+
+extern "C" int kvc_set_attention_v2_mode(int mode) {
+  KVC_REQUIRE(mode >= 0 && mode <= 2, KVC_ERR_INVALID, "attention v2 mode must be 0, 1 or 2, got %d", mode);
+  g_v2_mode = mode;
+  return KVC_OK;
+}
+extern "C" int kvc_get_attention_v2_mode(void) { attention_v2_mode(); return g_v2_mode; }
