@@ -89,7 +89,25 @@ def main():
         "warp_life_us_median": np.median((g7 - g0)[sel]) / 1e3,
         "warp_life_us_p95": np.percentile((g7 - g0)[sel], 95) / 1e3,
     }
-    print(json.dumps({"pdl": a.pdl, "launch_span_us_median": float(np.median(span[2:])),
+    # where does the exit skew come from?  per-SM exit time of one mid-step layer, relative to the layer's first
+    # warp entry; SM ids are dealt to GPCs round-robin-ish, so a pattern over the id shows a topology effect
+    lay = min(L - 1, 8)
+    smid = (t[lay, :, 6] >> 48) & 0xffff
+    rel_exit = (g7[lay] - g0[lay].min()) / 1e3
+    rel_entry = (g0[lay] - g0[lay].min()) / 1e3
+    per_sm = {}
+    for sm, ex in zip(smid.tolist(), rel_exit.tolist()):
+        per_sm.setdefault(sm, []).append(ex)
+    sm_last = {k: max(v) for k, v in per_sm.items()}
+    sm_cnt = {k: len(v) for k, v in per_sm.items()}
+    order = sorted(sm_last, key=lambda k: sm_last[k])
+    skew = {"layer": lay, "exit_us_percentiles": [float(np.percentile(rel_exit, q)) for q in (0, 5, 25, 50, 75, 95, 100)],
+            "entry_us_percentiles": [float(np.percentile(rel_entry, q)) for q in (0, 50, 95, 100)],
+            "sm_last_exit_percentiles": [float(np.percentile(list(sm_last.values()), q)) for q in (0, 25, 50, 75, 100)],
+            "fastest_sms": [(k, round(sm_last[k], 1), sm_cnt[k]) for k in order[:10]],
+            "slowest_sms": [(k, round(sm_last[k], 1), sm_cnt[k]) for k in order[-10:]],
+            "warps_per_sm_hist": {str(c): int(sum(1 for v in sm_cnt.values() if v == c)) for c in sorted(set(sm_cnt.values()))}}
+    print(json.dumps({"pdl": a.pdl, "skew": skew, "launch_span_us_median": float(np.median(span[2:])),
                       "launch_period_us_median": float(np.median(period[2:])),
                       "start_skew_us_median": float(np.median([r["last_start_us"] - r["start_us"] for r in rows[2:]])),
                       "exit_skew_us_median": float(np.median([r["end_us"] - r["first_exit_us"] for r in rows[2:]])),

@@ -457,7 +457,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 template <bool BF16, int NT, int MODE, bool ALIBI>
 __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kernel(AttnParams p, float* scratch,
                                                                                    int scratch_tokens,
-                                                                                   int smem_logit_tokens, int pdl) {
+                                                                                   int smem_logit_tokens, int pdl, int pair) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr bool kWrite = (MODE == kModeFusedWrite || MODE == kModeFusedWriteMove);
   constexpr bool kMove = (MODE == kModeFusedWriteMove);
@@ -493,6 +493,73 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   __syncthreads();
 
   // =========================== producer warp ===========================
+  if (wid == kConsumers && pair) {
+    // PAIR mode: whole 4 KB blocks per bulk copy (K lo + hi, V lo + hi are adjacent in global memory and in the
+    // ring): half as many copies and barrier transactions; three producer lanes per ring, lane j owns slot pair j
+    const int w = lane / 3, j = lane - 3 * w;
+    const int item = blockIdx.x * kConsumers + w;
+    if (w >= kConsumers || item >= num_items) return;
+    const int* __restrict__ bt = p.block_tables + (int64_t)item * p.max_num_blocks_per_seq;
+    const int bt_spec0 = bt[0], bt_spec1 = (p.max_num_blocks_per_seq > 1) ? bt[1] : 0;
+    const int ctx = p.context_lens[item];
+    const int64_t pdp = kMove ? p.pend_dst[item] : -1;
+    const int pd_phys = pdp >= 0 ? (int)(pdp >> 4) : -1;
+    bool patched = pd_phys < 0;
+    const int nblk = (ctx + kB - 1) / kB;
+    if (nblk == 0) return;
+    const uint16_t* __restrict__ kc = reinterpret_cast<const uint16_t*>(p.k_cache);
+    const uint16_t* __restrict__ vc = reinterpret_cast<const uint16_t*>(p.v_cache);
+    const uint32_t ring = smem_u32(ring_of(w)), full = full_of(w), empty = empty_of(w);
+    const unsigned lanes = __activemask();
+    const int npairs = 2 * nblk;
+    bool skip_last = false;
+    if (kWrite) {
+      const int64_t nslot = p.slot_mapping[item];
+      skip_last = nslot >= 0 && (nslot & (kB - 1)) == 0 && ctx == (nblk - 1) * kB + 1;
+    }
+    // pair order: K(0); then per block b: K(b+1) (if any), V(b)
+    auto decode = [&](int q, int& isv, int& blk) {
+      if (q == 0) { isv = 0; blk = 0; return; }
+      const int t = q - 1, b = t >> 1, r = t & 1;
+      if (b < nblk - 1) { isv = r; blk = isv ? b : b + 1; }
+      else { isv = 1; blk = nblk - 1; }
+    };
+    int q = j;
+    int isv = 0, blk = 0, phys = 0;
+    if (q < npairs) { decode(q, isv, blk); phys = (blk == 0) ? bt_spec0 : bt_spec1; }  // first pairs: blk <= 1
+    constexpr int kNPair = kNUnit / 2;
+    while (__any_sync(lanes, q < npairs)) {
+      if (q < npairs) {
+        const int sp = q % kNPair, round = q / kNPair;
+        bool ready = true;
+        if (round > 0) {  // the slot pair is free once its second unit has been released
+          uint32_t ok;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(empty + 8 * (2 * sp + 1)), "r"((uint32_t)((round - 1) & 1)) : "memory");
+          ready = ok != 0;
+        }
+        if (kMove && ready && !patched && phys == pd_phys) {
+          uint32_t ok;
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(patched_of(w)), "r"(0u) : "memory");
+          patched = ok != 0;
+          ready = patched;
+        }
+        if (ready) {
+          if (skip_last && blk == nblk - 1) {
+            mbar_arrive(full + 8 * (2 * sp));
+          } else {
+            const uint16_t* src = (isv ? vc : kc) + (int64_t)phys * p.kv_block_stride;
+            mbar_expect_tx(full + 8 * (2 * sp), 2 * kUnitBytes);
+            bulk_g2s(ring + 2 * sp * kUnitBytes, src, 2 * kUnitBytes, full + 8 * (2 * sp));
+          }
+          q += kNPair;
+          if (q < npairs) { decode(q, isv, blk); phys = bt[blk]; }
+        }
+      }
+    }
+    return;
+  }
   if (wid == kConsumers) {
     // four producer lanes per consumer ring: lane (w, j) issues units u = j, j+4, j+8, ... of ring w, so up
     // to 28 bulk copies go out per polling pass and no lane ever blocks (test_wait, not try_wait).
@@ -706,8 +773,9 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
   const int voff = g * (kB * 2) + c * 8;
   int slot = 0;
   uint32_t phase = 0;
+  const int full_mask = pair ? ~1 : ~0;  // pair mode: the two units of a block complete on the first one's barrier
   auto next_unit = [&]() -> const unsigned char* {  // wait for the next unit of the ring
-    mbar_wait(full + 8 * slot, phase);
+    mbar_wait(full + 8 * (slot & full_mask), phase);
     return ring + slot * kUnitBytes;
   };
   auto release_unit = [&]() {  // fragments of the current unit are in registers on every lane
@@ -1144,6 +1212,8 @@ __global__ void __launch_bounds__(128) paged_attention_tc_kernel(AttnParams p) {
   const unsigned char* __restrict__ vc = reinterpret_cast<const unsigned char*>(p.v_cache);
   const int64_t block_bytes = p.kv_block_stride * 2;
 
+  __shared__ int s_bt[kPartition / kB];   // the partition's block ids: no dependent table load per copy
+  if (tid < kPartition / kB) s_bt[tid] = (blk_begin + tid < blk_end) ? bt[blk_begin + tid] : 0;
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[0])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[1])));
@@ -1189,7 +1259,7 @@ __global__ void __launch_bounds__(128) paged_attention_tc_kernel(AttnParams p) {
       }
       const int b = blk_begin + t * 8 + bi;
       if (b < blk_end) {
-        const unsigned char* src = (is_v ? vc : kc) + (int64_t)bt[b] * block_bytes + src_off;
+        const unsigned char* src = (is_v ? vc : kc) + (int64_t)s_bt[b - blk_begin] * block_bytes + src_off;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + dst_off)), "l"(src) : "memory");
       } else {
         *reinterpret_cast<uint4*>(dst + dst_off) = make_uint4(0, 0, 0, 0);   // beyond the context: zero operand
@@ -1227,6 +1297,7 @@ __global__ void __launch_bounds__(128) paged_attention_tc_kernel(AttnParams p) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   };
   const int nstream = 2 * ntiles;
+  __syncthreads();   // s_bt
   issue_tile(0);
   issue_tile(1);   // nstream >= 2
   publish();       // Q tile, TMEM slot
@@ -1282,7 +1353,7 @@ __global__ void __launch_bounds__(128) paged_attention_tc_kernel(AttnParams p) {
           int64_t slot = 0;
           bool rec = false;
           if (live && p.record) {
-            slot = (int64_t)bt[tok >> 4] * kB + (tok & 15);
+            slot = (int64_t)s_bt[(tok >> 4) - blk_begin] * kB + (tok & 15);
             rec = p.kv_position[slot] <= max_pos;   // reference :309
           }
 #pragma unroll
@@ -1385,56 +1456,97 @@ __global__ void __launch_bounds__(128) paged_attention_tc_kernel(AttnParams p) {
 // -----------------------------------------------------------------------------
 // v2 reduce.  grid (num_kv_heads, num_seqs), 128 threads.  reference :525-652.
 // -----------------------------------------------------------------------------
+// grid (num_kv_heads, num_seqs, max_partitions): every CTA derives the final per-query-head (max, 1 / sum) from the
+// partitions' statistics (Q x nparts values, one warp lane per partition), the CTA of partition 0 reduces the
+// output, and EVERY CTA finalises the recorded probabilities of its own 512 tokens -- all Q columns of a token at
+// once, 8 tokens per thread in flight -- instead of one CTA walking the whole context Q times behind dependent loads.
 template <bool BF16>
 __global__ void __launch_bounds__(kAttnThreads) paged_attention_reduce_kernel(AttnParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* wts = reinterpret_cast<float*>(smem_raw);  // [max_partitions] rescaled exp sums
-  __shared__ float s_M, s_inv;
-  const int h = blockIdx.x, s = blockIdx.y, tid = threadIdx.x;
+  float* wts = reinterpret_cast<float*>(smem_raw);  // [Q][max_partitions] rescaled exp sums * 1 / sum
+  __shared__ float s_M[16], s_inv[16];
+  const int h = blockIdx.x, s = blockIdx.y, part = blockIdx.z, tid = threadIdx.x;
+  const int lane = tid % kWarp, wid = tid / kWarp;
   const int H = p.num_kv_heads, Q = p.Q;
   const int seq_head = s * H + h;
   const int ctx = p.context_lens[seq_head];
   const int nparts = (ctx + kPartition - 1) / kPartition;
+  if (part > 0 && (part >= nparts || !p.record)) return;   // CTA-uniform
   const int* __restrict__ bt = p.block_tables + (int64_t)seq_head * p.max_num_blocks_per_seq;
   const int max_pos = p.last_position[s] - p.kv_metric_buffer_len[s];
-  for (int q = 0; q < Q; ++q) {
-    const int qh = h * Q + q;
-    const int64_t base = ((int64_t)s * p.num_heads + qh) * p.max_partitions;
-    __syncthreads();
-    if (tid == 0) {
-      float M = -INFINITY;
-      for (int j = 0; j < nparts; ++j) M = fmaxf(M, p.max_logits[base + j]);
-      float L = 0.f;
-      for (int j = 0; j < nparts; ++j) {
-        const float r = p.exp_sums[base + j] * expf(p.max_logits[base + j] - M);  // :606-611
-        wts[j] = r;
-        L += r;
-      }
-      s_M = M;
-      s_inv = __fdividef(1.f, L + 1e-6f);  // :614
+  // ---- per query head: M = max_j m_j, L = sum_j l_j exp(m_j - M)  (reference :606-614); warp w takes heads w, w+4, ..
+  for (int q = wid; q < Q; q += kAttnWarps) {
+    const int64_t base = ((int64_t)s * p.num_heads + h * Q + q) * p.max_partitions;
+    float M = -INFINITY;
+    for (int j = lane; j < nparts; j += kWarp) M = fmaxf(M, p.max_logits[base + j]);
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, d));
+    float L = 0.f;
+    for (int j = lane; j < nparts; j += kWarp) {
+      const float r = p.exp_sums[base + j] * expf(p.max_logits[base + j] - M);
+      wts[q * p.max_partitions + j] = r;
+      L += r;
     }
-    __syncthreads();
-    {
-      const int d = tid;
-      float acc = 0.f;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) L += __shfl_xor_sync(0xffffffffu, L, d);
+    if (lane == 0) {
+      s_M[q] = M;
+      s_inv[q] = __fdividef(1.f, L + 1e-6f);  // :614
+    }
+  }
+  __syncthreads();
+  if (part == 0) {
+    const int d = tid;
+    for (int q = 0; q < Q; ++q) {
+      const int qh = h * Q + q;
+      const int64_t base = ((int64_t)s * p.num_heads + qh) * p.max_partitions;
       const uint16_t* tp = reinterpret_cast<const uint16_t*>(p.tmp_out) + base * kD;
+      float acc = 0.f;
       if (nparts == 1) {
         acc = from_bits16<BF16>(tp[d]);  // reference :555-562: plain copy
       } else {
+        const float inv = s_inv[q];
         for (int j = 0; j < nparts; ++j)
-          acc += from_bits16<BF16>(tp[(int64_t)j * kD + d]) * wts[j] * s_inv;  // :625
+          acc += from_bits16<BF16>(tp[(int64_t)j * kD + d]) * wts[q * p.max_partitions + j] * inv;  // :625
       }
       reinterpret_cast<uint16_t*>(p.out)[((int64_t)s * p.num_heads + qh) * kD + d] = to_bits16<BF16>(acc);
     }
-    if (p.record && nparts > 0) {
-      const float M = s_M, inv = s_inv;
-      for (int t = tid; t < ctx; t += kAttnThreads) {
-        const int64_t slot = (int64_t)bt[t / kB] * kB + t % kB;
-        if (p.kv_position[slot] <= max_pos) {
-          const float lg = p.metric[slot * Q + q];
-          p.metric[slot * Q + q] = __expf(lg - M) * inv;
+  }
+  if (p.record && part < nparts) {
+    const int t_begin = part * kPartition, t_end = min(ctx, t_begin + kPartition);
+    constexpr int U = 4;  // tokens per thread in flight (512 tokens / 128 threads)
+    int64_t slot[U];
+    int pos[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t_begin + u * kAttnThreads + tid;
+      slot[u] = (t < t_end) ? (int64_t)bt[t / kB] * kB + t % kB : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) pos[u] = (slot[u] >= 0) ? p.kv_position[slot[u]] : 0x7fffffff;
+    if (Q == 4) {  // one 16-byte access per token
+      float4 lg[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (pos[u] <= max_pos) lg[u] = *reinterpret_cast<const float4*>(p.metric + slot[u] * 4);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (pos[u] <= max_pos) {
+          float4 o;
+          o.x = __expf(lg[u].x - s_M[0]) * s_inv[0];
+          o.y = __expf(lg[u].y - s_M[1]) * s_inv[1];
+          o.z = __expf(lg[u].z - s_M[2]) * s_inv[2];
+          o.w = __expf(lg[u].w - s_M[3]) * s_inv[3];
+          *reinterpret_cast<float4*>(p.metric + slot[u] * 4) = o;
         }
-      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (pos[u] <= max_pos)
+          for (int q = 0; q < Q; ++q) {
+            const float lg = p.metric[slot[u] * Q + q];
+            p.metric[slot[u] * Q + q] = __expf(lg - s_M[q]) * s_inv[q];
+          }
     }
   }
 }
@@ -1533,6 +1645,7 @@ static int launch_stream(const AttnParams& p, int num_seqs, float* scratch, int 
   // mode 3 lets consecutive launches overlap completely.  The fused modes park raw logits in the caller's
   // workspace when they do not fit in shared memory, and consecutive launches may be handed the same
   // workspace: the wait then has to come before the first logit is parked (mode 2).
+  static const int pair = [] { const char* e_ = getenv("KVC_ATTN_PAIR"); return e_ ? atoi(e_) : 1; }();  // 4 KB copies
   int pdl = pdl_mode;
   const bool global_logits = (MODE == kModeFused || MODE == kModeFusedWrite || MODE == kModeFusedWriteMove) &&
                              smem_logit_tokens == 0;
@@ -1540,11 +1653,11 @@ static int launch_stream(const AttnParams& p, int num_seqs, float* scratch, int 
   if (p.alibi_slopes) {
     auto kern = paged_attention_stream_kernel<BF16, NT, MODE, true>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, p, scratch, scratch_tokens, smem_logit_tokens, pdl);
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, p, scratch, scratch_tokens, smem_logit_tokens, pdl, pair);
   } else {
     auto kern = paged_attention_stream_kernel<BF16, NT, MODE, false>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, p, scratch, scratch_tokens, smem_logit_tokens, pdl);
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, p, scratch, scratch_tokens, smem_logit_tokens, pdl, pair);
   }
   if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "paged attention (stream) launch: %s", cudaGetErrorString(e));
   KVC_CHECK_LAUNCH("paged_attention_stream_kernel");
@@ -1677,11 +1790,14 @@ extern "C" int kvc_paged_attention_v2(
     rc = dispatch_attention<kModeV2>(p, num_seqs, p.max_partitions, 0, dtype, st);
     if (rc != KVC_OK) return rc;
   }
-  const size_t smem = sizeof(float) * (size_t)p.max_partitions;
+  const size_t smem = sizeof(float) * (size_t)p.max_partitions * p.Q;
+  KVC_REQUIRE(smem <= 48 * 1024, KVC_ERR_UNSUPPORTED, "paged attention v2: %d partitions x %d query heads per kv head",
+              p.max_partitions, p.Q);
+  const dim3 rgrid(num_kv_heads, num_seqs, record_kv_metrics ? p.max_partitions : 1);
   if (dtype == KVC_F16)
-    paged_attention_reduce_kernel<false><<<dim3(num_kv_heads, num_seqs), kAttnThreads, smem, st>>>(p);
+    paged_attention_reduce_kernel<false><<<rgrid, kAttnThreads, smem, st>>>(p);
   else
-    paged_attention_reduce_kernel<true><<<dim3(num_kv_heads, num_seqs), kAttnThreads, smem, st>>>(p);
+    paged_attention_reduce_kernel<true><<<rgrid, kAttnThreads, smem, st>>>(p);
   KVC_CHECK_LAUNCH("paged_attention_reduce_kernel");
   return KVC_OK;
 }
