@@ -442,13 +442,15 @@ def gen_prefill_metrics():
         ([200, 50], 2, 2, torch.float16, 64, [0, 7], True, False, True),                  # MHA, 64 observed
         ([260], 4, 2, torch.float16, 100, [16], False, False, True),                      # 100 observed, no l2
         ([600, 140], 4, 1, torch.float16, 32, [0, 0], True, False, True),                 # several key splits
+        ([500, 90, 260], 4, 2, torch.float16, 200, [0, 4, 30], True, False, True),        # > 128 observed: 2 row chunks
+        ([700], 8, 2, torch.bfloat16, 300, [12], True, True, True),                       # 3 chunks, Q=4, average
     ]
     for k, (lens, Hq, H, dtype, n_obs, buf, use_l2, use_avg, use_pool) in enumerate(cfgs):
         T, D, Q = sum(lens), 128, Hq // H
         scale = float(D ** -0.5)
         q = torch.randn((T, Hq, D), generator=g)
         key = torch.randn((T, H, D), generator=g)
-        if k != len(cfgs) - 1:
+        if k != 5:
             # values on a 1/8 grid: every dot product is exact in fp32 whatever the summation order, so
             # the fp16/bf16 rounding of the logits is reproducible bit for bit (and the file compresses)
             q, key = (q * 8).round() / 8, (key * 8).round() / 8

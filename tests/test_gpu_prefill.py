@@ -86,6 +86,8 @@ def test_aggregate_prefill_golden(capi, name):
     (2, [2049, 511, 3], 8, 2, True, 32, [5, 0, 1], True, False, True),
     (3, [777, 1300], 16, 2, False, 48, [0, 100], True, True, True),  # Q=8, 64-row heads, atomics
     (4, [4097], 2, 2, False, 128, [0], False, False, False),        # one query head per tile
+    (5, [1500, 300], 16, 2, True, 500, [0, 20], True, False, True),   # 500 observed queries: 4 row chunks per head, Q=8
+    (6, [900], 4, 4, False, 4096, [0], True, True, True),             # the reference's whole observation chunk
 ])
 def test_prefill_metrics_random_vs_oracle(capi, O, cfg):
     seed, lens, Hq, H, bf, n_obs, buf, l2, avg, pool = cfg
@@ -129,7 +131,7 @@ def test_prefill_torch_op_surface_and_errors(capi):
     with pytest.raises(RuntimeError, match="Unsupported head size"):
         ops.prefill_kv_metrics(q[:, :, :64].contiguous(), k[:, :, :64].contiguous(), lens, 1.0, buf)
     with pytest.raises(RuntimeError, match="Unsupported prefill_observed_queries"):
-        ops.prefill_kv_metrics(q, k, lens, 1.0, buf, n_observed=4096)
+        ops.prefill_kv_metrics(q, k, lens, 1.0, buf, n_observed=5000)
     # empty prefill batch is a no-op
     e = ops.prefill_kv_metrics(q[:0], k[:0], [], 1.0, buf[:0])
     assert e.shape == (0, q.shape[1])

@@ -47,6 +47,7 @@ struct PrefillParams {
   float* raw;              // [Hq, T] column sums before the max-pool
   int64_t q_stride, k_stride;  // token strides in elements
   int num_seqs, T, H, Q, n_observed, np, qt, mtiles, tiles_per_split, max_splits;
+  int nchunks;             // 128-row query tiles per query head (n_observed > 128: np = 128, qt = 1)
   float scale;
   int use_l2, use_average;
 };
@@ -131,9 +132,11 @@ __global__ void __launch_bounds__(128) prefill_metrics_kernel(PrefillParams p) {
   const int n_obs = min(P, p.n_observed);
   const int q_offset = P - n_obs;
 
-  // this thread's query row
-  const int head_local = tid / p.np, qi = tid % p.np;
-  const int qh_in_group = mt * p.qt + head_local;
+  // this thread's query row.  n_observed <= 128: a tile holds qt query heads x np rows; n_observed > 128: a tile
+  // is one 128-query chunk of ONE query head (mtiles = Q * nchunks), the column sums of the chunks add up
+  const int chunk = mt % p.nchunks, mtq = mt / p.nchunks;
+  const int head_local = tid / p.np, qi = chunk * kTileRows + tid % p.np;
+  const int qh_in_group = mtq * p.qt + head_local;
   const bool row_valid = (qi < n_obs) && (head_local < p.qt) && (qh_in_group < p.Q);
   const int limit = qi + q_offset;  // last key the query may attend to (causal)
 
@@ -151,8 +154,8 @@ __global__ void __launch_bounds__(128) prefill_metrics_kernel(PrefillParams p) {
     const unsigned char* qbase = reinterpret_cast<const unsigned char*>(p.query);
     const int np = p.np, qt = p.qt, Q = p.Q;
     stage_tile(sQ, [&](int r) -> const unsigned char* {
-      const int hl = r / np, q = r % np;
-      const int qh = mt * qt + hl;
+      const int hl = r / np, q = chunk * kTileRows + r % np;
+      const int qh = mtq * qt + hl;
       if (q >= n_obs || hl >= qt || qh >= Q) return nullptr;
       return qbase + ((int64_t)(start + q_offset + q) * p.q_stride + (int64_t)(h * Q + qh) * kHeadDim) * 2;
     });
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(128) prefill_metrics_kernel(PrefillParams p) {
     invL = (l > 0.f) ? 1.f / l : 0.f;
     metric_limit = row_valid ? min(limit, limit - p.buffer_len[seq]) : -1;
   }
-  const bool head_valid = (warp * 32 / p.np < p.qt) && (mt * p.qt + warp * 32 / p.np < p.Q);
+  const bool head_valid = (warp * 32 / p.np < p.qt) && (mtq * p.qt + warp * 32 / p.np < p.Q);
 
   uint32_t phases = 0u;  // bit b = parity to wait for on bars[b]
   for (int t = t0; t < t1; ++t) {
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(128) prefill_metrics_kernel(PrefillParams p) {
         if (head_valid && kg < P) {
           float val = v[0];
           if (p.use_average) val *= (float)(kg + 1) / (float)n_obs;
-          float* dst = p.raw + (int64_t)(h * p.Q + mt * p.qt + warp * 32 / p.np) * p.T + start + kg;
+          float* dst = p.raw + (int64_t)(h * p.Q + mtq * p.qt + warp * 32 / p.np) * p.T + start + kg;
           if (p.np == 32) *dst = val; else atomicAdd(dst, val);
         }
       }
@@ -341,6 +344,14 @@ __global__ void __launch_bounds__(256) aggregate_prefill_kernel(float* __restric
 }
 
 static inline int pad_observed(int n_observed) { return n_observed <= 32 ? 32 : (n_observed <= 64 ? 64 : 128); }
+// 128-row tiles per (kv head): up to 128 observed queries several query heads share a tile, beyond that every
+// query head takes ceil(n_observed / 128) tiles
+static inline int prefill_mtiles(int Q, int n_observed, int* nchunks) {
+  const int np = pad_observed(n_observed), qt = kTileRows / np;
+  *nchunks = n_observed <= kTileRows ? 1 : (n_observed + kTileRows - 1) / kTileRows;
+  return n_observed <= kTileRows ? (Q + qt - 1) / qt : Q * *nchunks;
+}
+constexpr int kMaxObserved = 4096;  // the reference's max_observed_block_size: one observation chunk (flash_attn.py:1130)
 
 }  // namespace kvc
 
@@ -349,11 +360,11 @@ using namespace kvc;
 extern "C" size_t kvc_prefill_kv_metrics_workspace_bytes(int num_tokens, int num_seqs, int num_heads,
                                                          int num_kv_heads, int n_observed, int max_prompt_len) {
   if (num_tokens <= 0 || num_seqs <= 0 || num_heads <= 0 || num_kv_heads <= 0 || n_observed <= 0 ||
-      n_observed > 128 || max_prompt_len <= 0)
+      n_observed > kMaxObserved || max_prompt_len <= 0)
     return 0;
   const int Q = num_heads / num_kv_heads;
-  const int np = pad_observed(n_observed), qt = kTileRows / np;
-  const int mtiles = (Q + qt - 1) / qt;
+  int nchunks;
+  const int mtiles = prefill_mtiles(Q, n_observed, &nchunks);
   const int tiles = (max_prompt_len + kTileKeys - 1) / kTileKeys;
   const int tps = 4;
   const int max_splits = (tiles + tps - 1) / tps;
@@ -371,8 +382,9 @@ extern "C" int kvc_prefill_kv_metrics(
   KVC_REQUIRE(head_size == kHeadDim, KVC_ERR_UNSUPPORTED, "Unsupported head size: %d", head_size);
   KVC_REQUIRE(dtype == KVC_F16 || dtype == KVC_BF16, KVC_ERR_UNSUPPORTED,
               "Unsupported data type for prefill metrics: %d", dtype);
-  KVC_REQUIRE(n_observed >= 1 && n_observed <= 128, KVC_ERR_UNSUPPORTED,
-              "Unsupported prefill_observed_queries: %d (1..128)", n_observed);
+  KVC_REQUIRE(n_observed >= 1 && n_observed <= kMaxObserved, KVC_ERR_UNSUPPORTED,
+              "Unsupported prefill_observed_queries: %d (1..%d: one observation chunk of the reference)", n_observed,
+              kMaxObserved);
   KVC_REQUIRE(num_kv_heads > 0 && num_heads > 0 && num_heads % num_kv_heads == 0, KVC_ERR_INVALID,
               "prefill_kv_metrics: num_heads %d not a multiple of num_kv_heads %d", num_heads, num_kv_heads);
   KVC_REQUIRE(num_tokens >= 0 && num_seqs >= 0 && max_prompt_len >= 0, KVC_ERR_INVALID,
@@ -393,7 +405,7 @@ extern "C" int kvc_prefill_kv_metrics(
   p.q_stride = q_stride; p.k_stride = k_stride;
   p.num_seqs = num_seqs; p.T = num_tokens; p.H = num_kv_heads; p.Q = num_heads / num_kv_heads;
   p.n_observed = n_observed; p.np = pad_observed(n_observed); p.qt = kTileRows / p.np;
-  p.mtiles = (p.Q + p.qt - 1) / p.qt;
+  p.mtiles = prefill_mtiles(p.Q, n_observed, &p.nchunks);
   const int tiles = (max_prompt_len + kTileKeys - 1) / kTileKeys;
   p.tiles_per_split = 4;
   p.max_splits = (tiles + p.tiles_per_split - 1) / p.tiles_per_split;
