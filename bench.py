@@ -199,6 +199,21 @@ def cpu_step_rate(args, seconds=None, steps=None, warmup=1):
                       f"{reps} steps in {dt * reps:.1f} s"}, dt
 
 
+def cpu_reference_kernels(args, seconds):
+    """The reference's OWN CPU kernels (vLLM csrc/cpu paged_attention_v1 + reshape_and_cache, oracle/_ref/
+    _vllm_cpu_ref.so) on the per-layer attention part of the step: what exists of "the reference's CPU path" for
+    this hot path (the fork has no CPU build of the KV-Compress ops).  Reported next to cpu_baseline (the full-step
+    port); see oracle/cpu_reference_step.py."""
+    try:
+        from oracle import cpu_reference_step as C
+        if not C.available():
+            return {"unavailable": "oracle/_ref/_vllm_cpu_ref.so not built"}
+        return C.measure(num_seqs=args.cpu_sample_seqs, num_layers=args.layers, seconds=seconds,
+                         threads=os.cpu_count())
+    except Exception as ex:  # pragma: no cover
+        return {"error": repr(ex)}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the oracle port of the step on the host cores (rank 0 only).  The reference has no CPU
     build of these ops (csrc/cpu registers none of them), so the port is the CPU arm."""
@@ -213,6 +228,7 @@ def run_reference(args, rank, world):
         "dtype": "f16", "data": "synthetic",
         "config": workload_config(args, args.batch * args.gpus),
         "cpu_baseline": base,
+        "cpu_reference_kernels": cpu_reference_kernels(args, seconds=5),
         "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -490,6 +506,7 @@ def main():
             line["reference_cuda"] = {"error": repr(ex)}
     if not args.no_cpu_baseline and world == 1:   # reported at N=1 only (rank 0's host cores)
         line["cpu_baseline"] = cpu_step_rate(args, seconds=10)[0]
+        line["cpu_reference_kernels"] = cpu_reference_kernels(args, seconds=5)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
