@@ -191,3 +191,66 @@ def test_decode_chain_vs_reference_kernels_and_cpu_oracle(case, pdl):
                                       n(k_r.view(torch.int16))), tag
     prod.check_status()
     assert total_moves > 0
+
+
+def test_full_scale_step_vs_reference_kernels():
+    """BASELINE config 2 at FULL scale (256 sequences x 32 layers x 8 kv heads = 65 536 heads, 9.4 M slots per
+    compression call): four production steps against the reference's own CUDA kernels on the same logical cache.
+    Eviction / freed-block / move counts and context lengths bit-equal for every head, the move lists of a sample of
+    heads equal as logical pairs, outputs within 1e-3."""
+    from oracle import ref_ops
+    from vllm_kvcompress_b200.engine import DecodeHotPath, HotPathConfig
+    if not ref_ops.available():
+        pytest.skip("oracle/_ref/_kvc_ref.so not built")
+    dev = torch.device("cuda", 0)
+    kw = dict(num_seqs=256, num_layers=32, seed=31)       # HotPathConfig defaults = the benchmark's shape
+    prod = DecodeHotPath(HotPathConfig(**kw), dev)
+    ref = DecodeHotPath(HotPathConfig(allocator="static", selection="chain", fused_metrics=False,
+                                      fused_cache_write=False, deferred_append=False, **kw), dev,
+                        ops_module=ref_ops.RefOps())
+    cfg = prod.cfg
+    S, L, H, Q, D = cfg.num_seqs, cfg.num_layers, cfg.num_kv_heads, cfg.queries_per_kv, cfg.head_size
+    heads = L * S * H
+    nb0 = cfg.max_cache_tokens // B
+    bt_p = prod.st.block_tables.view(heads, -1)
+    bt_r = ref.st.block_tables.view(heads, -1)
+    for name in ("k_cache", "v_cache", "kv_metrics", "kv_position"):
+        for h0 in range(0, heads, 8192):
+            getattr(prod.st, name)[bt_p[h0:h0 + 8192, :nb0].long()] = getattr(ref.st, name)[bt_r[h0:h0 + 8192, :nb0].long()]
+    g = torch.Generator(device=dev).manual_seed(77)
+    qkv = (torch.rand((L, S, (H * Q + 2 * H) * D), generator=g, device=dev) - 0.5).to(cfg.dtype)
+    out_p = torch.zeros((L, S, H * Q * D), device=dev, dtype=cfg.dtype)
+    out_r = torch.zeros_like(out_p)
+    n = lambda t: t.detach().cpu().numpy()
+    rng = np.random.RandomState(5)
+    total_moves = 0
+    for i in range(4):    # step 0 has nothing to evict (every head exactly at max_cache_tokens)
+        ctx_before = n(ref.st.context_lens).copy()
+        bt_before = n(prod.st.block_tables).copy()
+        prod.step(qkv, out_p)
+        ref.step(qkv, out_r)
+        torch.cuda.synchronize()
+        tag = f"full scale step {i}"
+        assert torch.equal(prod.st.context_lens, ref.st.context_lens), tag
+        assert torch.equal(prod.evicted_kv_count, ref.evicted_kv_count), tag
+        assert torch.equal(prod.evicted_block_count, ref.evicted_block_count), tag
+        assert torch.equal(prod.moves_count, ref.moves_count), tag
+        total_moves += int(ref.moves_count.sum())
+        assert torch.allclose(out_p.float(), out_r.float(), atol=1e-3, rtol=1e-2), tag
+        # move lists of 300 random heads, as logical (dst, src) pairs
+        alloc = ((ctx_before + B - 1) // B * B).transpose(1, 0, 2).reshape(-1)
+        offs = (np.cumsum(alloc) - alloc).astype(np.int64).reshape(S, L, H)
+        mp, mr = n(prod.cache_moves), n(ref.cache_moves)
+        cnt = n(ref.moves_count)
+        bt_ref = n(ref.st.block_tables)
+        for _ in range(300):
+            s_, l_, h_ = rng.randint(S), rng.randint(L), rng.randint(H)
+            c, o = int(cnt[s_, l_, h_]), int(offs[s_, l_, h_])
+            def logical(mv, row):
+                inv = {}
+                for j, b in enumerate(row):
+                    inv.setdefault(int(b), j)
+                return [(inv[int(d) // B] * B + int(d) % B, inv[int(sr) // B] * B + int(sr) % B) for d, sr in mv]
+            assert logical(mp[o:o + c], bt_before[l_, s_, h_]) == logical(mr[o:o + c], bt_ref[l_, s_, h_]), tag
+    assert total_moves > 100000
+    prod.check_status()
