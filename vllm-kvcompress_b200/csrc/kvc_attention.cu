@@ -1102,28 +1102,57 @@ __global__ void __launch_bounds__(kStreamThreads, 2) paged_attention_stream_kern
         }
       }
     } else {
+      // token-major like the shared-memory path: a lane finalises four consecutive tokens (one 16-byte position
+      // load, Q independent 16-byte logit loads from the L2-resident scratch row, all issued before the first use),
+      // two such groups per pass, and issues one 16-byte reduction per group
       const float* lgi = scratch + (int64_t)item * Q * scratch_tokens;
-      for (int t0 = 0; t0 < ctx; t0 += U * kWarp) {
-        int64_t sl[U];
-        int pos[U];
+      const int ntok = nblk * kB;
+      constexpr int G = (NT == 1) ? 2 : 1;   // register budget: G * NT * 8 float4 of logits in flight per lane
+      for (int t0 = 0; t0 < ntok; t0 += G * 4 * kWarp) {
+        int t4[G];
+        int64_t slot4[G];
+        int4 pos4[G];
+        float4 lgv[G][NT * 8];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int t = t0 + u * kWarp + lane;
-          sl[u] = (t < ctx) ? (int64_t)bt[t / kB] * kB + t % kB : -1;
+        for (int u = 0; u < G; ++u) {
+          t4[u] = t0 + 4 * (lane + kWarp * u);
+          const bool valid = t4[u] < ntok;
+          const int b = valid ? (t4[u] >> 4) : 0;
+          // b differs between lanes here: every lane executes the shuffle, entries beyond 32 come from the table
+          const int sh = __shfl_sync(0xffffffffu, my_bt, b & (kWarp - 1));
+          const int64_t phys = (b < kWarp) ? (int64_t)sh : (int64_t)bt[b];
+          slot4[u] = valid ? phys * kB + (t4[u] & (kB - 1)) : -1;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) pos[u] = (sl[u] >= 0) ? p.kv_position[sl[u]] : 0x7fffffff;
+        for (int u = 0; u < G; ++u) {
+          pos4[u] = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
+          if (slot4[u] >= 0) {
+            pos4[u] = *reinterpret_cast<const int4*>(p.kv_position + slot4[u]);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (sl[u] >= 0 && pos[u] <= max_pos) {
-            const int t = t0 + u * kWarp + lane;
-            float acc = 0.f;
-            for (int q = 0; q < Q; ++q) {
-              const float pr = __expf(lgi[q * scratch_tokens + t] - mi[q * 2]) * mi[q * 2 + 1];
-              acc += pr * pr;
-            }
-            // every slot belongs to exactly one warp: a fire-and-forget reduction, no read-back
-            atomicAdd(&p.metric[sl[u]], acc);
+            for (int q = 0; q < NT * 8; ++q)
+              if (q < Q) lgv[u][q] = *reinterpret_cast<const float4*>(lgi + (int64_t)q * scratch_tokens + t4[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+          if (slot4[u] >= 0) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int q = 0; q < NT * 8; ++q)
+              if (q < Q) {
+                const float M = mi[2 * q], iv = mi[2 * q + 1];
+                const float p0 = __expf(lgv[u][q].x - M) * iv, p1 = __expf(lgv[u][q].y - M) * iv;
+                const float p2 = __expf(lgv[u][q].z - M) * iv, p3 = __expf(lgv[u][q].w - M) * iv;
+                a0 += p0 * p0; a1 += p1 * p1; a2 += p2 * p2; a3 += p3 * p3;
+              }
+            // recording rule (reference :124, :309); tokens beyond the context hold -inf logits: exactly 0
+            a0 = (pos4[u].x <= max_pos) ? a0 : 0.f;
+            a1 = (pos4[u].y <= max_pos) ? a1 : 0.f;
+            a2 = (pos4[u].z <= max_pos) ? a2 : 0.f;
+            a3 = (pos4[u].w <= max_pos) ? a3 : 0.f;
+            if (a0 != 0.f || a1 != 0.f || a2 != 0.f || a3 != 0.f)
+              asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                           ::"l"(p.metric + slot4[u]), "f"(a0), "f"(a1), "f"(a2), "f"(a3) : "memory");
           }
         }
       }
