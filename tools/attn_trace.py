@@ -107,6 +107,37 @@ def main():
             "fastest_sms": [(k, round(sm_last[k], 1), sm_cnt[k]) for k in order[:10]],
             "slowest_sms": [(k, round(sm_last[k], 1), sm_cnt[k]) for k in order[-10:]],
             "warps_per_sm_hist": {str(c): int(sum(1 for v in sm_cnt.values() if v == c)) for c in sorted(set(sm_cnt.values()))}}
+    # sweep-time variance: between SMs vs within an SM, persistence of the per-SM effect across layers, and the
+    # effect of the warp's position in its CTA (item = cta * consumers + warp)
+    sweep = (c6 - ck0) / clk                                    # [L, items] us
+    sm_all = (t[..., 6] >> 48) & 0xffff
+    lays = list(range(2, L))
+    sm_mean = np.full((L, 160), np.nan)
+    within = []
+    for l in lays:
+        for sm in np.unique(sm_all[l]):
+            v = sweep[l][sm_all[l] == sm]
+            sm_mean[l, sm] = v.mean()
+            within.append(v.var())
+    between = np.nanvar(sm_mean[lays], axis=1).mean()
+    persist = []
+    for l in lays[:-1]:
+        x, y = sm_mean[l], sm_mean[l + 1]
+        ok = ~np.isnan(x) & ~np.isnan(y)
+        persist.append(float(np.corrcoef(x[ok], y[ok])[0, 1]))
+    kcons = 7
+    by_warp = [float(sweep[lays][:, w::kcons].mean()) for w in range(kcons)]
+    sm_avg = np.nanmean(sm_mean[lays], axis=0)
+    ids = np.argsort(np.nan_to_num(sm_avg, nan=0))
+    ids = [int(i) for i in ids if not np.isnan(sm_avg[i])]
+    skew["sweep_us_percentiles"] = [float(np.percentile(sweep[lays], q)) for q in (0, 5, 25, 50, 75, 95, 100)]
+    skew["sweep_var_between_sm"] = float(between)
+    skew["sweep_var_within_sm"] = float(np.mean(within))
+    skew["sm_mean_corr_adjacent_layers"] = float(np.mean(persist))
+    skew["sweep_us_by_warp_in_cta"] = by_warp
+    skew["sm_avg_sweep_fastest"] = [(i, round(float(sm_avg[i]), 2)) for i in ids[:12]]
+    skew["sm_avg_sweep_slowest"] = [(i, round(float(sm_avg[i]), 2)) for i in ids[-12:]]
+    skew["sm_avg_sweep_by_id"] = [round(float(v), 2) if not np.isnan(v) else None for v in sm_avg[:148]]
     print(json.dumps({"pdl": a.pdl, "skew": skew, "launch_span_us_median": float(np.median(span[2:])),
                       "launch_period_us_median": float(np.median(period[2:])),
                       "start_skew_us_median": float(np.median([r["last_start_us"] - r["start_us"] for r in rows[2:]])),
