@@ -282,14 +282,19 @@ def prefill_metrics_bench(device):
     q = torch.randn((T, Hq, D), generator=g, device=device, dtype=torch.float32).to(torch.float16)
     k = torch.randn((T, H, D), generator=g, device=device, dtype=torch.float32).to(torch.float16)
     buf = torch.zeros(len(lens), dtype=torch.int32, device=device)
-    metrics = torch.zeros((T * H // 16 + 1, 16), dtype=torch.float32, device=device)
-    slots = torch.randperm(T * H, device=device).view(T, H)
+    starts = torch.tensor([0] + list(torch.tensor(lens).cumsum(0).tolist()), dtype=torch.int32, device=device)
+    # slots as the engine lays them out: every head owns randomly placed blocks of 16 consecutive tokens
+    nblk = (T + 15) // 16
+    blocks = torch.randperm(H * nblk, device=device).view(H, nblk)
+    tok = torch.arange(T, device=device)
+    slots = (blocks[:, tok // 16] * 16 + tok % 16).t().contiguous()
+    metrics = torch.zeros((H * nblk, 16), dtype=torch.float32, device=device)
     ts = []
     for _ in range(6):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         ops.prefill_kv_metrics(q, k, lens, D ** -0.5, buf, n_observed=32, kv_metrics=metrics, slot_mapping=slots,
-                               return_metrics=False)
+                               return_metrics=False, seq_start_loc=starts)
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))

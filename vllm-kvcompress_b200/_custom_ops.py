@@ -252,17 +252,24 @@ def prefill_kv_metrics(query, key, seq_lens, scale: float, kv_metric_buffer_len,
                        use_l2: bool = True, use_average: bool = False, use_maxpool: bool = True,
                        kv_metrics: Optional[torch.Tensor] = None,
                        slot_mapping: Optional[torch.Tensor] = None,
-                       return_metrics: bool = True) -> Optional[torch.Tensor]:
+                       return_metrics: bool = True,
+                       seq_start_loc: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
     """ADDITIVE op: tensor-core (tcgen05) replacement of _naive_kvc_attention
     (vllm/attention/backends/flash_attn.py:1122-1211; same argument meaning, `seq_lens` is the
     Python list prefill_meta.seq_lens, `key` is the un-repeated [T, num_kv_heads, D] tensor).
     Returns kv_metric_out [T, num_heads] f32 like the reference; when kv_metrics / slot_mapping
-    are given, CompressionMetrics.aggregate_prefill (metrics.py:395-427) is fused in."""
-    starts = [0]
-    for n in seq_lens:
-        starts.append(starts[-1] + int(n))
-    assert starts[-1] == query.shape[0], "seq_lens must cover the prefill tokens"
-    seq_start_loc = torch.tensor(starts, dtype=torch.int32, device=query.device)
+    are given, CompressionMetrics.aggregate_prefill (metrics.py:395-427) is fused in.
+    `seq_start_loc` (int32 [num_seqs + 1], on the device): the cumulative prompt starts the reference's prefill
+    metadata already holds (flash_attn.py: prefill_meta.seq_start_loc); built from `seq_lens` when absent, which
+    costs a host-to-device copy per call."""
+    if seq_start_loc is None:
+        starts = [0]
+        for n in seq_lens:
+            starts.append(starts[-1] + int(n))
+        assert starts[-1] == query.shape[0], "seq_lens must cover the prefill tokens"
+        seq_start_loc = torch.tensor(starts, dtype=torch.int32, device=query.device)
+    else:
+        assert seq_start_loc.dtype == torch.int32 and seq_start_loc.numel() == len(seq_lens) + 1
     out = (torch.empty((query.shape[0], query.shape[1]), dtype=torch.float32, device=query.device)
            if return_metrics else None)
     torch.ops._C_kvc_ops.prefill_kv_metrics(
