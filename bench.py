@@ -301,7 +301,8 @@ def prefill_metrics_bench(device):
     ms = sorted(ts[1:])[len(ts[1:]) // 2]
     flops = 2 * sum(2.0 * 32 * Hq * n * D for n in lens)
     return {"prompts": lens, "ms": ms, "tflops": flops / (ms * 1e-3) / 1e12,
-            "note": "3 launches: row stats, squared-probability column sums, max-pool + aggregate_prefill"}
+            "note": "3 launches (TMA + tcgen05 row stats, squared-probability column sums, max-pool + aggregate_prefill); "
+                    "prompt starts on the device as in the reference's prefill metadata"}
 
 
 def build_engine(args, model, device, rank, pdl="model"):
