@@ -397,7 +397,10 @@ KVC_API int kvc_get_attention_v2_mode(void);
  * sequences, block size 16 and <= 512 slots per head run as ONE launch, a CTA per sequence, whose sort is
  * pruned to the keys at or below a per-sequence bound on the E-th completion key (see kvc_select.cu);
  * 1 = always the three launches (rank, threshold, emit); 2 = the single launch whenever the shape
- * allows.  Results are identical in every mode. */
+ * allows.  Long contexts (more than 512 slots per head) take the sort-free radix path in modes 0 / 2 / 3: as
+ * ONE cooperative launch (keys resident in shared memory, grid barriers between the digit passes) when every
+ * head's CTA fits on the device at once, else -- and always in mode 3 -- as seven launches.  Results are
+ * identical in every mode. */
 KVC_API int kvc_set_select_mode(int mode);
 KVC_API int kvc_get_select_mode(void);
 

@@ -194,6 +194,7 @@ def test_deferred_ops_fail_loudly_on_cpu(built):
 def test_select_mode_switch_round_trips(built):
     lib = built.load_lib()
     assert lib.kvc_get_select_mode() == 0
+    assert lib.kvc_set_select_mode(3) == 0 and lib.kvc_get_select_mode() == 3
     assert lib.kvc_set_select_mode(2) == 0 and lib.kvc_get_select_mode() == 2
     assert lib.kvc_set_select_mode(7) != 0 and lib.kvc_get_select_mode() == 2   # rejected, unchanged
     assert lib.kvc_set_select_mode(0) == 0

@@ -738,8 +738,8 @@ SELV2 = load_cases("selection_v2.npz")
 @pytest.mark.parametrize("quantize", [0, 8, 3])
 @pytest.mark.parametrize("cfg", [(91, 3, 2, 4, 16, 120, 32), (92, 2, 3, 2, 16, 400, 16), (93, 4, 1, 3, 4, 300, 5)])
 def test_select_evictions_long_context_radix_equals_sort(capi, cfg, quantize):
-    """Long contexts: the sort-free radix path (default) against the CTA-per-head sort path (select mode 1) on the
-    same inputs, bit for bit, over budgets of 0 / small / typical / more than exists, with metrics quantised to a
+    """Long contexts: the sort-free radix path (default: one cooperative launch; mode 3: seven launches) against the
+    CTA-per-head sort path (select mode 1) on the same inputs, bit for bit, over budgets of 0 / small / typical / more than exists, with metrics quantised to a
     handful of values so that the tie rules (completion keys by (key, head, block), slots by (key, logical
     index)) decide almost every grant."""
     from vllm_kvcompress_b200 import workload as W
@@ -756,7 +756,7 @@ def test_select_evictions_long_context_radix_equals_sort(capi, cfg, quantize):
         budgets = (total.float() * frac).to(torch.int32)
         budgets[0] = int(total[0] * (1.0 - frac)) if frac <= 1 else budgets[0]   # sequences with different budgets
         outs = []
-        for mode in (1, 0):
+        for mode in (1, 3, 0):
             capi.set_select_mode(mode)
             logical = torch.full((N,), -5, dtype=torch.int32, device="cuda")
             kvc = torch.full((S, L, H), -5, dtype=torch.int32, device="cuda")
@@ -766,8 +766,9 @@ def test_select_evictions_long_context_radix_equals_sort(capi, cfg, quantize):
             torch.cuda.synchronize()
             outs.append((logical.cpu(), kvc.cpu(), blk.cpu()))
         capi.set_select_mode(0)
-        for a, b in zip(*outs):
-            assert torch.equal(a, b), (cfg, quantize, frac)
+        for other in outs[1:]:
+            for a, b in zip(outs[0], other):
+                assert torch.equal(a, b), (cfg, quantize, frac)
         assert int(outs[0][2].sum()) == int(torch.minimum(budgets, outs[0][2].sum(dim=(1, 2))).sum())
 
 

@@ -278,7 +278,8 @@ def get_attention_v2_mode() -> int:
 
 def set_select_mode(mode: int) -> None:
     """kvc_set_select_mode: 0 = choose by shape (default), 1 = rank / threshold / emit launches,
-    2 = one CTA per sequence with the pruned sort whenever block size and context lengths allow."""
+    2 = one CTA per sequence with the pruned sort whenever block size and context lengths allow,
+    3 = like 0 but the long-context radix path always runs as seven launches (never the cooperative one)."""
     _check(native.load_lib().kvc_set_select_mode(int(mode)))
 
 

@@ -34,6 +34,8 @@
 // block of completion keys; HBM/L2-bound, no tensor-core shapes.
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "kvc_common.cuh"
 
 namespace kvc {
@@ -524,6 +526,15 @@ __device__ __forceinline__ bool radix_state(const RadixWs& w, int S, int s, int 
 
 __device__ __forceinline__ void hist_add(int* hist, unsigned digit) { atomicAdd(&hist[digit], 1); }
 
+// shared scratch of the radix kernels (one instance per CTA; the fused kernel reuses it across its phases)
+struct RadixSmem {
+  int hist[256];
+  int scan[256];
+  int w[8], w2[8];
+  int tmp, base, less, eq, carry, lesssum, need;
+  unsigned prefix;
+};
+
 // 256-thread CTA: the bin b with cum[b-1] < need <= cum[b] (inclusive prefix sums of hist) and need - cum[b-1];
 // parallel replacement of a serial walk over the bins.  Returns through shared memory.
 __device__ __forceinline__ void pick_bin(const int* hist, int need, int* s_w, unsigned* s_bin, int* s_need) {
@@ -543,13 +554,14 @@ __device__ __forceinline__ void pick_bin(const int* hist, int need, int* s_w, un
   __syncthreads();
 }
 
+// One digit pass of head g.  kbuf: the head's keys in shared memory (fused kernel) or nullptr (keys live in the
+// workspace).  Every thread of the CTA returns together (no barrier is skipped by a subset).
 template <int PASS>
-__global__ void __launch_bounds__(256) select_radix_pass_kernel(SelectParams p, RadixWs w) {
-  __shared__ int hist[256];
-  __shared__ int s_w[8];
-  __shared__ int s_tmp, s_base;
+__device__ __forceinline__ void radix_pass_body(const SelectParams& p, const RadixWs& w, RadixSmem& sm, int g,
+                                                unsigned* kbuf) {
+  int* hist = sm.hist;
+  int* s_w = sm.w;
   const int t = threadIdx.x, lane = t % kWarp, wid = t / kWarp;
-  const int g = blockIdx.x;
   const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
   const int E = p.budgets[s];
   if (E <= 0) return;  // CTA-uniform
@@ -558,13 +570,13 @@ __global__ void __launch_bounds__(256) select_radix_pass_kernel(SelectParams p, 
   const int off = p.offsets[g];
   const int r0 = p.hanging[g];
   unsigned prefix = 0;
-  if (PASS > 0 && !radix_state(w, p.S, s, E, PASS, prefix, &s_tmp)) return;
+  if (PASS > 0 && !radix_state(w, p.S, s, E, PASS, prefix, &sm.tmp)) return;
   constexpr int shift = 24 - 8 * PASS;
   const unsigned hi_mask = PASS == 0 ? 0u : ~((1u << (shift + 8)) - 1u);
   hist[t] = 0;
-  if (t == 0) s_base = 0;
+  if (t == 0) sm.base = 0;
   __syncthreads();
-  unsigned* __restrict__ keys = w.keys + off;
+  unsigned* keys = kbuf ? kbuf : w.keys + off;
   int base = 0;  // keys below the prefix range
   if (PASS == 0) {
     const int last_pos = p.last_position[s];
@@ -603,8 +615,8 @@ __global__ void __launch_bounds__(256) select_radix_pass_kernel(SelectParams p, 
       if ((k & hi_mask) == prefix) hist_add(hist, (k >> shift) & 255u);
       else if (k < prefix) ++base;
     };
-    if ((off & 3) == 0) {  // 16-byte key loads (segments start at multiples of the block size)
-      const uint4* __restrict__ k4 = reinterpret_cast<const uint4*>(keys);
+    if (kbuf || (off & 3) == 0) {  // 16-byte key loads (segments start at multiples of the block size)
+      const uint4* k4 = reinterpret_cast<const uint4*>(keys);
       const int n4 = n >> 2;
       for (int i = t; i < n4; i += 256) {
         const uint4 v = k4[i];
@@ -616,7 +628,7 @@ __global__ void __launch_bounds__(256) select_radix_pass_kernel(SelectParams p, 
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) base += __shfl_xor_sync(0xffffffffu, base, d);
-    if (lane == 0 && base) atomicAdd(&s_base, base);
+    if (lane == 0 && base) atomicAdd(&sm.base, base);
   }
   __syncthreads();
   // inclusive scan of the 256 bins
@@ -629,16 +641,22 @@ __global__ void __launch_bounds__(256) select_radix_pass_kernel(SelectParams p, 
   if (lane == 31) s_w[wid] = v;
   __syncthreads();
   for (int q = 0; q < wid; ++q) v += s_w[q];
-  const int c = completions(s_base + v, r0, p.B);
+  const int c = completions(sm.base + v, r0, p.B);
   if (c) atomicAdd(w.fsum + ((size_t)PASS * p.S + s) * 256 + t, c);
+  __syncthreads();   // the scratch is reused by the next phase of the fused kernel
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256) select_radix_pass_kernel(SelectParams p, RadixWs w) {
+  __shared__ RadixSmem sm;
+  radix_pass_body<PASS>(p, w, sm, blockIdx.x, nullptr);
 }
 
 // per head: blocks completed by keys < K (-> evicted_block_count) and the extra ones completed by keys == K
 // (-> evicted_kv_count), K = inf: every finite key
-__global__ void __launch_bounds__(256) select_radix_count_kernel(SelectParams p, RadixWs w) {
-  __shared__ int s_tmp, s_less, s_eq;
+__device__ __forceinline__ void radix_count_body(const SelectParams& p, const RadixWs& w, RadixSmem& sm, int g,
+                                                 const unsigned* kbuf) {
   const int t = threadIdx.x, lane = t % kWarp;
-  const int g = blockIdx.x;
   const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
   const int E = p.budgets[s];
   if (E <= 0) {
@@ -646,10 +664,10 @@ __global__ void __launch_bounds__(256) select_radix_count_kernel(SelectParams p,
     return;
   }
   unsigned K = 0;
-  const bool found = radix_state(w, p.S, s, E, 4, K, &s_tmp);
+  const bool found = radix_state(w, p.S, s, E, 4, K, &sm.tmp);
   const int n = p.context_lens[(l * p.S + s) * p.H + h];
-  const unsigned* __restrict__ keys = w.keys + p.offsets[g];
-  if (t == 0) s_less = s_eq = 0;
+  const unsigned* keys = kbuf ? kbuf : w.keys + p.offsets[g];
+  if (t == 0) sm.less = sm.eq = 0;
   __syncthreads();
   int less = 0, eq = 0;
   auto one = [&](unsigned k) {
@@ -657,8 +675,8 @@ __global__ void __launch_bounds__(256) select_radix_count_kernel(SelectParams p,
     if (!found || k < K) ++less;
     else if (k == K) ++eq;
   };
-  if ((p.offsets[g] & 3) == 0) {
-    const uint4* __restrict__ k4 = reinterpret_cast<const uint4*>(keys);
+  if (kbuf || (p.offsets[g] & 3) == 0) {
+    const uint4* k4 = reinterpret_cast<const uint4*>(keys);
     const int n4 = n >> 2;
     for (int i = t; i < n4; i += 256) {
       const uint4 v = k4[i];
@@ -674,34 +692,38 @@ __global__ void __launch_bounds__(256) select_radix_count_kernel(SelectParams p,
     eq += __shfl_xor_sync(0xffffffffu, eq, d);
   }
   if (lane == 0) {
-    if (less) atomicAdd(&s_less, less);
-    if (eq) atomicAdd(&s_eq, eq);
+    if (less) atomicAdd(&sm.less, less);
+    if (eq) atomicAdd(&sm.eq, eq);
   }
   __syncthreads();
   if (t == 0) {
     const int r0 = p.hanging[g];
-    const int c_less = completions(s_less, r0, p.B);
+    const int c_less = completions(sm.less, r0, p.B);
     p.evicted_block_count[g] = c_less;
-    p.evicted_kv_count[g] = completions(s_less + s_eq, r0, p.B) - c_less;  // completion keys == K
+    p.evicted_kv_count[g] = completions(sm.less + sm.eq, r0, p.B) - c_less;  // completion keys == K
   }
 }
 
+__global__ void __launch_bounds__(256) select_radix_count_kernel(SelectParams p, RadixWs w) {
+  __shared__ RadixSmem sm;
+  radix_count_body(p, w, sm, blockIdx.x, nullptr);
+}
+
 // one CTA per sequence: grants at K go to the heads in order (same rule as select_threshold_kernel)
-__global__ void __launch_bounds__(256) select_radix_grant_kernel(SelectParams p) {
-  __shared__ int s_scan[256];
-  __shared__ int s_carry, s_lesssum;
-  const int s = blockIdx.x, tid = threadIdx.x;
+__device__ __forceinline__ void radix_grant_body(const SelectParams& p, RadixSmem& sm, int s) {
+  int* s_scan = sm.scan;
+  const int tid = threadIdx.x;
   const int LH = p.L * p.H;
   const int g0 = s * LH;
   const int E = p.budgets[s];
   if (E <= 0) return;  // counts already zeroed
-  if (tid == 0) s_carry = s_lesssum = 0;
+  if (tid == 0) sm.carry = sm.lesssum = 0;
   __syncthreads();
   int local = 0;
   for (int hd = tid; hd < LH; hd += 256) local += p.evicted_block_count[g0 + hd];
-  if (local) atomicAdd(&s_lesssum, local);
+  if (local) atomicAdd(&sm.lesssum, local);
   __syncthreads();
-  const int need = E - s_lesssum;  // grants left for completion keys == K (<= 0: K was inf, no ties exist)
+  const int need = E - sm.lesssum;  // grants left for completion keys == K (<= 0: K was inf, no ties exist)
   for (int h0 = 0; h0 < LH; h0 += 256) {
     const int hd = h0 + tid;
     const int eq = (hd < LH) ? p.evicted_kv_count[g0 + hd] : 0;
@@ -713,7 +735,7 @@ __global__ void __launch_bounds__(256) select_radix_grant_kernel(SelectParams p)
       s_scan[tid] += v;
       __syncthreads();
     }
-    const int eq_before = s_carry + s_scan[tid] - eq;
+    const int eq_before = sm.carry + s_scan[tid] - eq;
     if (hd < LH) {
       const int g = g0 + hd;
       const int k = p.evicted_block_count[g] + max(0, min(eq, need - eq_before));
@@ -721,21 +743,24 @@ __global__ void __launch_bounds__(256) select_radix_grant_kernel(SelectParams p)
       p.evicted_kv_count[g] = (k > 0) ? (k - 1) * p.B + p.hanging[g] : 0;  // metrics.py:788-792
     }
     __syncthreads();
-    if (tid == 255) s_carry += s_scan[255];
+    if (tid == 255) sm.carry += s_scan[255];
     __syncthreads();
   }
 }
 
+__global__ void __launch_bounds__(256) select_radix_grant_kernel(SelectParams p) {
+  __shared__ RadixSmem sm;
+  radix_grant_body(p, sm, blockIdx.x);
+}
+
 // CTA per head: T = the head's cnt-th smallest key (radix select over the keys staged in shared memory), then
-// the ordered emission of select_emit_cta_kernel
-__global__ void __launch_bounds__(256) select_radix_emit_kernel(SelectParams p, RadixWs w) {
-  extern __shared__ __align__(16) unsigned skeys[];
-  __shared__ int hist[256];
-  __shared__ int s_less, s_w[8], s_w2[8];
-  __shared__ unsigned s_prefix;
-  __shared__ int s_need;
+// the ordered emission of select_emit_cta_kernel.  staged: skeys already holds the head's keys (fused kernel).
+__device__ __forceinline__ void radix_emit_body(const SelectParams& p, const RadixWs& w, RadixSmem& sm, int g,
+                                                unsigned* skeys, bool staged) {
+  int* hist = sm.hist;
+  int* s_w = sm.w;
+  int* s_w2 = sm.w2;
   const int t = threadIdx.x, lane = t % kWarp, wid = t / kWarp;
-  const int g = blockIdx.x;
   const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
   const int n = p.context_lens[(l * p.S + s) * p.H + h];
   const int nblk = (n + p.B - 1) / p.B;
@@ -743,14 +768,16 @@ __global__ void __launch_bounds__(256) select_radix_emit_kernel(SelectParams p, 
   const int cnt = p.evicted_kv_count[g];
   int* __restrict__ out = p.evicted_logical_indices + off;
   if (cnt > 0) {  // CTA-uniform
-    const unsigned* __restrict__ keys = w.keys + off;
-    if ((off & 3) == 0) {
-      const uint4* __restrict__ k4 = reinterpret_cast<const uint4*>(keys);
-      const int n4 = n >> 2;
-      for (int i = t; i < n4; i += 256) reinterpret_cast<uint4*>(skeys)[i] = k4[i];
-      for (int i = (n4 << 2) + t; i < n; i += 256) skeys[i] = keys[i];
-    } else {
-      for (int i = t; i < n; i += 256) skeys[i] = keys[i];
+    if (!staged) {
+      const unsigned* __restrict__ keys = w.keys + off;
+      if ((off & 3) == 0) {
+        const uint4* __restrict__ k4 = reinterpret_cast<const uint4*>(keys);
+        const int n4 = n >> 2;
+        for (int i = t; i < n4; i += 256) reinterpret_cast<uint4*>(skeys)[i] = k4[i];
+        for (int i = (n4 << 2) + t; i < n; i += 256) skeys[i] = keys[i];
+      } else {
+        for (int i = t; i < n; i += 256) skeys[i] = keys[i];
+      }
     }
     __syncthreads();
     unsigned prefix = 0, mask = 0;
@@ -763,47 +790,83 @@ __global__ void __launch_bounds__(256) select_radix_emit_kernel(SelectParams p, 
         if ((k & mask) == prefix) hist_add(hist, (k >> shift) & 255u);
       }
       __syncthreads();
-      pick_bin(hist, need, s_w, &s_prefix, &s_need);
-      prefix |= s_prefix << shift;
-      need = s_need;
+      pick_bin(hist, need, s_w, &sm.prefix, &sm.need);
+      prefix |= sm.prefix << shift;
+      need = sm.need;
       mask |= 255u << shift;
       __syncthreads();
     }
     const unsigned T = prefix;  // cnt-th smallest key; `need` of the keys == T are evicted, in logical order
     const int allowed = need;
+    // ordered emission: every warp owns a contiguous range of the logical indices; one CTA barrier for the
+    // ranges' counts, then the warps emit on their own (ballot prefix sums, no barrier per 256 keys)
+    const int chunk = ((n + 8 * kWarp - 1) / (8 * kWarp)) * kWarp;
+    const int lo = min(n, wid * chunk), hi = min(n, lo + chunk);
+    int cl = 0, ce = 0;
+    for (int i = lo + lane; i < hi; i += kWarp) {
+      const unsigned k = skeys[i];
+      cl += k < T;
+      ce += k == T;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      cl += __shfl_xor_sync(0xffffffffu, cl, d);
+      ce += __shfl_xor_sync(0xffffffffu, ce, d);
+    }
+    if (lane == 0) { s_w[wid] = cl; s_w2[wid] = ce; }
+    __syncthreads();
     int eq_base = 0, written = 0;
-    for (int i0 = 0; i0 < n; i0 += 256) {
-      const int i = i0 + t;
-      const unsigned k = (i < n) ? skeys[i] : kInfKey;
-      const bool less = (i < n) && k < T, eq = (i < n) && (k == T);
+    for (int q = 0; q < wid; ++q) {
+      written += s_w[q] + max(0, min(s_w2[q], allowed - eq_base));
+      eq_base += s_w2[q];
+    }
+    for (int i0 = lo; i0 < hi; i0 += kWarp) {
+      const int i = i0 + lane;
+      const unsigned k = (i < hi) ? skeys[i] : kInfKey;
+      const bool less = (i < hi) && k < T, eq = (i < hi) && (k == T);
       const unsigned em = __ballot_sync(0xffffffffu, eq);
-      if (lane == 0) s_w[wid] = __popc(em);
-      __syncthreads();
-      int eq_before = eq_base + __popc(em & lanemask_lt());
-      int eq_tot = 0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (q < wid) eq_before += s_w[q];
-        eq_tot += s_w[q];
-      }
-      const bool ev = less || (eq && eq_before < allowed);
+      const bool ev = less || (eq && eq_base + __popc(em & lanemask_lt()) < allowed);
       const unsigned vm = __ballot_sync(0xffffffffu, ev);
-      if (lane == 0) s_w2[wid] = __popc(vm);
-      __syncthreads();
-      int pos = written + __popc(vm & lanemask_lt());
-      int tot = 0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (q < wid) pos += s_w2[q];
-        tot += s_w2[q];
-      }
-      if (ev) out[pos] = i;
-      written += tot;
-      eq_base += eq_tot;
-      __syncthreads();
+      if (ev) out[written + __popc(vm & lanemask_lt())] = i;
+      written += __popc(vm);
+      eq_base += __popc(em);
     }
   }
   for (int i = cnt + t; i < nblk * p.B; i += 256) out[i] = p.null_index;
+}
+
+__global__ void __launch_bounds__(256) select_radix_emit_kernel(SelectParams p, RadixWs w) {
+  extern __shared__ __align__(16) unsigned skeys[];
+  __shared__ RadixSmem sm;
+  radix_emit_body(p, w, sm, blockIdx.x, skeys, false);
+}
+
+// All of the above in ONE cooperative launch when every head's CTA is resident at once (post-prefill compression
+// of a few prompts): the head's keys are built once and stay in shared memory for the four digit passes, the
+// count and the emission (the workspace copy and its five re-reads disappear), and the six kernel boundaries
+// become grid barriers.
+__global__ void __launch_bounds__(256, 6) select_radix_fused_kernel(SelectParams p, RadixWs w, int stop_after) {
+  extern __shared__ __align__(16) unsigned skeys[];
+  __shared__ RadixSmem sm;
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int g = blockIdx.x;
+  // (profiling aid: KVC_SELECT_STOP_AFTER = n truncates the kernel after phase n, tools/select_phases.py long)
+  radix_pass_body<0>(p, w, sm, g, skeys);
+  if (stop_after == 1) return;
+  grid.sync();
+  radix_pass_body<1>(p, w, sm, g, skeys);
+  grid.sync();
+  radix_pass_body<2>(p, w, sm, g, skeys);
+  grid.sync();
+  radix_pass_body<3>(p, w, sm, g, skeys);
+  if (stop_after == 2) return;
+  grid.sync();
+  radix_count_body(p, w, sm, g, skeys);
+  grid.sync();
+  if (g < p.S) radix_grant_body(p, sm, g);
+  if (stop_after == 3) return;
+  grid.sync();
+  radix_emit_body(p, w, sm, g, skeys, true);
 }
 
 // one CTA per sequence
@@ -1289,7 +1352,7 @@ using namespace kvc;
 
 static int g_select_mode = 0;
 extern "C" int kvc_set_select_mode(int mode) {
-  KVC_REQUIRE(mode >= 0 && mode <= 2, KVC_ERR_INVALID, "select mode must be 0, 1 or 2, got %d", mode);
+  KVC_REQUIRE(mode >= 0 && mode <= 3, KVC_ERR_INVALID, "select mode must be 0 .. 3, got %d", mode);
   g_select_mode = mode;
   return KVC_OK;
 }
@@ -1436,6 +1499,29 @@ extern "C" int kvc_select_evictions_ex(
     rw.fsum = reinterpret_cast<int*>((kp + ((size_t)max_evicted_kv + 64) * sizeof(unsigned) + 255) & ~uintptr_t(255));
     cudaError_t e = cudaMemsetAsync(rw.fsum, 0, (size_t)num_seqs * 4 * 256 * sizeof(int), st);
     if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "select_evictions memset: %s", cudaGetErrorString(e));
+    const size_t smem_keys = (size_t)max_slots * sizeof(unsigned);
+    {
+      // one cooperative launch when all head CTAs fit on the device at once (select mode 3: always the
+      // seven-launch path, which larger batches take anyway)
+      const bool want_fused = g_select_mode != 3;
+      int per_sm = 0;
+      if (want_fused) {
+        e = cudaFuncSetAttribute(select_radix_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_keys);
+        if (e == cudaSuccess)
+          e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, select_radix_fused_kernel, 256, smem_keys);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); per_sm = 0; }
+      }
+      if (per_sm > 0 && (int64_t)per_sm * sm_count() >= total) {
+        const char* sa = getenv("KVC_SELECT_STOP_AFTER");
+        int stop_after = sa ? atoi(sa) : 0;
+        void* args[] = {&p, &rw, &stop_after};
+        e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(select_radix_fused_kernel), dim3(total), dim3(256),
+                                        args, smem_keys, st);
+        if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "select_radix_fused launch: %s", cudaGetErrorString(e));
+        KVC_CHECK_LAUNCH("select_radix_fused_kernel");
+        return KVC_OK;
+      }
+    }
     select_radix_pass_kernel<0><<<total, 256, 0, st>>>(p, rw);
     select_radix_pass_kernel<1><<<total, 256, 0, st>>>(p, rw);
     select_radix_pass_kernel<2><<<total, 256, 0, st>>>(p, rw);
