@@ -111,6 +111,28 @@ def test_prefill_metrics_random_vs_oracle(capi, O, cfg):
     np.testing.assert_allclose(got, want, rtol=2e-2, atol=1e-5)
 
 
+@pytest.mark.gpu
+def test_prefill_metrics_negative_scale_vs_oracle(capi, O):
+    """A negative softmax scale turns the row maximum of the logits into the minimum of the accumulators: the
+    kernel tracks the extremum in accumulator units (the scale is folded into the exponent constant)."""
+    g = torch.Generator().manual_seed(11)
+    lens, Hq, H, D, n_obs = [700, 45], 8, 2, 128, 32
+    T = sum(lens)
+    q = torch.randn((T, Hq, D), generator=g).to(torch.float16)
+    k = torch.randn((T, H, D), generator=g).to(torch.float16)
+    bits = lambda t: t.view(torch.int16).numpy().view(np.uint16)
+    buf = np.array([0, 3], np.int32)
+    want = O.prefill_kv_metrics(bits(q), bits(k), lens, -0.05, buf, n_obs, 4096, True, False, True, False)
+    out = torch.empty((T, Hq), dtype=torch.float32, device="cuda")
+    capi.prefill_kv_metrics(out, None, None, q.cuda(), k.cuda(), starts_of(lens), torch.as_tensor(buf).cuda(),
+                            max(lens), -0.05, n_obs, True, False, True)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    close = np.isclose(got, want, rtol=RTOL, atol=ATOL)
+    assert close.mean() > 0.999, f"{(~close).sum()} of {close.size} entries differ"
+    np.testing.assert_allclose(got, want, rtol=2e-2, atol=1e-5)
+
+
 def test_prefill_torch_op_surface_and_errors(capi):
     from vllm_kvcompress_b200 import _custom_ops as ops
     c = PREFILL["prefill0"]
@@ -128,6 +150,16 @@ def test_prefill_torch_op_surface_and_errors(capi):
     out2 = ops.prefill_kv_metrics(qkv[:, : q.shape[1] * 128].view(q.shape[0], q.shape[1], 128), k, lens,
                                   float(c["scale"]), buf, n_observed=32)
     assert torch.equal(out, out2)
+    # query AND key as views of one fused projection output (the key's base pointer and token stride both differ
+    # from a dense [T, H, D] tensor: the TMA tensor maps are built from the strides)
+    Hq, H = q.shape[1], k.shape[1]
+    fused = torch.randn((q.shape[0], (Hq + 2 * H) * 128), device="cuda").to(q.dtype)
+    fused[:, : Hq * 128] = q.reshape(q.shape[0], -1)
+    fused[:, Hq * 128: (Hq + H) * 128] = k.reshape(k.shape[0], -1)
+    out3 = ops.prefill_kv_metrics(fused[:, : Hq * 128].view(-1, Hq, 128),
+                                  fused[:, Hq * 128: (Hq + H) * 128].view(-1, H, 128), lens, float(c["scale"]), buf,
+                                  n_observed=32)
+    assert torch.equal(out, out3)
     with pytest.raises(RuntimeError, match="Unsupported head size"):
         ops.prefill_kv_metrics(q[:, :, :64].contiguous(), k[:, :, :64].contiguous(), lens, 1.0, buf)
     with pytest.raises(RuntimeError, match="Unsupported prefill_observed_queries"):

@@ -558,7 +558,7 @@ __device__ __forceinline__ void pick_bin(const int* hist, int need, int* s_w, un
 // workspace).  Every thread of the CTA returns together (no barrier is skipped by a subset).
 template <int PASS>
 __device__ __forceinline__ void radix_pass_body(const SelectParams& p, const RadixWs& w, RadixSmem& sm, int g,
-                                                unsigned* kbuf) {
+                                                unsigned* kbuf, int* s_bt = nullptr) {
   int* hist = sm.hist;
   int* s_w = sm.w;
   const int t = threadIdx.x, lane = t % kWarp, wid = t / kWarp;
@@ -582,25 +582,23 @@ __device__ __forceinline__ void radix_pass_body(const SelectParams& p, const Rad
     const int last_pos = p.last_position[s];
     const int max_pos = last_pos - p.protected_window[s];
     const int* __restrict__ bt = p.block_tables + (int64_t)lsh * p.MB;
-    // four independent table -> metric / position chains per thread: the gather is bound by the bytes in flight
-    for (int i0 = t; i0 < n; i0 += 4 * 256) {
-      int blk[4];
-      float mm[4];
-      int qq[4];
+    // the head's block-table row goes to shared memory first (one coalesced read), so the gather below is ONE
+    // round of independent loads per slot instead of table -> data; eight slots per thread in flight
+    const int nblk = (n + p.B - 1) / p.B;
+    for (int b = t; b < nblk; b += 256) s_bt[b] = bt[b];
+    __syncthreads();
+    for (int i0 = t; i0 < n; i0 += 8 * 256) {
+      float mm[8];
+      int qq[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int i = i0 + u * 256;
-        blk[u] = (i < n) ? bt[i / p.B] : 0;
+        const int64_t slot = (i < n) ? (int64_t)s_bt[i / p.B] * p.B + i % p.B : 0;
+        mm[u] = p.kv_metrics[slot];
+        qq[u] = p.kv_position[slot];
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * 256;
-        const int64_t slot = (int64_t)blk[u] * p.B + i % p.B;
-        mm[u] = (i < n) ? p.kv_metrics[slot] : 0.f;
-        qq[u] = (i < n) ? p.kv_position[slot] : 0;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int i = i0 + u * 256;
         if (i < n) {
           const unsigned k = slot_key(p, mm[u], qq[u], max_pos, last_pos, l, h);
@@ -648,8 +646,9 @@ __device__ __forceinline__ void radix_pass_body(const SelectParams& p, const Rad
 
 template <int PASS>
 __global__ void __launch_bounds__(256) select_radix_pass_kernel(SelectParams p, RadixWs w) {
+  extern __shared__ __align__(16) int s_bt_dyn[];   // pass 0: the head's block-table row (MB ints)
   __shared__ RadixSmem sm;
-  radix_pass_body<PASS>(p, w, sm, blockIdx.x, nullptr);
+  radix_pass_body<PASS>(p, w, sm, blockIdx.x, nullptr, s_bt_dyn);
 }
 
 // per head: blocks completed by keys < K (-> evicted_block_count) and the extra ones completed by keys == K
@@ -842,26 +841,146 @@ __global__ void __launch_bounds__(256) select_radix_emit_kernel(SelectParams p, 
 }
 
 // All of the above in ONE cooperative launch when every head's CTA is resident at once (post-prefill compression
-// of a few prompts): the head's keys are built once and stay in shared memory for the four digit passes, the
-// count and the emission (the workspace copy and its five re-reads disappear), and the six kernel boundaries
-// become grid barriers.
+// of a few prompts): the head's keys are built once and stay in shared memory for the four digit passes and the
+// emission (the workspace copy and its five re-reads disappear), the kernel boundaries become grid barriers, and
+// because a CTA keeps its histogram across a barrier the running count of keys below the prefix is carried from
+// pass to pass: no per-key comparison with the prefix, and no count sweep at the end (keys < K = carried base +
+// bins below the last digit, keys == K = that digit's bin).
+struct FusedRadixState {
+  unsigned prefix = 0;
+  int base = 0;        // keys of the head below the prefix range
+  bool alive = true;   // false: the sequence has fewer than E finite completion keys (K = inf)
+};
+
+template <int PASS>
+__device__ __forceinline__ void radix_pass_fused(const SelectParams& p, const RadixWs& w, RadixSmem& sm, int g,
+                                                 unsigned* skeys, int* s_bt, FusedRadixState& st) {
+  int* hist = sm.hist;
+  const int t = threadIdx.x, lane = t % kWarp, wid = t / kWarp;
+  const int s = g / (p.L * p.H), l = (g / p.H) % p.L, h = g % p.H;
+  const int E = p.budgets[s];
+  if (E <= 0) return;  // CTA-uniform
+  const int lsh = (l * p.S + s) * p.H + h;
+  const int n = p.context_lens[lsh];
+  const int r0 = p.hanging[g];
+  if (PASS > 0) {
+    if (!st.alive) return;
+    // the digit the previous pass decided (same for every head of the sequence); sm.scan = that pass's inclusive
+    // bin sums of this head
+    const int d = pick_digit(w.fsum + ((size_t)(PASS - 1) * p.S + s) * 256, E, &sm.tmp);
+    if (d >= 256) { st.alive = false; return; }   // can only happen after pass 0
+    st.base += (d > 0) ? sm.scan[d - 1] : 0;
+    st.prefix |= (unsigned)d << (24 - 8 * (PASS - 1));
+    __syncthreads();   // sm.scan is rewritten below
+  }
+  constexpr int shift = 24 - 8 * PASS;
+  const unsigned hi_mask = PASS == 0 ? 0u : ~((1u << (shift + 8)) - 1u);
+  hist[t] = 0;
+  __syncthreads();
+  if (PASS == 0) {
+    const int last_pos = p.last_position[s];
+    const int max_pos = last_pos - p.protected_window[s];
+    const int* __restrict__ bt = p.block_tables + (int64_t)lsh * p.MB;
+    const int nblk = (n + p.B - 1) / p.B;
+    for (int b = t; b < nblk; b += 256) s_bt[b] = bt[b];
+    __syncthreads();
+    for (int i0 = t; i0 < n; i0 += 8 * 256) {
+      float mm[8];
+      int qq[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * 256;
+        const int64_t slot = (i < n) ? (int64_t)s_bt[i / p.B] * p.B + i % p.B : 0;
+        mm[u] = p.kv_metrics[slot];
+        qq[u] = p.kv_position[slot];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int i = i0 + u * 256;
+        if (i < n) {
+          const unsigned k = slot_key(p, mm[u], qq[u], max_pos, last_pos, l, h);
+          skeys[i] = k;
+          if (k != kInfKey) hist_add(hist, k >> 24);
+        }
+      }
+    }
+  } else {
+    const unsigned prefix = st.prefix;
+    auto one = [&](unsigned k) {
+      if (k != kInfKey && (k & hi_mask) == prefix) hist_add(hist, (k >> shift) & 255u);
+    };
+    const uint4* k4 = reinterpret_cast<const uint4*>(skeys);
+    const int n4 = n >> 2;
+    for (int i = t; i < n4; i += 256) {
+      const uint4 v = k4[i];
+      one(v.x); one(v.y); one(v.z); one(v.w);
+    }
+    for (int i = (n4 << 2) + t; i < n; i += 256) one(skeys[i]);
+  }
+  __syncthreads();
+  // inclusive scan of the 256 bins, kept in sm.scan for the next phase
+  int v = hist[t];
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += u;
+  }
+  if (lane == 31) sm.w[wid] = v;
+  __syncthreads();
+  for (int q = 0; q < wid; ++q) v += sm.w[q];
+  sm.scan[t] = v;
+  const int c = completions(st.base + v, r0, p.B);
+  if (c) atomicAdd(w.fsum + ((size_t)PASS * p.S + s) * 256 + t, c);
+  __syncthreads();
+}
+
+// after the last pass: blocks completed by keys < K and the extra ones completed by keys == K, without a sweep
+__device__ __forceinline__ void radix_count_fused(const SelectParams& p, const RadixWs& w, RadixSmem& sm, int g,
+                                                  FusedRadixState& st) {
+  const int t = threadIdx.x;
+  const int s = g / (p.L * p.H);
+  const int E = p.budgets[s];
+  if (E <= 0) {
+    if (t == 0) { p.evicted_block_count[g] = 0; p.evicted_kv_count[g] = 0; }
+    return;
+  }
+  int less, eq;
+  if (st.alive) {
+    const int d = pick_digit(w.fsum + ((size_t)3 * p.S + s) * 256, E, &sm.tmp);   // < 256: pass 0 found a digit
+    less = st.base + ((d > 0) ? sm.scan[d - 1] : 0);
+    eq = sm.hist[d];
+  } else {   // K = inf: every finite key (sm.scan still holds pass 0's sums)
+    less = sm.scan[255];
+    eq = 0;
+  }
+  if (t == 0) {
+    const int r0 = p.hanging[g];
+    const int c_less = completions(less, r0, p.B);
+    p.evicted_block_count[g] = c_less;
+    p.evicted_kv_count[g] = completions(less + eq, r0, p.B) - c_less;  // completion keys == K
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(256, 6) select_radix_fused_kernel(SelectParams p, RadixWs w, int stop_after) {
   extern __shared__ __align__(16) unsigned skeys[];
   __shared__ RadixSmem sm;
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   const int g = blockIdx.x;
-  // (profiling aid: KVC_SELECT_STOP_AFTER = n truncates the kernel after phase n, tools/select_phases.py long)
-  radix_pass_body<0>(p, w, sm, g, skeys);
+  int* s_bt = reinterpret_cast<int*>(skeys + p.MB * p.B);   // the head's block-table row, behind its keys
+  FusedRadixState st;
+  // (profiling aid: KVC_SELECT_STOP_AFTER = n truncates the kernel after phase n, tools/select_long_phases.py)
+  radix_pass_fused<0>(p, w, sm, g, skeys, s_bt, st);
   if (stop_after == 1) return;
   grid.sync();
-  radix_pass_body<1>(p, w, sm, g, skeys);
+  radix_pass_fused<1>(p, w, sm, g, skeys, s_bt, st);
   grid.sync();
-  radix_pass_body<2>(p, w, sm, g, skeys);
+  radix_pass_fused<2>(p, w, sm, g, skeys, s_bt, st);
   grid.sync();
-  radix_pass_body<3>(p, w, sm, g, skeys);
+  radix_pass_fused<3>(p, w, sm, g, skeys, s_bt, st);
   if (stop_after == 2) return;
   grid.sync();
-  radix_count_body(p, w, sm, g, skeys);
+  radix_count_fused(p, w, sm, g, st);
   grid.sync();
   if (g < p.S) radix_grant_body(p, sm, g);
   if (stop_after == 3) return;
@@ -1499,7 +1618,8 @@ extern "C" int kvc_select_evictions_ex(
     rw.fsum = reinterpret_cast<int*>((kp + ((size_t)max_evicted_kv + 64) * sizeof(unsigned) + 255) & ~uintptr_t(255));
     cudaError_t e = cudaMemsetAsync(rw.fsum, 0, (size_t)num_seqs * 4 * 256 * sizeof(int), st);
     if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "select_evictions memset: %s", cudaGetErrorString(e));
-    const size_t smem_keys = (size_t)max_slots * sizeof(unsigned);
+    const size_t smem_bt = (size_t)max_num_blocks_per_seq * sizeof(int);
+    const size_t smem_keys = (size_t)max_slots * sizeof(unsigned) + smem_bt;   // fused: keys + block-table row
     {
       // one cooperative launch when all head CTAs fit on the device at once (select mode 3: always the
       // seven-launch path, which larger batches take anyway)
@@ -1522,7 +1642,7 @@ extern "C" int kvc_select_evictions_ex(
         return KVC_OK;
       }
     }
-    select_radix_pass_kernel<0><<<total, 256, 0, st>>>(p, rw);
+    select_radix_pass_kernel<0><<<total, 256, smem_bt, st>>>(p, rw);
     select_radix_pass_kernel<1><<<total, 256, 0, st>>>(p, rw);
     select_radix_pass_kernel<2><<<total, 256, 0, st>>>(p, rw);
     select_radix_pass_kernel<3><<<total, 256, 0, st>>>(p, rw);
