@@ -533,6 +533,8 @@ struct RadixSmem {
   int w[8], w2[8];
   int tmp, base, less, eq, carry, lesssum, need;
   unsigned prefix;
+  int hist0[256];   // cooperative kernel: the head's top-byte histogram of its finite keys (pass 0), for the emission
+  int finite;       // ... and their number
 };
 
 // 256-thread CTA: the bin b with cum[b-1] < need <= cum[b] (inclusive prefix sums of hist) and need - cum[b-1];
@@ -755,7 +757,7 @@ __global__ void __launch_bounds__(256) select_radix_grant_kernel(SelectParams p)
 // CTA per head: T = the head's cnt-th smallest key (radix select over the keys staged in shared memory), then
 // the ordered emission of select_emit_cta_kernel.  staged: skeys already holds the head's keys (fused kernel).
 __device__ __forceinline__ void radix_emit_body(const SelectParams& p, const RadixWs& w, RadixSmem& sm, int g,
-                                                unsigned* skeys, bool staged) {
+                                                unsigned* skeys, bool staged, bool have_hist0 = false) {
   int* hist = sm.hist;
   int* s_w = sm.w;
   int* s_w2 = sm.w2;
@@ -782,11 +784,16 @@ __device__ __forceinline__ void radix_emit_body(const SelectParams& p, const Rad
     unsigned prefix = 0, mask = 0;
     int need = cnt;  // rank (1-based) among the keys that match the prefix
     for (int shift = 24; shift >= 0; shift -= 8) {
-      hist[t] = 0;
-      __syncthreads();
-      for (int i = t; i < n; i += 256) {
-        const unsigned k = skeys[i];
-        if ((k & mask) == prefix) hist_add(hist, (k >> shift) & 255u);
+      if (shift == 24 && have_hist0) {
+        // top byte: pass 0's histogram of the finite keys; the non-candidates (key = inf) sit in bin 255
+        hist[t] = sm.hist0[t] + ((t == 255) ? n - sm.finite : 0);
+      } else {
+        hist[t] = 0;
+        __syncthreads();
+        for (int i = t; i < n; i += 256) {
+          const unsigned k = skeys[i];
+          if ((k & mask) == prefix) hist_add(hist, (k >> shift) & 255u);
+        }
       }
       __syncthreads();
       pick_bin(hist, need, s_w, &sm.prefix, &sm.need);
@@ -929,6 +936,10 @@ __device__ __forceinline__ void radix_pass_fused(const SelectParams& p, const Ra
   __syncthreads();
   for (int q = 0; q < wid; ++q) v += sm.w[q];
   sm.scan[t] = v;
+  if (PASS == 0) {
+    sm.hist0[t] = hist[t];
+    if (t == 255) sm.finite = v;
+  }
   const int c = completions(st.base + v, r0, p.B);
   if (c) atomicAdd(w.fsum + ((size_t)PASS * p.S + s) * 256 + t, c);
   __syncthreads();
@@ -985,7 +996,7 @@ __global__ void __launch_bounds__(256, 6) select_radix_fused_kernel(SelectParams
   if (g < p.S) radix_grant_body(p, sm, g);
   if (stop_after == 3) return;
   grid.sync();
-  radix_emit_body(p, w, sm, g, skeys, true);
+  radix_emit_body(p, w, sm, g, skeys, true, true);
 }
 
 // one CTA per sequence
