@@ -1648,9 +1648,13 @@ extern "C" int kvc_select_evictions_ex(
         void* args[] = {&p, &rw, &stop_after};
         e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(select_radix_fused_kernel), dim3(total), dim3(256),
                                         args, smem_keys, st);
-        if (e != cudaSuccess) KVC_FAIL(KVC_ERR_CUDA, "select_radix_fused launch: %s", cudaGetErrorString(e));
-        KVC_CHECK_LAUNCH("select_radix_fused_kernel");
-        return KVC_OK;
+        if (e == cudaSuccess) {
+          KVC_CHECK_LAUNCH("select_radix_fused_kernel");
+          return KVC_OK;
+        }
+        // e.g. cudaErrorCooperativeLaunchTooLarge under a partitioned device: the seven launches below need no
+        // co-residency
+        (void)cudaGetLastError();
       }
     }
     select_radix_pass_kernel<0><<<total, 256, smem_bt, st>>>(p, rw);
