@@ -1,0 +1,10 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import torch
+import compaction_bench as cb
+dev = torch.device("cuda", 0)
+c = cb.build_schedule(dev, 64)
+for _ in range(4):
+    c["sel"]()
+torch.cuda.synchronize()
