@@ -185,7 +185,24 @@ __global__ void __launch_bounds__(kPrefillThreads) prefill_metrics_kernel(Prefil
 
   const uint32_t kbar = smem_u32(&bars[0]), mmabar = smem_u32(&bars[2]), accfree = smem_u32(&bars[4]),
                  qbar = smem_u32(&bars[6]);
-  if (tid == 0) {
+  // this row's place in the tile.  n_observed <= 128: a tile holds qt query heads x np rows; n_observed > 128: a
+  // tile is one 128-query chunk of ONE query head (mtiles = Q * nchunks), the column sums of the chunks add up
+  const int chunk = mt % p.nchunks, mtq = mt / p.nchunks;
+  auto issue_tma = [&](int i) {   // control thread: K tile i of the split -> buffer i & 1
+    const int buf = i & 1;
+    const uint32_t bar = kbar + 8 * buf, dst = smem_u32(sK0 + buf * kTileBytes);
+    const int row = start + (t0 + i) * kTileKeys;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kTileBytes) : "memory");
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+          ::"r"(dst + half * kHalfBytes), "l"(&kmap), "r"(h * kHeadDim + half * 64), "r"(row), "r"(bar)
+          : "memory");
+  };
+  if (warp == kEpiWarps && lane == 0) {
+    // the control thread initialises the barriers and has the Q tile and the first two K tiles on their way before
+    // the CTA has even allocated its tensor memory
     for (int b = 0; b < 2; ++b) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(kbar + 8 * b));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mmabar + 8 * b));
@@ -193,7 +210,24 @@ __global__ void __launch_bounds__(kPrefillThreads) prefill_metrics_kernel(Prefil
     }
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(qbar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the Q tile: per query head of the tile two swizzled boxes of [np queries x 64 d]; rows of queries beyond
+    // the observed window or of padding heads hold finite data of other tokens / heads and are given weight 0
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(qbar), "r"(kTileBytes) : "memory");
+    for (int hl = 0; hl < p.qt; ++hl) {
+      const int qh = min(mtq * p.qt + hl, p.Q - 1);
+#pragma unroll
+      for (int half = 0; half < 2; ++half)
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+            ::"r"(smem_u32(sQ) + half * kHalfBytes + hl * p.np * 128), "l"(&qmap),
+            "r"((h * p.Q + qh) * kHeadDim + half * 64), "r"(start + q_offset + chunk * kTileRows), "r"(qbar)
+            : "memory");
+    }
+    issue_tma(0);
+    if (n > 1) issue_tma(1);
+    PF_STAMP(8);
   }
+  __syncwarp();
   if (warp == kEpiWarps) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -204,10 +238,6 @@ __global__ void __launch_bounds__(kPrefillThreads) prefill_metrics_kernel(Prefil
   const uint32_t tmem = *tmem_slot;
   if (tid == 0) PF_STAMP(1);
 
-  // this row's place in the tile.  n_observed <= 128: a tile holds qt query heads x np rows; n_observed > 128: a
-  // tile is one 128-query chunk of ONE query head (mtiles = Q * nchunks), the column sums of the chunks add up
-  const int chunk = mt % p.nchunks, mtq = mt / p.nchunks;
-
   if (warp == kEpiWarps) {
     // =========================== control thread: TMA + MMA ===========================
     if (lane == 0) {
@@ -215,18 +245,6 @@ __global__ void __launch_bounds__(kPrefillThreads) prefill_metrics_kernel(Prefil
       // instruction descriptor: D = f32, A = B = f16 (0) / bf16 (1), both K-major, N = 128, M = 128
       constexpr uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(kTileKeys >> 3) << 17) |
                                  ((uint32_t)(kTileRows >> 4) << 24);
-      auto issue_tma = [&](int i) {
-        const int buf = i & 1;
-        const uint32_t bar = kbar + 8 * buf, dst = smem_u32(sK0 + buf * kTileBytes);
-        const int row = start + (t0 + i) * kTileKeys;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kTileBytes) : "memory");
-#pragma unroll
-        for (int half = 0; half < 2; ++half)
-          asm volatile(
-              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-              ::"r"(dst + half * kHalfBytes), "l"(&kmap), "r"(h * kHeadDim + half * 64), "r"(row), "r"(bar)
-              : "memory");
-      };
       auto issue_mma = [&](int buf) {
         const uint32_t a0 = smem_u32(sQ), b0 = smem_u32(sK0 + buf * kTileBytes);
 #pragma unroll
@@ -244,22 +262,6 @@ __global__ void __launch_bounds__(kPrefillThreads) prefill_metrics_kernel(Prefil
                          mmabar + 8 * buf)
                      : "memory");
       };
-      // the Q tile: per query head of the tile two swizzled boxes of [np queries x 64 d]; rows of queries beyond
-      // the observed window or of padding heads hold finite data of other tokens / heads and are given weight 0
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(qbar), "r"(kTileBytes) : "memory");
-      for (int hl = 0; hl < p.qt; ++hl) {
-        const int qh = min(mtq * p.qt + hl, p.Q - 1);
-#pragma unroll
-        for (int half = 0; half < 2; ++half)
-          asm volatile(
-              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-              ::"r"(smem_u32(sQ) + half * kHalfBytes + hl * p.np * 128), "l"(&qmap),
-              "r"((h * p.Q + qh) * kHeadDim + half * 64), "r"(start + q_offset + chunk * kTileRows), "r"(qbar)
-              : "memory");
-      }
-      issue_tma(0);
-      if (n > 1) issue_tma(1);
-      PF_STAMP(8);
       mbar_wait(qbar, 0);   // the Q tile is staged (and visible to the tensor core)
       PF_STAMP(9);
       for (int i = 0; i < n; ++i) {
