@@ -226,6 +226,55 @@ __global__ void __launch_bounds__(128) schedule_moves_kernel(
                          occ, wid, lane, g);
 }
 
+// one CTA per head (few heads, thousands of evictions each: post-prefill compression).  No window bitmaps and no
+// binary searches: with the evicted tail entries T_0 > T_1 > ... (E read backwards, T_{-1} = n, and the sentinel
+// new_n - 1 after the last one), the survivors between T_{i-1} and T_i have exactly i evicted positions above them,
+// so the survivor at position pos is move number k = (n - 1 - pos) - i.  A thread takes the gaps i = tid, tid + 256,
+// ...: two coalesced reads of E per gap, and work only where a gap is not empty.
+template <int B>
+__global__ void __launch_bounds__(256) schedule_moves_cta_kernel(
+    int* __restrict__ cache_moves_idx, int* __restrict__ cache_moves_count,
+    const int* __restrict__ evicted_logical_indices, const int* __restrict__ evicted_kv_count,
+    const int* __restrict__ evicted_kv_offsets, const int* __restrict__ block_tables,
+    const int* __restrict__ context_lens, int num_seqs, int num_layers, int num_kv_heads, int MB) {
+  __shared__ int s_m;
+  const int g = blockIdx.x, t = threadIdx.x;
+  const int s = g / (num_layers * num_kv_heads);
+  const int l = (g / num_kv_heads) % num_layers;
+  const int h = g % num_kv_heads;
+  const int lsh = (l * num_seqs + s) * num_kv_heads + h;
+  const int* __restrict__ bt = block_tables + (int64_t)lsh * MB;
+  const int n = context_lens[lsh];
+  const int c = evicted_kv_count[g];
+  const int off = evicted_kv_offsets[g];
+  const int* __restrict__ E = evicted_logical_indices + off;
+  const int new_n = n - c;
+  if (t == 0) s_m = 0;
+  __syncthreads();
+  // m = |E ∩ [0, new_n)|
+  int cnt = 0;
+  for (int j = t; j < c; j += 256) cnt += E[j] < new_n;
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+  if ((t & 31) == 0 && cnt) atomicAdd(&s_m, cnt);
+  __syncthreads();
+  const int m = s_m;
+  if (t == 0) cache_moves_count[g] = m;
+  if (m == 0) return;
+  const int ngaps = c - m + 1;   // gap i lies below the i-th largest evicted tail entry
+  for (int i = t; i < ngaps; i += 256) {
+    const int hi = (i == 0) ? n : E[c - i];                    // exclusive
+    const int lo = (i == c - m) ? new_n - 1 : E[c - 1 - i];    // exclusive
+    for (int pos = hi - 1; pos > lo; --pos) {
+      const int k = (n - 1 - pos) - i;
+      const int dst = E[k];
+      const int src_phys = bt[pos / B] * B + pos % B;
+      const int dst_phys = bt[dst / B] * B + dst % B;
+      reinterpret_cast<int2*>(cache_moves_idx)[(int64_t)off + k] = make_int2(dst_phys, src_phys);
+    }
+  }
+}
+
 // many heads with 0 or 1 evicted slot each (decode-time continual compression): a warp looks at 32 heads, every
 // lane settles its own head when c <= 1 (closed form: the one evicted index E0 takes the last token unless it
 // IS the last token), the heads with longer lists are then done by the whole warp one after the other
@@ -714,9 +763,16 @@ extern "C" int kvc_schedule_t1_cache_moves(
   if (total <= 0) return KVC_OK;
   const bool many = total >= 4096;  // decode-time batches: 32 heads per warp
   const dim3 grid(many ? ceil_div(ceil_div(total, 32), 4) : ceil_div(total, 4)), block(128);
+  // few heads whose lists can be long (post-prefill compression): one CTA per head
+  const bool long_lists = !many && (int64_t)max_num_blocks_per_seq * block_size > 512;
   cudaStream_t st = as_stream(stream);
 #define KVC_LAUNCH_K4(BS)                                                              \
-  if (many)                                                                            \
+  if (long_lists)                                                                      \
+    schedule_moves_cta_kernel<BS><<<total, 256, 0, st>>>(                              \
+        cache_moves_idx, cache_moves_count, evicted_logical_indices, evicted_kv_count, \
+        evicted_kv_offsets, block_tables, context_lens, num_seqs, num_layers,          \
+        num_kv_heads, max_num_blocks_per_seq);                                         \
+  else if (many)                                                                       \
     schedule_moves_many_kernel<BS><<<grid, block, 0, st>>>(                            \
         cache_moves_idx, cache_moves_count, evicted_logical_indices, evicted_kv_count, \
         evicted_kv_offsets, block_tables, context_lens, num_seqs, num_layers,          \
