@@ -590,6 +590,57 @@ def test_k2_k3_vs_reference_cuda(capi, ref_ops):
         assert torch.equal(rc, gc) and torch.equal(rl, gl)
 
 
+@pytest.mark.parametrize("lens", [[53, 16, 7, 130, 32], [300, 53, 16, 7, 130, 32, 411, 1]])
+@pytest.mark.parametrize("bf16", [False, True])
+def test_k6_prefill_blocks_vs_reference_cuda(capi, ref_ops, O, bf16, lens):
+    """K6 on a prefill batch: every head's prompt tokens fill randomly placed blocks in order, so most (16 tokens,
+    head) groups are whole blocks (the warp of the block's first token writes all 4 KB) next to
+    partial tail blocks, prompts that do not start on a multiple of 16 in the batch, a padding token and a
+    re-directed slot inside what would otherwise be whole blocks.  Against the reference's CUDA kernel and the C
+    oracle, on strided views of one QKV tensor, in both launch geometries (batches of >= 512 tokens take one warp per
+    16-token window)."""
+    rng = np.random.RandomState(99)
+    H, D, B, x = 8, 128, 16, 8
+    T = sum(lens)   # 238 tokens: one warp per (token, head); 950 tokens: one warp per (16-token window, head)
+    dt = torch.bfloat16 if bf16 else torch.float16
+    qkv = (torch.rand((T, (4 * H + 2 * H) * D), device="cuda") - 0.5).to(dt)
+    key = qkv[:, 4 * H * D: 5 * H * D].view(T, H, D)
+    val = qkv[:, 5 * H * D:].view(T, H, D)
+    nblk = [(n + B - 1) // B for n in lens]
+    NB = H * sum(nblk) + 5
+    perm = rng.permutation(NB)
+    slots = np.empty((T, H), np.int64)
+    t0 = b0 = 0
+    for n, nb in zip(lens, nblk):
+        blocks = perm[b0:b0 + H * nb].reshape(H, nb)
+        tok = np.arange(n)
+        slots[t0:t0 + n] = (blocks[:, tok // B] * B + tok % B).T
+        t0 += n
+        b0 += H * nb
+    slots[60, 2] = -1                       # padding token inside a whole block of head 2
+    slots[100, 5] = perm[-1] * B + 3        # one token of head 5 goes elsewhere: its block is not a whole one
+    slots[20, :] = -1
+    kc = (torch.rand((NB, D // x, B, x), device="cuda") - 0.5).to(dt)
+    vc = (torch.rand((NB, D, B), device="cuda") - 0.5).to(dt)
+    m = torch.rand((NB, B), device="cuda")
+    bias = torch.rand(H, device="cuda")
+    sl = torch.from_numpy(slots).cuda()
+    r = (kc.clone(), vc.clone(), m.clone())
+    g = (kc.clone(), vc.clone(), m.clone())
+    ref_ops.kvcompress_reshape_and_cache(key, val, r[0], r[1], r[2], sl.view(-1), bias, "auto", 1.0, 1.0)
+    capi.reshape_and_cache(key, val, g[0], g[1], g[2], sl, bias)
+    torch.cuda.synchronize()
+    for a_, b_ in zip(r, g):
+        assert torch.equal(a_.view(torch.int16) if a_.dtype != torch.float32 else a_,
+                           b_.view(torch.int16) if b_.dtype != torch.float32 else b_)
+    bits = lambda t_: t_.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+    wk, wv, wm = bits(kc), bits(vc), m.cpu().numpy().copy()
+    O.reshape_and_cache_kvc(bits(key), bits(val), wk, wv, wm, slots, bias.cpu().numpy())
+    np.testing.assert_array_equal(bits(g[0]), wk)
+    np.testing.assert_array_equal(bits(g[1]), wv)
+    np.testing.assert_array_equal(g[2].cpu().numpy(), wm)
+
+
 @pytest.mark.parametrize("bf16", [False, True])
 def test_k6_vs_reference_cuda(capi, ref_ops, bf16):
     """kvcompress_reshape_and_cache (K6) kernel-vs-kernel against the reference's CUDA kernel
