@@ -523,6 +523,35 @@ extern "C" int kvc_alloc_add_sequences(
   return KVC_OK;
 }
 
+// the same with one WARP per head (few heads that free hundreds of blocks each: the compression right after a
+// prefill; the thread-per-head form above would walk 367 blocks serially in each of 1024 threads)
+__global__ void __launch_bounds__(256) alloc_free_compressed_warp_kernel(
+    uint8_t* free_mask, int* free_count, const int* block_tables, int* context_lens,
+    const int* evicted_block_count, const int* seq_slots, int* seq_index_by_block, int num_batch, int max_seqs,
+    int L, int H, int MB, int B) {
+  const int g = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (g >= num_batch * L * H) return;
+  const int k = evicted_block_count[g];
+  if (k <= 0) return;
+  const int h = g % H, l = (g / H) % L, sb = g / (L * H);
+  const int slot = seq_slots ? seq_slots[sb] : sb;
+  const int lsh = (l * max_seqs + slot) * H + h;
+  const int ctx = context_lens[lsh];
+  const int nblk = (ctx + B - 1) / B;   // block.py:337-355, 367-379: the last k allocated blocks
+  const int* bt = block_tables + (int64_t)lsh * MB;
+  for (int j = max(nblk - k, 0) + lane; j < nblk; j += 32) {
+    const int blk = bt[j];
+    free_mask[blk] = 1;
+    if (seq_index_by_block) seq_index_by_block[blk] = -1;   // metrics.py:364-370
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const int hanging = (ctx % B) ? (ctx % B) : B;            // block.py:330-335
+    context_lens[lsh] = ctx - max(k * B - (B - hanging), 0);  // block.py:184-210
+    atomicAdd(free_count, min(k, nblk));
+  }
+}
+
 extern "C" int kvc_alloc_free_compressed(uint8_t* free_mask, int* free_count, const int* block_tables,
                                          int* context_lens, const int* evicted_block_count, const int* seq_slots,
                                          int* seq_index_by_block, int num_batch, int max_seqs, int num_layers,
@@ -534,6 +563,13 @@ extern "C" int kvc_alloc_free_compressed(uint8_t* free_mask, int* free_count, co
               KVC_ERR_INVALID, "alloc_free_compressed: bad sizes");
   if (num_batch == 0) return KVC_OK;
   const int heads = num_batch * num_layers * num_kv_heads;
+  if (heads < 16384) {   // post-prefill calls: long per-head lists
+    alloc_free_compressed_warp_kernel<<<(heads + 7) / 8, 256, 0, as_stream(stream)>>>(
+        free_mask, free_count, block_tables, context_lens, evicted_block_count, seq_slots, seq_index_by_block,
+        num_batch, max_seqs, num_layers, num_kv_heads, max_num_blocks_per_seq, block_size);
+    KVC_CHECK_LAUNCH("alloc_free_compressed_warp_kernel");
+    return KVC_OK;
+  }
   alloc_free_compressed_kernel<<<(heads + 255) / 256, 256, 0, as_stream(stream)>>>(
       free_mask, free_count, block_tables, context_lens, evicted_block_count, seq_slots, seq_index_by_block,
       num_batch, max_seqs, num_layers, num_kv_heads, max_num_blocks_per_seq, block_size);
