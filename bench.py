@@ -494,6 +494,16 @@ def main():
             line["prefill_kv_metrics"] = prefill_metrics_bench(device)
         except Exception as ex:  # pragma: no cover
             line["prefill_kv_metrics"] = {"error": repr(ex)}
+        try:
+            # the other KV-Compress ops around a prefill: the per-head cache write of 4 x 6000-token prompts and the
+            # allocator calls of the compression that follows it (tools/k6_bench.py, tools/alloc_bench.py)
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import alloc_bench
+            import k6_bench
+            line["prefill_cache_write"] = k6_bench.run(device, [6000] * 4)
+            line["allocator_post_prefill"] = alloc_bench.measure()
+        except Exception as ex:  # pragma: no cover
+            line["prefill_cache_write"] = {"error": repr(ex)}
     if not args.no_reference_cuda and world == 1 and args.model == "llama3-8b":
         # the fork's own CUDA kernels (unmodified .cu files rebuilt for sm_100a, oracle/_ref) driving the same
         # step in the fork's op order: the "reference fork's own decode tokens/s on the same box" (north_star).

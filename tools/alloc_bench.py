@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 
-def main():
+def measure():
     from vllm_kvcompress_b200 import capi
     dev = "cuda"
     L, H, B, MS, n_seq, P = 32, 8, 16, 8, 4, 6000
@@ -42,8 +42,8 @@ def main():
         timed("remove_sequences_ms", lambda: al.remove_sequences(slots))
     res["blocks_allocated"] = n_seq * L * H * ((P + B - 1) // B)
     res["num_blocks"] = NB
-    print(json.dumps(res))
+    return res
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(measure()))
