@@ -1643,8 +1643,8 @@ extern "C" int kvc_select_evictions_ex(
         if (e != cudaSuccess) { (void)cudaGetLastError(); per_sm = 0; }
       }
       if (per_sm > 0 && (int64_t)per_sm * sm_count() >= total) {
-        const char* sa = getenv("KVC_SELECT_STOP_AFTER");
-        int stop_after = sa ? atoi(sa) : 0;
+        static const int stop_env = [] { const char* sa = getenv("KVC_SELECT_STOP_AFTER"); return sa ? atoi(sa) : 0; }();
+        int stop_after = stop_env;
         void* args[] = {&p, &rw, &stop_after};
         e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(select_radix_fused_kernel), dim3(total), dim3(256),
                                         args, smem_keys, st);
