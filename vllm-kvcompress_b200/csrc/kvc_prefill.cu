@@ -12,20 +12,23 @@
 // This is the one dense contraction of the path that is not a single-query product: per KV head
 // the GQA group's Q x n_obs query rows form a 128-row operand, so one UMMA tile
 //   S[128 rows x 128 keys] = Qtile[128 x D=128] . Ktile[128 x 128]^T
-// is issued as 8 tcgen05.mma (M=128, N=128, K=16, fp16/bf16 in, fp32 accumulators in TMEM) by one
-// thread; the four warps read their 32 TMEM lanes back with tcgen05.ld (one thread = one query
-// row, so the row max / row sum of the softmax need no shuffles).  Softmax needs the row
-// statistics over ALL keys before a probability can be squared, so the work is two sweeps:
+// is issued as 8 tcgen05.mma (M=128, N=128, K=16, fp16/bf16 in, fp32 accumulators in TMEM).  Softmax needs the
+// row statistics over ALL keys before a probability can be squared, so the work is two sweeps:
 //   pass 1 (stats):   per (sequence, kv head, 128-row tile, key split): running (max, sum exp)
-//   pass 2 (metrics): merge the splits' statistics, recompute S, p = exp(s - M) / L, p^2, mask,
+//   pass 2 (metrics): merge the splits' statistics, recompute S, p^2 = ex2(2 (s - M) log2 e) / L^2, mask,
 //                     column sums per query head by a warp reduce-scatter (31 shuffles per 32 keys)
 //   finalize:         max-pool 7 + [T, Hq] output (+ fused aggregate_prefill)
-// K tiles are re-read from L2 in pass 2 (a prompt's keys of one head: P x 256 B).  Both operands
-// are staged in shared memory in the canonical no-swizzle K-major core-matrix layout
-// (8 rows x 16 B contiguous; LBO = 2048 B between K-adjacent cores, SBO = 128 B between row-adjacent
-// cores -- the descriptor convention verified on the B200 by tools/tcgen05_probe.cu); the K tile
-// and the TMEM accumulator are double-buffered so the MMAs of tile t+1 run under the softmax
-// epilogue of tile t.
+// A CTA is warp-specialised.  The control thread (warp 8, lane 0) brings the operands in with TMA
+// (cp.async.bulk.tensor.2d through tensor maps over the caller's [T, Hq*D] query and [T, H*D] key tensors, built
+// per call from their strides; a tile = two 128-byte-swizzled boxes of [rows x 64 d], the layout the K-major
+// SWIZZLE_128B shared-memory descriptors expect: 8-row atoms of 1024 B, a K step of 16 elements = +32 B), keeps
+// two K tiles in flight, and issues the MMAs of tile i+1 into the other TMEM accumulator while the eight epilogue
+// warps work on tile i; a K buffer is requested again as soon as tcgen05.commit reports its MMAs complete.
+// Epilogue warps w and w + 4 share TMEM lane quarter w & 3 (tcgen05.ld.32x32b.x32: one thread = one query row,
+// so the row max / row sum of the softmax need no shuffles) and split a tile's columns.  All hand-offs are
+// mbarriers (transaction barriers for the copies, tcgen05.commit for the MMAs, an arrival count of 8 for a
+// drained accumulator); the loop has no CTA-wide barrier.  The key splits are sized so that the grid is one wave
+// of 2 CTAs per SM; pass 2 and the finalisation are launched as programmatic dependents.
 //
 // Arithmetic mirrors the reference: the fp16/bf16 einsum result is rounded to the input type before
 // the fp32 scale (flash_attn.py:1178: `scale * einsum(...).float()`), softmax / squares / sums fp32.
@@ -72,16 +75,6 @@ __device__ __forceinline__ void pf_stamp(unsigned long long* trace, int pass, in
 #else
 #define PF_STAMP(slot) do {} while (0)
 #endif
-
-// shared-memory matrix descriptor, no swizzle, K-major (tools/tcgen05_probe.cu)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-  d |= 1ull << 46;  // sm_100 descriptor version
-  return d;
-}
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
