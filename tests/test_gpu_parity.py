@@ -1119,6 +1119,65 @@ def test_execute_moves_many_heads_small_counts_vs_oracle(capi, O, deferred, full
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def test_k4_few_heads_long_lists_vs_oracle(capi, O):
+    """schedule_t1_cache_moves at the post-prefill shape (few heads, block tables of more than 512 slots: one CTA
+    per head over the gaps of the evicted tail): counts and (dst, src) pairs bit-exact against the C oracle for
+    eviction patterns that make the gaps degenerate -- nothing evicted, everything evicted, only the oldest / only
+    the newest tokens evicted (one gap holds every survivor), every other token, and random sets at CR 64 ... 1.3."""
+    rs = np.random.RandomState(77)
+    S, L, H, B, MB = 2, 3, 8, 16, 130            # 48 heads, up to 2080 slots each
+    ctx = rs.randint(600, MB * B + 1, size=(L, S, H)).astype(np.int32)
+    ctx[0, 0, 0] = MB * B                        # a full table
+    ctx[1, 1, 3] = 1                             # and a single token
+    nblk = (ctx + B - 1) // B
+    NB = int(nblk.sum()) + 5
+    perm = rs.permutation(NB).astype(np.int32)
+    bt = np.zeros((L, S, H, MB), np.int32)
+    k = 0
+    for idx in np.ndindex(L, S, H):
+        n = int(nblk[idx])
+        bt[idx][:n] = perm[k:k + n]
+        k += n
+    ctx_slh = ctx.transpose(1, 0, 2)
+    alloc = (nblk.transpose(1, 0, 2) * B).reshape(-1)
+    offs = np.concatenate([[0], np.cumsum(alloc)[:-1]]).astype(np.int32).reshape(S, L, H)
+    N = int(alloc.sum())
+    cnt = np.zeros((S, L, H), np.int32)
+    elog = np.full(N, MAX_INT, np.int32)
+    for i, idx in enumerate(np.ndindex(S, L, H)):
+        n = int(ctx_slh[idx])
+        kind = i % 8
+        if kind == 0:
+            ev = np.arange(0)                                 # nothing
+        elif kind == 1:
+            ev = np.arange(n)                                 # everything
+        elif kind == 2:
+            ev = np.arange(n - n // 3)                        # the oldest two thirds: survivors are all in the tail
+        elif kind == 3:
+            ev = np.arange(n // 4, n)                         # the newest three quarters: no move at all
+        elif kind == 4:
+            ev = np.arange(0, n, 2)                           # every other token
+        else:
+            keep = max(1, int(n / [64, 8, 1.3][kind - 5]))
+            ev = np.sort(rs.choice(n, size=n - keep, replace=False))
+        cnt[idx] = len(ev)
+        elog[offs[idx]:offs[idx] + len(ev)] = ev
+    wm = np.zeros((N, 2), np.int32)
+    wc = np.zeros((S, L, H), np.int32)
+    O.schedule_cache_moves(wm, wc, elog, cnt, offs, bt, ctx, B)
+    moves = torch.zeros((N, 2), dtype=torch.int32, device="cuda")
+    mcnt = torch.full((S, L, H), -3, dtype=torch.int32, device="cuda")
+    capi.schedule_t1_cache_moves(moves, mcnt, cu(elog), cu(cnt), cu(offs), cu(bt), cu(ctx), B)
+    got_c, got_m = mcnt.cpu().numpy(), moves.cpu().numpy()
+    np.testing.assert_array_equal(got_c, wc)
+    valid = np.zeros(N, bool)
+    for o, c in zip(offs.reshape(-1), wc.reshape(-1)):
+        valid[o:o + c] = True
+    np.testing.assert_array_equal(got_m[valid], wm[valid])
+    assert (got_m[~valid] == 0).all()
+    assert int(wc.sum()) > 5000 and int((wc == 0).sum()) >= 12
+
+
 def test_k4_many_heads_short_lists_vs_oracle(capi, O):
     """schedule_t1_cache_moves at decode-time shape (>= 4096 heads: 32 heads per warp, heads with at most one
     evicted slot settled by their own lane, longer lists by the whole warp): counts and (dst, src) pairs
