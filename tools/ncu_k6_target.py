@@ -1,3 +1,5 @@
+"""ncu target: one prefill-scale K6 call (4 x 6000-token prompts) and three post-prefill K4 calls (profiles/README.md).
+python tools/ncu_k6_target.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

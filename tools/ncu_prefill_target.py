@@ -1,3 +1,5 @@
+"""ncu target: a few prefill_kv_metrics calls on n prompts of L tokens (profiles/README.md).
+python tools/ncu_prefill_target.py 4 6000"""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
