@@ -744,6 +744,7 @@ def selection_case(seed, S, L, H, B, max_blocks, prot, frac):
 @pytest.mark.parametrize("cfg", [
     (71, 3, 2, 2, 4, 5, 3, 0.5),
     (72, 4, 4, 8, 16, 10, 16, 0.4),      # <= 256 slots per head: warp-per-head path
+    (79, 4, 4, 8, 16, 14, 16, 0.4),      # 193..256 slots per head
     (77, 3, 4, 8, 16, 28, 32, 0.6),      # 257..512 slots per head: warp path with 16 keys per lane
     (73, 2, 4, 8, 16, 40, 32, 0.7),      # > 512 slots per head: CTA-per-head sort path
     (78, 2, 1, 3, 16, 380, 32, 0.95),    # post-prefill-like: ~6000 slots per head, CR ~ 20
