@@ -192,6 +192,10 @@ KVC_API int kvc_execute_cache_moves(
  *   slot_mapping [T, H] int64 (<0 = padding)
  *   kv_metric_head_bias [H] f32: metric of every written slot is set to it.
  * kv_cache_dtype "auto" only (dtype = element type of key AND cache).
+ * Batches of >= 512 tokens in the production layout (fp16 / bf16, D = 128, B = 16, x = 8) are
+ * written block-wise: 16 batch tokens of a head that map to the 16 slots of one block in order
+ * become one 4 KB block write (V transposed in shared memory); everything else, and every other
+ * shape, goes element-wise like the reference.  Same bytes in the cache either way.
  * ------------------------------------------------------------------------- */
 KVC_API int kvc_reshape_and_cache(
     const void* key, const void* value, void* key_cache, void* value_cache,
@@ -492,8 +496,13 @@ KVC_API int kvc_free_and_append_slots(
  *   query [T, Hq, D], key [T, H, D] (NOT repeated per query head), token strides in elements
  *   seq_start_loc [num_seqs+1], kv_metric_buffer_len [num_seqs]; max_prompt_len (host int)
  * The QK product is rounded to the input type before the fp32 scale exactly as the reference's
- * fp16/bf16 einsum is (flash_attn.py:1178).  head_size 128, F16/BF16, n_observed <= 128
- * (single observation chunk: the reference default max_observed_block_size is 4096).
+ * fp16/bf16 einsum is (flash_attn.py:1178).  head_size 128, F16/BF16, n_observed <= 4096 (one
+ * observation chunk: the reference default max_observed_block_size).
+ * query / key are read through TMA tensor maps built per call from the pointers and token
+ * strides (so they may be views of a fused qkv projection output): both must be 16-byte
+ * aligned with token strides that are multiples of 8 elements, heads contiguous within a token.
+ * Three launches (row statistics, squared-probability column sums, max-pool + aggregation),
+ * the last two as programmatic dependents of their predecessor.
  * ------------------------------------------------------------------------- */
 KVC_API size_t kvc_prefill_kv_metrics_workspace_bytes(
     int num_tokens, int num_seqs, int num_heads, int num_kv_heads,
